@@ -1,0 +1,137 @@
+/*
+ * vr_oracle.h -- CPU restatement of the reference ray caster.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is the parity oracle for the B200 port of MitchellHansen/voxel-raycaster's per-pixel
+ * ray casting hot path.  It restates, function by function, `kernels/ray_caster_kernel.cl`
+ * (the OpenCL kernel) and the host-side input producers `CLCaster::create_viewport`
+ * (src/CLCaster.cpp:233-299) and `Octree::GenerationRecursion` (src/map/Octree.cpp:171-323).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  Nothing under voxel-raycaster_b200/ links, imports or executes it.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden images or known-answer vectors for this
+ * path and cannot be compiled here (no OpenCL runtime, SFML or GL in the
+ * image), so this restatement cannot be checked against reference-owned fixtures.  What pins it:
+ *   - the derived known answers listed in tests/test_oracle.py (HEAD 16^3 octree: 585 descriptors,
+ *     root index 99415; hand-computed rays in tiny maps; Octree::Validate's occupancy property),
+ *   - line-against-line review with the kernel (every function cites the kernel lines it follows).
+ *
+ * OpenCL built-ins whose results are implementation-defined in the reference (it is built with
+ * -cl-fast-relaxed-math, src/CLCaster.cpp:771) are pinned here to IEEE-754 binary32:
+ *   normalize(v) = v / sqrtf(dot(v,v));  fast_length = sqrtf(dot);  dot = (x*x' + y*y') + z*z';
+ *   pow(x, 1.0f) = x;  mix(a,b,t) = a + (b-a)*t;  max(x,y) = (x < y) ? y : x;
+ *   convert_int(float) truncates toward zero;  write_imagef = rint(clamp(c*255, 0, 255)) (RTE);
+ *   sin/cos of the camera angles = host sinf/cosf, passed in precomputed (they are frame-uniform).
+ * No FMA contraction: compile with -ffp-contract=off -fno-fast-math.
+ */
+#ifndef VR_ORACLE_H
+#define VR_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Everything the kernel reads (kernel:256-273), in host memory. */
+typedef struct vro_scene {
+    /* viewport */
+    int32_t width, height;              /* viewport_resolution (kernel arg 2)                    */
+    const float *ray_table;             /* viewport_matrix, float4 stride, W*H entries (arg 3)   */
+    /* dense map (args 0,1) */
+    const int8_t *map;                  /* char map[x + X*(y + Z*z)]                              */
+    int32_t map_dim[3];
+    /* camera (args 4,5) */
+    float cam_dir[2];                   /* (inclination, azimuth)                                 */
+    float cam_pos[3];
+    float trig[4];                      /* sin(dir.x), cos(dir.x), sin(dir.y), cos(dir.y)         */
+    /* lights (args 6,7): 10 floats each {r,g,b,i,x,y,z,dx,dy,dz}; only light 0 is read           */
+    const float *lights;
+    int32_t light_count;
+    /* atlas (args 9,10,11): RGBA8 */
+    const uint8_t *atlas;
+    int32_t atlas_dim[2];
+    int32_t tile_dim[2];
+    /* octree (args 12-14) -- may be NULL: then get_oct_vox's start bias is 0 */
+    const uint64_t *oct_desc;
+    uint64_t oct_desc_len;
+    /* settings (arg 15) */
+    int64_t octdim;                     /* setting(OCTDIM)                                        */
+    int64_t oct_root_index;             /* setting(OCTREE_ROOT_INDEX)                             */
+    /* kernel:326 -- HEAD hard-codes 20; lifted into a parameter                                  */
+    int32_t max_distance;
+    /* extension beyond the reference: number of shadow lights, 1 = reference      */
+    int32_t shadow_lights;
+} vro_scene;
+
+/* Per-pixel auxiliary record, 32 bytes.  The reference kernel only writes RGBA8; these expose
+ * the integer state the parity tests compare bit-exactly. */
+typedef struct vro_aux {
+    int32_t hit[3];          /* first voxel hit by the primary ray (type 5 or 6); -1,-1,-1 if none */
+    uint8_t face;            /* bits0-2 face_mask x/y/z at first hit; bits 3-5 voxel_step<0 per axis */
+    uint8_t status;          /* VRO_ST_* terminal event                                             */
+    uint8_t flags;           /* VRO_FL_*                                                            */
+    uint8_t hit_type;        /* voxel value at first hit (5 / 6), 0 if none                         */
+    uint32_t steps_first;    /* distance_traveled when the first hit happened                       */
+    uint32_t steps_total;    /* distance_traveled at termination                                    */
+    uint32_t pad[2];
+} vro_aux;
+
+enum {
+    VRO_ST_SKIP_PRIMARY = 0,   /* kernel:293  zero component in the rotated ray: pixel not written   */
+    VRO_ST_OOB          = 1,   /* kernel:563  ray left the map                                       */
+    VRO_ST_MAXDIST      = 2,   /* kernel:357  distance_traveled reached max_distance                 */
+    VRO_ST_SHADOW_HIT   = 3,   /* kernel:706  shadow ray (or any ray while shadow_ray) hit 5/6       */
+    VRO_ST_SKIP_REDIRECT= 4,   /* kernel:671/694 zero component after redirect: pixel not written    */
+    VRO_ST_BOUNCES      = 5    /* kernel:357  bounce_count reached 2                                 */
+};
+enum {
+    VRO_FL_LIT       = 1,      /* a type-5 primary hit happened (shadow ray spawned)                  */
+    VRO_FL_REFLECTED = 2,      /* at least one type-6 reflection                                     */
+    VRO_FL_TIE       = 4,      /* some DDA step moved along more than one axis (exact t tie)         */
+    VRO_FL_ATLAS_CLAMP = 8,    /* atlas texel coordinate fell outside the image and was clamped      */
+    VRO_FL_FRAC0     = 16      /* a camera position component is an exact integer                    */
+};
+
+/* Whole-frame counters (SURVEY 8d byte model). */
+typedef struct vro_counters {
+    uint64_t pixels;
+    uint64_t pixels_written;
+    uint64_t primary_rays;     /* pixels that entered the loop                                       */
+    uint64_t shadow_rays;      /* shadow redirects                                                   */
+    uint64_t reflect_rays;
+    uint64_t dda_steps;        /* S_dense: loop iterations that loaded map[]                         */
+    uint64_t texel_fetches;    /* T                                                                  */
+    uint64_t svo_desc_fetches; /* D_svo: canonical descent fetches (only if counted)                 */
+    uint64_t svo_cell_changes;
+    uint64_t tie_pixels;
+} vro_counters;
+
+/* create_viewport's ray table (src/CLCaster.cpp:233-299).  out: W*H float4. */
+void vro_make_ray_table(int width, int height, float *out);
+
+/* raycaster kernel, dense branch (kernel:256-724 with setting(OCTENABLED) != 0), rows y0, y0+row_stride,
+ * ... < y1 (row_stride > 1 is the bounded sample used for CPU-baseline timing and byte counting).
+ * rgba must be pre-filled by the caller (skipped pixels keep their contents, kernel:293).
+ * aux / counters may be NULL.  count_svo != 0 additionally walks the reference-format octree to
+ * count canonical descriptor fetches (needs oct_desc).  Returns 0 on success. */
+int vro_raycast(const vro_scene *s, int y0, int y1, int row_stride, uint8_t *rgba, vro_aux *aux,
+                vro_counters *counters, int count_svo, int num_threads);
+
+/* get_oct_vox (kernel:140-251) at one position: writes found, sub_oct_pos[3], resolution, scale. */
+void vro_get_oct_vox(const uint64_t *desc, int64_t root_index, int64_t octdim, const int32_t pos[3],
+                     int32_t *found, int32_t sub_oct_pos[3], int32_t *resolution, int32_t *scale);
+
+/* Octree::Generate + GenerationRecursion (src/map/Octree.cpp:13-43,171-323) into a caller buffer of
+ * buffer_size entries (reference: 100000), written from the top down.  Returns the root index, or
+ * -1 if the buffer is too small (the reference has no such check).  *used = descriptors written. */
+int64_t vro_octree_generate(const int8_t *data, int dim, uint64_t *buffer, uint64_t buffer_size,
+                            uint64_t *used);
+
+int vro_num_procs(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

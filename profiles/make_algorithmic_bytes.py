@@ -1,0 +1,60 @@
+"""Computes the ALGORITHMIC bytes per frame of a bench workload from the oracle's counters
+(SURVEY.md 8d / DESIGN.md "byte model"):
+
+    B = P*(16 + 4) + 8*D_svo + 4*T            (SVO mode)
+    B = P*(16 + 4) + 1*S_dense + 4*T          (dense mode)
+
+P pixels (16 B ray-table read + 4 B RGBA8 store), D_svo child-descriptor fetches of the canonical
+stack-based descent of the reference-format octree, S_dense DDA steps (1 B map load each), T atlas texel
+fetches.  Counted on every `--row-stride`-th row and scaled; the result is committed as
+profiles/algorithmic_bytes_<config>.json and read by bench.py (the oracle is NOT run inside the timed
+benchmark for this).
+
+    python profiles/make_algorithmic_bytes.py --config c3 --row-stride 8
+"""
+import argparse
+import importlib
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle_lib as O  # noqa: E402
+
+pkg = importlib.import_module("voxel-raycaster_b200")
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="c3")
+ap.add_argument("--row-stride", type=int, default=8)
+args = ap.parse_args()
+
+scene = bench.bench_scene(args.config)
+t0 = time.time()
+desc, root = pkg.octree_generate(scene.volume)
+print(f"reference-format octree: {desc.size} descriptors ({desc.nbytes / 1e6:.1f} MB) in {time.time() - t0:.1f} s")
+t0 = time.time()
+_, aux, cnt = O.raycast(scene, octree=(desc, root), want_counters=True, count_svo=True, row_stride=args.row_stride)
+print(f"oracle counters over 1/{args.row_stride} of the rows in {time.time() - t0:.1f} s: {cnt}")
+k = scene.height * scene.width / cnt["pixels"]
+P = scene.width * scene.height
+out = {
+    "config": args.config, "scene": scene.name, "width": scene.width, "height": scene.height, "n": scene.n,
+    "camera_pos": [float(v) for v in scene.cam_pos], "camera_dir": [float(v) for v in scene.cam_dir],
+    "max_distance": scene.max_distance, "row_stride": args.row_stride, "sample_pixels": cnt["pixels"],
+    "pixels": P,
+    "primary_rays": cnt["primary_rays"] * k, "shadow_rays": cnt["shadow_rays"] * k, "reflect_rays": cnt["reflect_rays"] * k,
+    "dda_steps": cnt["dda_steps"] * k, "texel_fetches": cnt["texel_fetches"] * k,
+    "svo_desc_fetches": cnt["svo_desc_fetches"] * k, "svo_cell_changes": cnt["svo_cell_changes"] * k,
+    "tie_pixels": cnt["tie_pixels"] * k,
+    "ref_octree_descriptors": int(desc.size),
+}
+out["bytes_svo"] = P * 20 + 8 * out["svo_desc_fetches"] + 4 * out["texel_fetches"]
+out["bytes_dense"] = P * 20 + 1 * out["dda_steps"] + 4 * out["texel_fetches"]
+out["rays"] = out["primary_rays"] + out["shadow_rays"] + out["reflect_rays"]
+path = ROOT / "profiles" / f"algorithmic_bytes_{args.config}.json"
+path.write_text(json.dumps(out, indent=1) + "\n")
+print(json.dumps(out, indent=1))

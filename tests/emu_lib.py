@@ -1,0 +1,45 @@
+"""ctypes wrapper of tests/host_emu/libvremu.so: the device core compiled for the host.  TEST INFRASTRUCTURE."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+EMU_DIR = Path(__file__).resolve().parent / "host_emu"
+_lib = None
+AUX_DTYPE = np.dtype([
+    ("hit", "<i4", (3,)), ("face", "u1"), ("status", "u1"), ("flags", "u1"), ("hit_type", "u1"),
+    ("steps_first", "<u4"), ("steps_total", "<u4"), ("node_fetches", "<u4"), ("lookups", "<u4"),
+])
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", str(EMU_DIR)], check=True, capture_output=True)
+        _lib = C.CDLL(str(EMU_DIR / "libvremu.so"))
+        _lib.emu_raycast.restype = C.c_int
+    return _lib
+
+
+def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False, max_distance: int | None = None):
+    w, h = scene.width, scene.height
+    vol = np.ascontiguousarray(scene.volume, dtype=np.int8)
+    lights = np.ascontiguousarray(scene.lights, dtype=np.float32)
+    atlas = np.ascontiguousarray(scene.atlas, dtype=np.uint8)
+    rgba = np.empty((h, w, 4), dtype=np.uint8)
+    rgba[...] = (255, 255, 255, 100)
+    aux = np.zeros((h, w), dtype=AUX_DTYPE)
+    b = (C.c_int32 * 3)(*[int(v) for v in bias])
+    fp = C.POINTER(C.c_float)
+    rc = lib().emu_raycast(
+        C.c_int(w), C.c_int(h), ray_table.ctypes.data_as(fp), vol.ctypes.data_as(C.c_void_p), C.c_int(scene.n),
+        scene.cam_pos.ctypes.data_as(fp), scene.cam_dir.ctypes.data_as(fp), b, lights.ctypes.data_as(fp),
+        atlas.ctypes.data_as(C.c_void_p), C.c_int(atlas.shape[1]), C.c_int(atlas.shape[0]), C.c_int(scene.tile), C.c_int(scene.tile),
+        C.c_int(scene.max_distance if max_distance is None else max_distance), C.c_int(int(use_svo)),
+        rgba.ctypes.data_as(C.c_void_p), aux.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"emu_raycast failed: {rc}")
+    return rgba, aux

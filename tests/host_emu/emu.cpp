@@ -1,0 +1,56 @@
+/*
+ * emu.cpp -- TEST INFRASTRUCTURE: compiles the device core (voxel-raycaster_b200/csrc/vr_trace.h) for
+ * the host so its control flow can be single-stepped against the oracle without a GPU.  The product
+ * never loads this file; it exists because a gpurun round-trip takes minutes.
+ */
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+#include "../../voxel-raycaster_b200/csrc/vr_trace.h"
+#include "../../voxel-raycaster_b200/csrc/vr_octree.h"
+
+struct LocalStack {
+    uint32_t v[VR_MAX_LEVELS];
+    void set(int l, uint32_t x) { v[l] = x; }
+    uint32_t get(int l) const { return v[l]; }
+};
+
+extern "C" int emu_raycast(int width, int height, const float *ray_table, const int8_t *map, int n,
+                           const float *cam_pos, const float *cam_dir, const int32_t *bias, const float *lights,
+                           const uint8_t *atlas, int atlas_w, int atlas_h, int tile_w, int tile_h, int max_distance,
+                           int use_svo, uint8_t *rgba, vr_aux *aux) {
+    vr_native_tree tree;
+    vr_frame_params P;
+    memset(&P, 0, sizeof(P));
+    P.width = width; P.height = height;
+    P.local_rows = height; P.band_rows = 1; P.band_stride = 1; P.band_first = 0;
+    P.ray_table = ray_table;
+    P.map = map;
+    P.dim[0] = P.dim[1] = P.dim[2] = n;
+    for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = (float)bias[i]; P.light_pos[i] = lights[4 + i]; }
+    for (int i = 0; i < 4; i++) P.light_rgbi[i] = lights[i];
+    P.trig[0] = sinf(cam_dir[0]); P.trig[1] = cosf(cam_dir[0]); P.trig[2] = sinf(cam_dir[1]); P.trig[3] = cosf(cam_dir[1]);
+    P.atlas = atlas; P.atlas_dim[0] = atlas_w; P.atlas_dim[1] = atlas_h;
+    P.atlas_scale[0] = atlas_w / tile_w; P.atlas_scale[1] = atlas_h / tile_h;
+    P.max_distance = max_distance;
+    if (use_svo) {
+        if (!vr_native_from_dense(map, n, tree)) return -1;
+        P.nodes = tree.nodes.data(); P.leaf_types = tree.leaf_types.data();
+        P.levels = tree.levels; P.root_shift = 2 * (tree.levels - 1);
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            uint32_t px;
+            vr_aux a;
+            bool w;
+            if (use_svo) { LocalStack s; w = vr_trace_svo<true>(P, x, y, &px, &a, s); }
+            else w = vr_trace_dense<true>(P, x, y, &px, &a);
+            const size_t i = (size_t)x + (size_t)width * y;
+            if (w) memcpy(rgba + 4 * i, &px, 4);
+            if (aux) aux[i] = a;
+        }
+    return 0;
+}

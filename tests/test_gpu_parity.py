@@ -1,0 +1,254 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(libvrcaster.so via voxel-raycaster_b200.CUDACaster), against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): hit voxel index and face bit-exact, RGBA8 max abs diff <= 1 on >= 99.9 % of
+pixels.  What is asserted here is stricter: RGBA8 and every integer aux field are IDENTICAL on ALL pixels,
+for the dense DDA kernel and for the 64-tree kernel alike (tolerance 0, written in assert_same_frame)."""
+import numpy as np
+import pytest
+
+from conftest import AUX_FIELDS, assert_same_frame, oracle_bias
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["head", "tiny", "small", "features", "features-low", "features-high", "features-mirror"]
+
+
+def make_caster(pkg, scene, use_octree, assign_octree=True, aux=True):
+    c = pkg.CUDACaster()
+    c.load_scene(scene, use_octree=use_octree, assign_octree=assign_octree)
+    if aux:
+        assert c.enable_aux(True)
+    return c
+
+
+def test_ray_table_bit_exact(pkg, oracle):
+    """create_viewport (ref src/CLCaster.cpp:244-275): the device-resident table equals the restated one."""
+    for w, h in ((50, 50), (64, 36), (1280, 720), (5, 7)):
+        c = pkg.CUDACaster()
+        assert c.init(0)
+        assert c.create_viewport(w, h, 56.25, 90.0)
+        assert np.array_equal(c.read_ray_table().view(np.uint32), oracle.make_ray_table(w, h).view(np.uint32))
+        c.close()
+
+
+@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("use_octree", [False, True])
+def test_small_scenes(pkg, oracle, name, use_octree):
+    scene = pkg.scene.make_scene(name)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    c = make_caster(pkg, scene, use_octree)
+    assert c.compute(), c.last_error()
+    st = c.stats()
+    assert list(st.bias) == oracle_bias(oracle, scene, desc, root)
+    assert st.used_svo == int(use_octree) and st.kernel_launches >= 1
+    assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"{name} use_octree={use_octree}")
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["head", "features", "features-low", "features-high", "features-mirror"])
+def test_golden_fixtures(pkg, name):
+    """The committed fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+    scene = pkg.scene.make_scene(name)
+    for use_octree in (False, True):
+        c = make_caster(pkg, scene, use_octree)
+        assert c.compute(), c.last_error()
+        got, aux = c.draw(), c.read_aux()
+        assert np.array_equal(got, z["rgba"])
+        for k in ("hit", "face", "status", "flags", "hit_type", "steps_first", "steps_total"):
+            assert np.array_equal(aux[k], z[k]), (name, k)
+        c.close()
+
+
+def test_head_defaults(pkg, oracle):
+    """HEAD scene with HEAD's max_distance of 20 (kernel:326) when no MAX_DISTANCE setting is registered."""
+    scene = pkg.scene.make_scene("head")
+    c = pkg.CUDACaster()
+    assert c.init(0)
+    assert c.add_to_settings_buffer("octree_dimensions", "OCTDIM", 16)
+    assert c.add_to_settings_buffer("using_octree", "OCTENABLED", 1)
+    desc, root = pkg.octree_generate(scene.volume)
+    assert c.assign_octree(desc, root) and c.assign_map(scene.volume)
+    assert c.assign_camera(scene.cam_dir, scene.cam_pos) and c.create_viewport(50, 50, 56.25, 90.0)
+    assert c.assign_lights(scene.lights) and c.create_texture_atlas(scene.atlas, (16, 16)) and c.validate()
+    assert list(c.settings()[:3]) == [16, 1, root]          # slot order = call order (ref host:1047-1049)
+    assert c.compute()
+    ref, _, _ = oracle.raycast(scene, octree=(desc, root), max_distance=20)
+    assert np.array_equal(c.draw(), ref)
+    c.close()
+
+
+@pytest.mark.parametrize("cam", [0, 1, 3, 4, 7])
+def test_c1_terrain_64(pkg, oracle, cam):
+    """BASELINE config 1 size: 64^3 procedural map, 1280x720, primary + 1 shadow light (+5 % mirrors)."""
+    S = pkg.scene
+    n = 64
+    vol = S.terrain_map(n, "shell", reflect_fraction=0.05 if cam % 2 else 0.0)
+    pos, direction = S.make_camera(n, S.heightfield(n), cam)
+    scene = S.Scene(n, vol, 1280, 720, pos, direction, S.make_lights(n), max_distance=3 * n)
+    desc, root = pkg.octree_generate(vol)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    for use_octree in (False, True):
+        c = make_caster(pkg, scene, use_octree)
+        assert c.compute(), c.last_error()
+        assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"c1 cam={cam} use_octree={use_octree}")
+        c.close()
+
+
+@pytest.mark.parametrize("variant", ["shell", "solid"])
+def test_c2_terrain_256(pkg, oracle, variant):
+    """BASELINE config 2 size: 256^3 terrain, 1920x1080, SVO kernel, shading + atlas + shadow light."""
+    S = pkg.scene
+    n = 256
+    vol = S.terrain_map(n, variant)
+    pos, direction = S.make_camera(n, S.heightfield(n), 4)
+    scene = S.Scene(n, vol, 1920, 1080, pos, direction, S.make_lights(n), max_distance=3 * n)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene)
+    for use_octree in (False, True):
+        c = make_caster(pkg, scene, use_octree, assign_octree=False)
+        assert c.compute(), c.last_error()
+        assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"c2 {variant} use_octree={use_octree}")
+        c.close()
+
+
+def test_octree_only_import(pkg, oracle):
+    """assign_octree without assign_map: the 64-tree is imported from the reference-format descriptors."""
+    scene = pkg.scene.make_scene("small")
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    c = pkg.CUDACaster()
+    assert c.init(0)
+    assert c.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n)
+    assert c.add_to_settings_buffer("using_octree", "OCTENABLED", 0)
+    assert c.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance)
+    assert c.assign_octree(desc, root)
+    assert c.assign_camera(scene.cam_dir, scene.cam_pos) and c.create_viewport(scene.width, scene.height)
+    assert c.assign_lights(scene.lights) and c.create_texture_atlas(scene.atlas) and c.validate(), c.last_error()
+    assert c.enable_aux(True) and c.compute(), c.last_error()
+    assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), "octree-only")
+    # dense traversal without a map must fail loudly, not fall back
+    assert c.overwrite_setting("using_octree", 1)
+    assert not c.compute() and "no map" in c.last_error()
+    c.close()
+
+
+def test_host_pointer_aliasing(pkg, oracle):
+    """CL_MEM_USE_HOST_PTR semantics (ref src/CLCaster.cpp:137-139,322,1069): camera, lights and settings are
+    re-read from the caller's memory at every compute()."""
+    scene = pkg.scene.make_scene("features")
+    desc, root = pkg.octree_generate(scene.volume)
+    c = make_caster(pkg, scene, True)
+    assert c.compute()
+    first = c.draw()
+    scene.cam_pos[:] = (20.4, 5.6, 9.35)          # in place: same arrays the caster aliases
+    scene.cam_dir[:] = (1.65, 1.9)
+    scene.lights[0, 4:7] = (8.0, 20.0, 18.5)
+    assert c.compute()
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    got = c.draw()
+    assert not np.array_equal(first, got)
+    assert_same_frame(ref_rgba, ref_aux, got, c.read_aux(), "aliased update")
+    c.settings()[2] = 7                             # MAX_DISTANCE slot, written through the aliased array
+    assert c.compute()
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), max_distance=7)
+    assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), "aliased setting")
+    c.close()
+
+
+def test_bands_and_pipelined_frames(pkg, oracle):
+    """Multi-GPU screen-tile split on one device: the interleaved band slabs reassemble to the full frame
+    bit for bit; frame_begin/frame_end (async D2H, double buffered) return the same pixels as compute()."""
+    scene = pkg.scene.make_scene("features-low")
+    ref_rgba, ref_aux, _ = oracle.raycast(scene)
+    H, W = scene.height, scene.width
+    for band_rows, stride in ((8, 2), (8, 4), (16, 3), (7, 2)):
+        out = np.zeros((H, W, 4), np.uint8)
+        nb = (H + band_rows - 1) // band_rows
+        for first in range(stride):
+            c = pkg.CUDACaster()
+            c.load_scene(scene, use_octree=True, assign_octree=False)
+            assert c.set_bands(band_rows, stride, first)
+            assert c.compute(), c.last_error()
+            slab = c.draw()
+            rows = [r for b in range(first, nb, stride) for r in range(b * band_rows, min(H, (b + 1) * band_rows))]
+            assert slab.shape[0] == len(rows) == c.local_rows()
+            out[rows] = slab
+            c.close()
+        assert np.array_equal(out, ref_rgba), (band_rows, stride)
+    c = pkg.CUDACaster()
+    c.load_scene(scene, use_octree=True, assign_octree=False)
+    assert c.frame_begin() and c.frame_begin() and not c.frame_begin()      # at most two frames in flight
+    a = c.frame_end().copy()
+    b = c.frame_end().copy()
+    assert np.array_equal(a, ref_rgba) and np.array_equal(b, ref_rgba)
+    c.close()
+
+
+def test_native_tree_broadcast_roundtrip(pkg, oracle):
+    """The multi-GPU scene replication path on one device: export the 64-tree, adopt it in a second context
+    that never saw the map, render the same frame."""
+    import torch
+
+    scene = pkg.scene.make_scene("features")
+    a = pkg.CUDACaster()
+    a.load_scene(scene, use_octree=True, assign_octree=False)
+    nb, tb, levels, dim = a.native_tree_info()
+    nodes = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
+    types = torch.empty(tb, dtype=torch.uint8, device="cuda:0")
+    assert a.native_tree_copy(nodes.data_ptr(), types.data_ptr())
+    assert a.compute()
+    want = a.draw()
+    b = pkg.CUDACaster()
+    assert b.init(0)
+    assert b.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n)
+    assert b.add_to_settings_buffer("using_octree", "OCTENABLED", 0)
+    assert b.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance)
+    assert b.assign_native_tree(nodes.data_ptr(), nb, types.data_ptr(), tb, levels, dim), b.last_error()
+    assert b.assign_camera(scene.cam_dir, scene.cam_pos) and b.create_viewport(scene.width, scene.height)
+    assert b.assign_lights(scene.lights) and b.create_texture_atlas(scene.atlas) and b.validate(), b.last_error()
+    assert b.compute(), b.last_error()
+    assert np.array_equal(b.draw(), want)
+    a.close()
+    b.close()
+
+
+def test_error_behaviour(pkg):
+    """CLCaster returns false and logs instead of throwing (ref src/CLCaster.cpp:157-185, 1029-1109)."""
+    c = pkg.CUDACaster()
+    assert c.init(0)
+    assert not c.validate() and "camera" in c.last_error()
+    assert c.add_to_settings_buffer("a", "A", 1) and not c.add_to_settings_buffer("b", "A", 2)     # duplicate define
+    for i in range(63):
+        assert c.add_to_settings_buffer(f"s{i}", f"S{i}", i)
+    assert not c.add_to_settings_buffer("overflow", "OVERFLOW", 0) and "maximum size" in c.last_error()
+    assert not c.overwrite_setting("nope", 3) and not c.remove_from_settings_buffer("a")
+    assert not c.release_map() and not c.release_viewport()
+    assert not c.compute()
+    c.close()
+
+
+def test_full_size_c3_properties(pkg, oracle):
+    """BASELINE full size (1024^3 SVO, 3840x2160): size-independent properties.
+    (1) 64-tree kernel frame == dense DDA kernel frame, bit for bit (both CUDA, 8.3 M pixels);
+    (2) every 90th row equals the oracle; (3) determinism: two SVO frames are identical."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    frames = {}
+    for use_octree in (True, False):
+        c = make_caster(pkg, scene, use_octree, assign_octree=False)
+        assert c.compute(), c.last_error()
+        frames[use_octree] = (c.draw(), c.read_aux())
+        if use_octree:
+            assert c.compute()
+            assert np.array_equal(c.draw(), frames[True][0])
+        c.close()
+    assert np.array_equal(frames[True][0], frames[False][0])
+    for f in AUX_FIELDS:
+        assert np.array_equal(frames[True][1][f], frames[False][1][f]), f
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, row_stride=90)
+    assert_same_frame(ref_rgba[::90], ref_aux[::90], frames[True][0][::90], frames[True][1][::90], "c3 rows")

@@ -1,0 +1,796 @@
+/*
+ * vr_capi.cu -- implementation of the C ABI declared in include/vr_caster.h.
+ *
+ * The context object plays the role of the reference's CLCaster instance
+ * (include/CLCaster.h:93-329): it owns the device buffers the reference keeps in `buffer_map`,
+ * the settings buffer, and the retained (aliased) camera / light pointers, and dispatches one
+ * kernel per frame on a CUDA stream instead of an OpenCL command queue.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vr_caster.h"
+#include "vr_kernels.h"
+#include "vr_octree.h"
+#include "vr_types.h"
+
+#define VR_SETTINGS_BUFFER_SIZE 64          /* ref include/CLCaster.h:303 */
+#define VR_FILL_RGBA 0x64FFFFFFu            /* (255,255,255,100), ref src/CLCaster.cpp:280-286 */
+
+struct vr_ctx {
+    int device = 0;
+    unsigned flags = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timing_pending = false;
+    float last_kernel_ms = 0.f;
+    unsigned long long launches = 0, frames = 0;
+
+    /* viewport */
+    int width = 0, height = 0;
+    float *d_ray_table = nullptr;
+    uint8_t *d_image[2] = {nullptr, nullptr};
+    uint8_t *h_image[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    unsigned long long frame_issued = 0, frame_retired = 0;   /* pipelined frames */
+    int cur_image = 0;
+    vr_aux *d_aux = nullptr;
+    bool aux_on = false;
+    int band_rows = 1, band_stride = 1, band_first = 0;
+
+    /* dense map */
+    int8_t *d_map = nullptr;
+    int dim[3] = {0, 0, 0};
+    /* reference-format octree (host copy: the start bias is evaluated on the host) */
+    std::vector<uint64_t> oct_desc;
+    uint64_t oct_root = 0;
+    bool has_octree = false;
+    /* native 64-tree */
+    vr_node *d_nodes = nullptr;
+    uint8_t *d_leaf_types = nullptr;
+    int levels = 0, tree_dim = 0;
+    uint64_t n_nodes = 0, n_leaf_types = 0, solid_voxels = 0;
+    bool tree_valid = false, tree_from_map = false;
+
+    /* retained host pointers (CL_MEM_USE_HOST_PTR semantics) */
+    const float *cam_dir = nullptr, *cam_pos = nullptr;
+    const float *lights = nullptr;
+    int light_count = 0;
+
+    /* atlas */
+    cudaArray_t atlas_arr = nullptr;
+    cudaTextureObject_t atlas_tex = 0;
+    uint8_t *d_atlas = nullptr;
+    int atlas_dim[2] = {0, 0}, tile_dim[2] = {0, 0};
+
+    /* settings (ref include/CLCaster.h:303-311) */
+    int64_t *settings = nullptr;
+    unsigned settings_pos = 0;
+    std::map<std::string, unsigned> settings_indices;
+    std::map<std::string, std::string> defines;
+
+    int used_svo = 0;
+    int bias[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(vr_ctx *c, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    fprintf(stderr, "[vrcaster] ERROR: %s\n", buf);      /* ref Logger::log(..., ERROR) */
+    return 0;
+}
+
+#define VR_CUDA(c, call)                                                                        \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) return fail((c), "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+int local_rows_padded(const vr_ctx *c) {
+    if (c->height <= 0) return 0;
+    const int nb = (c->height + c->band_rows - 1) / c->band_rows;
+    int mine = 0;
+    for (int b = c->band_first; b < nb; b += c->band_stride) mine++;
+    return mine * c->band_rows;
+}
+
+/* rows actually owned (last band may be partial) */
+int local_rows_exact(const vr_ctx *c) {
+    if (c->height <= 0) return 0;
+    const int nb = (c->height + c->band_rows - 1) / c->band_rows;
+    int rows = 0;
+    for (int b = c->band_first; b < nb; b += c->band_stride) {
+        const int r0 = b * c->band_rows;
+        rows += (c->height - r0 < c->band_rows) ? c->height - r0 : c->band_rows;
+    }
+    return rows;
+}
+
+/* CLCaster::create_viewport ray table, ref src/CLCaster.cpp:244-275 (own restatement) */
+void make_ray_table(int w, int h, std::vector<float> &out) {
+    out.assign((size_t)4 * w * h, 0.0f);
+    const double s = sin(1.57), c = cos(1.57);
+    const int hw = w / 2, hh = h / 2;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < 2 * hh; j++) {
+        const float py = (float)(j - hh);
+        for (int i = 0; i < 2 * hw; i++) {
+            const float px = (float)(i - hw);
+            const float bx = -800.0f;
+            const float nx = (float)((double)py * s + (double)bx * c);
+            const float ny = px;
+            const float nz = (float)((double)py * c - (double)bx * s);
+            const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+            float *o = &out[4 * ((size_t)i + (size_t)w * (size_t)j)];
+            o[0] = nx / len;
+            o[1] = ny / len;
+            o[2] = nz / len;
+            o[3] = 0.0f;
+        }
+    }
+}
+
+void free_tree(vr_ctx *c) {
+    if (c->d_nodes) cudaFree(c->d_nodes);
+    if (c->d_leaf_types) cudaFree(c->d_leaf_types);
+    c->d_nodes = nullptr;
+    c->d_leaf_types = nullptr;
+    c->tree_valid = false;
+    c->n_nodes = c->n_leaf_types = c->solid_voxels = 0;
+}
+
+int upload_tree(vr_ctx *c, const vr_native_tree &t, bool from_map) {
+    free_tree(c);
+    VR_CUDA(c, cudaMalloc(&c->d_nodes, t.nodes.size() * sizeof(vr_node)));
+    VR_CUDA(c, cudaMalloc(&c->d_leaf_types, t.leaf_types.size()));
+    VR_CUDA(c, cudaMemcpy(c->d_nodes, t.nodes.data(), t.nodes.size() * sizeof(vr_node), cudaMemcpyHostToDevice));
+    VR_CUDA(c, cudaMemcpy(c->d_leaf_types, t.leaf_types.data(), t.leaf_types.size(), cudaMemcpyHostToDevice));
+    c->levels = t.levels;
+    c->tree_dim = t.dim;
+    c->n_nodes = t.nodes.size();
+    c->n_leaf_types = t.leaf_types.size();
+    c->solid_voxels = t.solid_voxels;
+    c->tree_valid = true;
+    c->tree_from_map = from_map;
+    return 1;
+}
+
+bool setting_value(const vr_ctx *c, const char *define, int64_t *out) {
+    auto it = c->defines.find(define);
+    if (it == c->defines.end() || !c->settings) return false;
+    char *end = nullptr;
+    const long slot = strtol(it->second.c_str(), &end, 10);
+    if (end == it->second.c_str() || slot < 0 || slot >= VR_SETTINGS_BUFFER_SIZE) return false;
+    *out = c->settings[slot];
+    return true;
+}
+
+int ensure_tree(vr_ctx *c) {
+    if (c->tree_valid) return 1;
+    if (!c->has_octree) return fail(c, "octree traversal requested but neither a cubic map nor an octree is assigned");
+    int64_t octdim = 0;
+    if (!setting_value(c, "OCTDIM", &octdim) || octdim < 2)
+        return fail(c, "octree assigned but the OCTDIM setting is missing");
+    vr_native_tree t;
+    if (!vr_native_from_ref(c->oct_desc.data(), c->oct_desc.size(), c->oct_root, (int)octdim, nullptr, t))
+        return fail(c, "malformed octree descriptor buffer");
+    return upload_tree(c, t, false);
+}
+
+/* Builds the launch parameters from the retained pointers and the settings buffer, i.e. what the
+ * reference gets for free through CL_MEM_USE_HOST_PTR aliasing (ref src/CLCaster.cpp:137-139,322,1069). */
+int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
+    if (!c->d_ray_table || !c->d_image[0]) return fail(c, "compute: viewport not created");
+    if (!c->cam_dir || !c->cam_pos) return fail(c, "compute: camera not assigned");
+    if (!c->lights || c->light_count < 1) return fail(c, "compute: lights not assigned");
+    if (!c->atlas_tex) return fail(c, "compute: texture atlas not created");
+
+    int64_t v = 0;
+    int svo;
+    if (setting_value(c, "OCTENABLED", &v)) svo = (v == 0);          /* kernel:359: 0 selects the octree branch */
+    else svo = c->d_map ? 0 : 1;
+    if (svo) {
+        if (!ensure_tree(c)) return 0;
+    } else if (!c->d_map) {
+        return fail(c, "compute: dense traversal selected (OCTENABLED != 0) but no map is assigned");
+    }
+    *use_svo = svo;
+
+    memset(&P, 0, sizeof(P));
+    P.width = c->width;
+    P.height = c->height;
+    P.band_rows = c->band_rows;
+    P.band_stride = c->band_stride;
+    P.band_first = c->band_first;
+    P.local_rows = local_rows_padded(c);
+    P.ray_table = c->d_ray_table;
+    P.image = image;
+    P.aux = c->aux_on ? c->d_aux : nullptr;
+    P.map = c->d_map;
+    if (c->d_map) { P.dim[0] = c->dim[0]; P.dim[1] = c->dim[1]; P.dim[2] = c->dim[2]; }
+    else P.dim[0] = P.dim[1] = P.dim[2] = c->tree_dim;
+    for (int i = 0; i < 3; i++) P.cam_pos[i] = c->cam_pos[i];
+    P.trig[0] = sinf(c->cam_dir[0]);
+    P.trig[1] = cosf(c->cam_dir[0]);
+    P.trig[2] = sinf(c->cam_dir[1]);
+    P.trig[3] = cosf(c->cam_dir[1]);
+
+    /* get_oct_vox on the camera voxel, kernel:342-354, evaluated once per frame */
+    c->bias[0] = c->bias[1] = c->bias[2] = 0;
+    if (c->has_octree) {
+        int64_t octdim = 0, root = (int64_t)c->oct_root;
+        setting_value(c, "OCTREE_ROOT_INDEX", &root);
+        if (!setting_value(c, "OCTDIM", &octdim)) octdim = P.dim[0];
+        const int pos[3] = {(int)floorf(c->cam_pos[0]), (int)floorf(c->cam_pos[1]), (int)floorf(c->cam_pos[2])};
+        int sub[3], res = 0;
+        vr_ref_octree_query(c->oct_desc.data(), c->oct_desc.size(), (uint64_t)root, (int)octdim, pos, sub, &res);
+        for (int i = 0; i < 3; i++) c->bias[i] = ((sub[i] - pos[i]) * res) / 2;
+    }
+    for (int i = 0; i < 3; i++) P.bias[i] = (float)c->bias[i];
+
+    for (int i = 0; i < 4; i++) P.light_rgbi[i] = c->lights[i];
+    for (int i = 0; i < 3; i++) P.light_pos[i] = c->lights[4 + i];
+    P.atlas_tex = (unsigned long long)c->atlas_tex;
+    P.atlas = c->d_atlas;
+    P.atlas_dim[0] = c->atlas_dim[0];
+    P.atlas_dim[1] = c->atlas_dim[1];
+    P.atlas_scale[0] = c->atlas_dim[0] / c->tile_dim[0];
+    P.atlas_scale[1] = c->atlas_dim[1] / c->tile_dim[1];
+    P.max_distance = 20;                                             /* kernel:326 */
+    if (setting_value(c, "MAX_DISTANCE", &v)) P.max_distance = (int)v;
+    P.nodes = c->d_nodes;
+    P.leaf_types = c->d_leaf_types;
+    P.levels = c->levels;
+    P.root_shift = 2 * (c->levels - 1);
+    if (svo && (c->tree_dim != P.dim[0] || P.dim[0] != P.dim[1] || P.dim[0] != P.dim[2]))
+        return fail(c, "octree traversal needs a cubic power-of-two map");
+    return 1;
+}
+
+int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
+    vr_frame_params P;
+    int use_svo = 0;
+    if (!build_params(c, P, image, &use_svo)) return 0;
+    if (timed) VR_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches));
+    if (timed) {
+        VR_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+        c->timing_pending = true;
+    }
+    c->used_svo = use_svo;
+    c->frames++;
+    return 1;
+}
+
+int alloc_aux(vr_ctx *c) {
+    if (c->d_aux) { cudaFree(c->d_aux); c->d_aux = nullptr; }
+    if (c->aux_on && c->width > 0)
+        VR_CUDA(c, cudaMalloc(&c->d_aux, sizeof(vr_aux) * (size_t)c->width * (size_t)c->height));
+    return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vr_version(void) { return "voxel-raycaster_b200 0.1 (sm_100a)"; }
+
+const char *vr_last_error(const vr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vr_init(vr_ctx **out, int device, unsigned flags) {
+    if (!out) return 0;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, "no usable CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    vr_ctx *c = new vr_ctx();
+    c->flags = flags;
+    if (device < 0) {
+        c->device = 0;
+        vr_load_config(c, nullptr);
+    } else {
+        c->device = device;
+    }
+    if (c->device >= count) { fail(c, "device %d out of range (%d devices)", c->device, count); delete c; return 0; }
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess) {
+        fail(c, "failed to create CUDA stream/events on device %d: %s", c->device, cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return 0;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+    }
+    c->stream = c->own_stream;
+    if (!vr_create_settings_buffer(c)) { delete c; return 0; }
+    *out = c;
+    return 1;
+}
+
+void vr_destroy(vr_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    vr_release_viewport(c);
+    vr_release_map(c);
+    vr_release_octree(c);
+    free_tree(c);
+    if (c->atlas_tex) cudaDestroyTextureObject(c->atlas_tex);
+    if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+    if (c->d_atlas) cudaFree(c->d_atlas);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete[] c->settings;
+    delete c;
+}
+
+int vr_load_config(vr_ctx *c, const char *path) {
+    if (!c) return 0;
+    FILE *f = fopen(path ? path : "device_config.bin", "rb");
+    if (!f) return 0;                                     /* ref :500-503: no file -> false, caller picks */
+    int ordinal = -1;
+    char name[256] = {0};
+    const bool ok = fread(&ordinal, sizeof(ordinal), 1, f) == 1 && fread(name, 1, sizeof(name), f) == sizeof(name);
+    fclose(f);
+    if (!ok || ordinal < 0) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ordinal) != cudaSuccess) return 0;
+    if (strncmp(prop.name, name, sizeof(name)) != 0) return 0;     /* ref :527: saved device must still match */
+    c->device = ordinal;
+    return 1;
+}
+
+int vr_save_config(vr_ctx *c, const char *path) {
+    if (!c) return 0;
+    cudaDeviceProp prop;
+    VR_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    FILE *f = fopen(path ? path : "device_config.bin", "wb");
+    if (!f) return fail(c, "cannot write device config");
+    char name[256] = {0};
+    snprintf(name, sizeof(name), "%s", prop.name);
+    fwrite(&c->device, sizeof(c->device), 1, f);
+    fwrite(name, 1, sizeof(name), f);
+    fclose(f);
+    return 1;
+}
+
+/* ---- viewport ---- */
+int vr_create_viewport(vr_ctx *c, int width, int height, float v_fov, float h_fov) {
+    (void)v_fov; (void)h_fov;                              /* ignored by the reference too (host:249) */
+    if (!c) return 0;
+    if (width <= 0 || height <= 0) return fail(c, "create_viewport: bad size %dx%d", width, height);
+    cudaSetDevice(c->device);
+    vr_release_viewport(c);
+    c->width = width;
+    c->height = height;
+    std::vector<float> table;
+    make_ray_table(width, height, table);
+    const size_t tbytes = table.size() * sizeof(float), ibytes = (size_t)width * height * 4;
+    VR_CUDA(c, cudaMalloc(&c->d_ray_table, tbytes));
+    VR_CUDA(c, cudaMemcpy(c->d_ray_table, table.data(), tbytes, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; i++) {
+        VR_CUDA(c, cudaMalloc(&c->d_image[i], ibytes));
+        VR_CUDA(c, cudaMallocHost(&c->h_image[i], ibytes));
+        VR_CUDA(c, vr_launch_fill(reinterpret_cast<uint32_t *>(c->d_image[i]), ibytes / 4, VR_FILL_RGBA, c->stream, &c->launches));
+    }
+    VR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->cur_image = 0;
+    c->frame_issued = c->frame_retired = 0;
+    return alloc_aux(c);
+}
+
+int vr_release_viewport(vr_ctx *c) {
+    if (!c) return 0;
+    const bool had = c->d_ray_table != nullptr;
+    if (c->d_ray_table) cudaFree(c->d_ray_table);
+    c->d_ray_table = nullptr;
+    for (int i = 0; i < 2; i++) {
+        if (c->d_image[i]) cudaFree(c->d_image[i]);
+        if (c->h_image[i]) cudaFreeHost(c->h_image[i]);
+        c->d_image[i] = nullptr;
+        c->h_image[i] = nullptr;
+    }
+    if (c->d_aux) cudaFree(c->d_aux);
+    c->d_aux = nullptr;
+    c->width = c->height = 0;
+    return had ? 1 : 0;                                    /* ref release_buffer: false if absent */
+}
+
+/* ---- lights / camera: retained pointers ---- */
+int vr_assign_lights(vr_ctx *c, const float *packed, int count) {
+    if (!c) return 0;
+    if (!packed || count < 1) return fail(c, "assign_lights: empty light array");
+    c->lights = packed;
+    c->light_count = count;
+    return 1;
+}
+
+int vr_assign_camera(vr_ctx *c, const float *direction2, const float *position3) {
+    if (!c) return 0;
+    if (!direction2 || !position3) return fail(c, "assign_camera: null pointer");
+    c->cam_dir = direction2;
+    c->cam_pos = position3;
+    return 1;
+}
+
+int vr_release_camera(vr_ctx *c) {
+    if (!c) return 0;
+    const bool had = c->cam_dir != nullptr;
+    c->cam_dir = c->cam_pos = nullptr;
+    return had ? 1 : 0;
+}
+
+/* ---- map ---- */
+int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
+    if (!c) return 0;
+    if (!voxels || nx <= 0 || ny <= 0 || nz <= 0) return fail(c, "assign_map: bad arguments");
+    cudaSetDevice(c->device);
+    if (c->d_map) vr_release_map(c);                       /* ref store_buffer: silently replaces (host:859-863) */
+    const size_t bytes = (size_t)nx * ny * nz;
+    VR_CUDA(c, cudaMalloc(&c->d_map, bytes));
+    VR_CUDA(c, cudaMemcpy(c->d_map, voxels, bytes, cudaMemcpyHostToDevice));
+    c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
+    /* traversal structure for the octree branch, built from the same voxels (types included) */
+    if (nx == ny && ny == nz && (nx & (nx - 1)) == 0) {
+        vr_native_tree t;
+        if (!vr_native_from_dense(voxels, nx, t)) return fail(c, "assign_map: 64-tree build failed");
+        if (!upload_tree(c, t, true)) return 0;
+    } else if (c->tree_from_map) {
+        free_tree(c);
+    }
+    return 1;
+}
+
+int vr_release_map(vr_ctx *c) {
+    if (!c) return 0;
+    const bool had = c->d_map != nullptr;
+    if (c->d_map) cudaFree(c->d_map);
+    c->d_map = nullptr;
+    c->dim[0] = c->dim[1] = c->dim[2] = 0;
+    if (c->tree_from_map) free_tree(c);
+    return had ? 1 : 0;
+}
+
+/* ---- octree ---- */
+int vr_assign_octree(vr_ctx *c, const uint64_t *descriptors, const uint32_t *attach_lookup, const uint64_t *attach,
+                     uint64_t entries, uint64_t root_index) {
+    (void)attach_lookup; (void)attach;                     /* all zero in the reference (Octree.cpp:8-9) */
+    if (!c) return 0;
+    if (!descriptors || !entries || root_index >= entries) return fail(c, "assign_octree: bad arguments");
+    c->oct_desc.assign(descriptors, descriptors + entries);
+    c->oct_root = root_index;
+    c->has_octree = true;
+    if (!c->tree_from_map) free_tree(c);                   /* re-import lazily at validate/compute */
+    /* ref host:113: registers the root index as a setting (fails quietly when already present) */
+    if (!c->defines.count("OCTREE_ROOT_INDEX")) vr_add_to_settings_buffer(c, "octree_root_index", "OCTREE_ROOT_INDEX", (int64_t)root_index);
+    else vr_overwrite_setting(c, "octree_root_index", (const int64_t *)&root_index);
+    return 1;
+}
+
+int vr_release_octree(vr_ctx *c) {
+    if (!c) return 0;
+    const bool had = c->has_octree;
+    c->oct_desc.clear();
+    c->oct_desc.shrink_to_fit();
+    c->has_octree = false;
+    if (!c->tree_from_map) free_tree(c);
+    return had ? 1 : 0;
+}
+
+/* ---- atlas ---- */
+int vr_create_texture_atlas(vr_ctx *c, const uint8_t *rgba, int width, int height, int tile_w, int tile_h) {
+    if (!c) return 0;
+    if (!rgba || width <= 0 || height <= 0 || tile_w <= 0 || tile_h <= 0) return fail(c, "create_texture_atlas: bad arguments");
+    cudaSetDevice(c->device);
+    if (c->atlas_tex) { cudaDestroyTextureObject(c->atlas_tex); c->atlas_tex = 0; }
+    if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; }
+    if (c->d_atlas) { cudaFree(c->d_atlas); c->d_atlas = nullptr; }
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    VR_CUDA(c, cudaMallocArray(&c->atlas_arr, &fmt, width, height));
+    VR_CUDA(c, cudaMemcpy2DToArray(c->atlas_arr, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = c->atlas_arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;                   /* sampler-less read_imagef: nearest, kernel:652 */
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    VR_CUDA(c, cudaCreateTextureObject(&c->atlas_tex, &res, &td, nullptr));
+    VR_CUDA(c, cudaMalloc(&c->d_atlas, (size_t)width * height * 4));
+    VR_CUDA(c, cudaMemcpy(c->d_atlas, rgba, (size_t)width * height * 4, cudaMemcpyHostToDevice));
+    c->atlas_dim[0] = width; c->atlas_dim[1] = height;
+    c->tile_dim[0] = tile_w; c->tile_dim[1] = tile_h;
+    return 1;
+}
+
+/* ---- settings ---- */
+int vr_create_settings_buffer(vr_ctx *c) {
+    if (!c) return 0;
+    delete[] c->settings;
+    c->settings = new int64_t[VR_SETTINGS_BUFFER_SIZE]();
+    c->settings_pos = 0;
+    c->settings_indices.clear();
+    return 1;
+}
+
+int vr_release_settings_buffer(vr_ctx *c) {
+    if (!c || !c->settings) return 0;
+    delete[] c->settings;
+    c->settings = nullptr;
+    return 1;
+}
+
+int vr_add_to_settings_buffer(vr_ctx *c, const char *setting_name, const char *define_name, int64_t value) {
+    if (!c || !setting_name || !define_name) return 0;
+    if (!c->settings) return fail(c, "Trying to push settings to an uninitialized settings buffer");
+    if (c->defines.count(define_name)) return fail(c, "Define name already present in the defines map");
+    if (c->settings_pos >= VR_SETTINGS_BUFFER_SIZE)
+        return fail(c, "Settings buffer has reached the maximum size of %d elements", VR_SETTINGS_BUFFER_SIZE);
+    c->defines[define_name] = std::to_string(c->settings_pos);
+    c->settings[c->settings_pos] = value;
+    c->settings_indices[setting_name] = c->settings_pos;
+    c->settings_pos++;
+    return 1;
+}
+
+int vr_overwrite_setting(vr_ctx *c, const char *setting_name, const int64_t *value) {
+    if (!c || !setting_name || !value) return 0;
+    if (!c->settings) return fail(c, "Trying to push settings to an uninitialized settings buffer");
+    auto it = c->settings_indices.find(setting_name);
+    if (it == c->settings_indices.end()) return fail(c, "No setting matching [%s]", setting_name);
+    c->settings[it->second] = *value;
+    return 1;
+}
+
+int vr_remove_from_settings_buffer(vr_ctx *c, const char *setting_name) {
+    (void)setting_name;
+    if (c) c->err = "remove_from_settings_buffer() not implemented";      /* ref host:1074-1078 */
+    return 0;
+}
+
+int64_t *vr_settings_data(vr_ctx *c) { return c ? c->settings : nullptr; }
+
+int vr_set_define(vr_ctx *c, const char *name, const char *value) {
+    if (!c || !name || !value) return 0;
+    c->defines[name] = value;
+    return 1;
+}
+
+int vr_remove_define(vr_ctx *c, const char *name) {
+    if (!c || !name) return 0;
+    c->defines.erase(name);
+    return 1;
+}
+
+/* ---- per frame ---- */
+int vr_validate(vr_ctx *c) {
+    if (!c) return 0;
+    if (!c->cam_dir) return fail(c, "Raycaster.validate() failed, camera not initialized");
+    if (!c->d_map && !c->has_octree && !c->tree_valid) return fail(c, "Raycaster.validate() failed, map not initialized");
+    if (!c->d_image[0]) return fail(c, "Raycaster.validate() failed, viewport_image not initialized");
+    if (!c->d_ray_table) return fail(c, "Raycaster.validate() failed, viewport_matrix not initialized");
+    cudaSetDevice(c->device);
+    int64_t v = 0;
+    const bool svo = setting_value(c, "OCTENABLED", &v) ? (v == 0) : (c->d_map == nullptr);
+    if (svo && !ensure_tree(c)) return 0;
+    return 1;
+}
+
+int vr_debug_quick_recompile(vr_ctx *c) { return vr_validate(c); }
+
+int vr_compute_async(vr_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    return launch_frame(c, c->d_image[c->cur_image], true);
+}
+
+int vr_sync(vr_ctx *c) {
+    if (!c) return 0;
+    VR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->timing_pending) {
+        cudaEventElapsedTime(&c->last_kernel_ms, c->ev_start, c->ev_stop);
+        c->timing_pending = false;
+    }
+    return 1;
+}
+
+int vr_compute(vr_ctx *c) { return vr_compute_async(c) && vr_sync(c); }
+
+int vr_compute_into(vr_ctx *c, void *device_rgba) {
+    if (!c || !device_rgba) return 0;
+    cudaSetDevice(c->device);
+    return launch_frame(c, static_cast<uint8_t *>(device_rgba), false);
+}
+
+int vr_read_framebuffer(vr_ctx *c, uint8_t *rgba_out, size_t bytes) {
+    if (!c || !rgba_out) return 0;
+    if (!c->d_image[0]) return fail(c, "read_framebuffer: viewport not created");
+    const size_t have = (size_t)c->width * 4 * (size_t)(c->band_stride > 1 ? local_rows_padded(c) : c->height);
+    const size_t full = (size_t)c->width * 4 * (size_t)c->height;
+    size_t n = bytes < have ? bytes : have;
+    if (n > full) n = full;
+    VR_CUDA(c, cudaMemcpyAsync(rgba_out, c->d_image[c->cur_image], n, cudaMemcpyDeviceToHost, c->stream));
+    return vr_sync(c);
+}
+
+int vr_frame_begin(vr_ctx *c) {
+    if (!c) return 0;
+    if (c->frame_issued - c->frame_retired >= 2) return fail(c, "frame_begin: two frames already in flight");
+    cudaSetDevice(c->device);
+    const int slot = (int)(c->frame_issued & 1);
+    /* the image of two frames ago must have left the device before it is overwritten */
+    if (c->frame_issued >= 2) VR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+    if (!launch_frame(c, c->d_image[slot], false)) return 0;
+    VR_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
+    VR_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
+    const size_t bytes = (size_t)c->width * 4 * (size_t)(c->band_stride > 1 ? local_rows_padded(c) : c->height);
+    VR_CUDA(c, cudaMemcpyAsync(c->h_image[slot], c->d_image[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    VR_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->cur_image = slot;
+    c->frame_issued++;
+    return 1;
+}
+
+int vr_frame_end(vr_ctx *c, const uint8_t **rgba) {
+    if (!c) return 0;
+    if (c->frame_issued == c->frame_retired) return fail(c, "frame_end: no frame in flight");
+    const int slot = (int)(c->frame_retired & 1);
+    VR_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
+    if (rgba) *rgba = c->h_image[slot];
+    c->frame_retired++;
+    return 1;
+}
+
+/* ---- extensions ---- */
+int vr_set_bands(vr_ctx *c, int band_rows, int stride, int first) {
+    if (!c) return 0;
+    if (band_rows < 1 || stride < 1 || first < 0 || first >= stride) return fail(c, "set_bands: bad arguments");
+    c->band_rows = band_rows;
+    c->band_stride = stride;
+    c->band_first = first;
+    return 1;
+}
+
+int vr_local_rows(const vr_ctx *c) { return c ? local_rows_exact(c) : 0; }
+
+int vr_set_stream(vr_ctx *c, void *cuda_stream) {
+    if (!c) return 0;
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return 1;
+}
+
+int vr_enable_aux(vr_ctx *c, int enable) {
+    if (!c) return 0;
+    c->aux_on = enable != 0;
+    cudaSetDevice(c->device);
+    return alloc_aux(c);
+}
+
+int vr_read_aux(vr_ctx *c, void *out, size_t bytes) {
+    if (!c || !out) return 0;
+    if (!c->d_aux) return fail(c, "read_aux: aux records are not enabled");
+    const size_t have = sizeof(vr_aux) * (size_t)c->width * (size_t)c->height;
+    VR_CUDA(c, cudaMemcpyAsync(out, c->d_aux, bytes < have ? bytes : have, cudaMemcpyDeviceToHost, c->stream));
+    return vr_sync(c);
+}
+
+void *vr_device_image(vr_ctx *c) { return c ? c->d_image[c->cur_image] : nullptr; }
+
+int vr_read_ray_table(vr_ctx *c, float *out, size_t bytes) {
+    if (!c || !out) return 0;
+    if (!c->d_ray_table) return fail(c, "read_ray_table: viewport not created");
+    const size_t have = sizeof(float) * 4 * (size_t)c->width * (size_t)c->height;
+    VR_CUDA(c, cudaMemcpy(out, c->d_ray_table, bytes < have ? bytes : have, cudaMemcpyDeviceToHost));
+    return 1;
+}
+
+int vr_native_tree_info(vr_ctx *c, uint64_t *node_bytes, uint64_t *type_bytes, int32_t *levels, int32_t *dim) {
+    if (!c) return 0;
+    if (!c->tree_valid && !ensure_tree(c)) return 0;
+    if (node_bytes) *node_bytes = c->n_nodes * sizeof(vr_node);
+    if (type_bytes) *type_bytes = c->n_leaf_types;
+    if (levels) *levels = c->levels;
+    if (dim) *dim = c->tree_dim;
+    return 1;
+}
+
+int vr_native_tree_copy(vr_ctx *c, void *device_nodes, void *device_types) {
+    if (!c || !device_nodes || !device_types) return 0;
+    if (!c->tree_valid) return fail(c, "native_tree_copy: no 64-tree built");
+    VR_CUDA(c, cudaMemcpyAsync(device_nodes, c->d_nodes, c->n_nodes * sizeof(vr_node), cudaMemcpyDeviceToDevice, c->stream));
+    VR_CUDA(c, cudaMemcpyAsync(device_types, c->d_leaf_types, c->n_leaf_types, cudaMemcpyDeviceToDevice, c->stream));
+    VR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 1;
+}
+
+int vr_assign_native_tree(vr_ctx *c, const void *device_nodes, uint64_t node_bytes, const void *device_types,
+                          uint64_t type_bytes, int32_t levels, int32_t dim) {
+    if (!c) return 0;
+    if (!device_nodes || !device_types || node_bytes < sizeof(vr_node) || node_bytes % sizeof(vr_node) || !type_bytes ||
+        levels < 1 || levels > VR_MAX_LEVELS || dim < 1 || (dim & (dim - 1)) || (1 << (2 * levels)) < dim)
+        return fail(c, "assign_native_tree: bad arguments");
+    cudaSetDevice(c->device);
+    free_tree(c);
+    VR_CUDA(c, cudaMalloc(&c->d_nodes, node_bytes));
+    VR_CUDA(c, cudaMalloc(&c->d_leaf_types, type_bytes));
+    VR_CUDA(c, cudaMemcpyAsync(c->d_nodes, device_nodes, node_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    VR_CUDA(c, cudaMemcpyAsync(c->d_leaf_types, device_types, type_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    VR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->levels = levels;
+    c->tree_dim = dim;
+    c->n_nodes = node_bytes / sizeof(vr_node);
+    c->n_leaf_types = type_bytes;
+    c->solid_voxels = type_bytes;
+    c->tree_valid = true;
+    c->tree_from_map = true;      /* not tied to an assigned reference octree */
+    return 1;
+}
+
+int vr_get_stats(vr_ctx *c, vr_stats *out) {
+    if (!c || !out) return 0;
+    memset(out, 0, sizeof(*out));
+    out->kernel_launches = c->launches;
+    out->frames = c->frames;
+    out->native_nodes = c->n_nodes;
+    out->native_bytes = c->n_nodes * sizeof(vr_node) + c->n_leaf_types;
+    out->solid_voxels = c->solid_voxels;
+    out->levels = c->levels;
+    out->used_svo = c->used_svo;
+    for (int i = 0; i < 3; i++) out->bias[i] = c->bias[i];
+    out->device = c->device;
+    out->last_kernel_ms = c->last_kernel_ms;
+    return 1;
+}
+
+int vr_octree_generate(const int8_t *voxels, int dim, uint64_t *out, uint64_t *entries, uint64_t *root_index) {
+    if (!voxels || !entries) return 0;
+    std::vector<uint64_t> buf;
+    uint64_t root = 0;
+    if (!vr_ref_octree_generate(voxels, dim, buf, &root)) return 0;
+    if (out) {
+        if (*entries < buf.size()) { *entries = buf.size(); return 0; }
+        memcpy(out, buf.data(), buf.size() * sizeof(uint64_t));
+    }
+    *entries = buf.size();
+    if (root_index) *root_index = root;
+    return 1;
+}
+
+int vr_octree_get_voxel(const uint64_t *descriptors, uint64_t entries, uint64_t root_index, int dim, const int32_t pos[3],
+                        int32_t sub_oct_pos[3], int32_t *resolution) {
+    int sub[3] = {0, 0, 0}, res = 0;
+    const int p[3] = {pos[0], pos[1], pos[2]};
+    const int found = vr_ref_octree_query(descriptors, entries, root_index, dim, p, sub, &res);
+    if (sub_oct_pos) { sub_oct_pos[0] = sub[0]; sub_oct_pos[1] = sub[1]; sub_oct_pos[2] = sub[2]; }
+    if (resolution) *resolution = res;
+    return found;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+/*
+ * vr_kernels.cu -- sm_100a kernels of the B200 voxel ray caster.
+ *
+ * Replaces clEnqueueNDRangeKernel("raycaster", global=(W,H), local=NULL)
+ * (reference src/CLCaster.cpp:946-987) and the OpenCL kernel it runs
+ * (kernels/ray_caster_kernel.cl:256).  The per-pixel logic lives in vr_trace.h.
+ *
+ * Pixel -> thread mapping: a CTA of 256 threads covers a 32x8 pixel tile, each warp an 8x4 block
+ * of it, so that the 32 rays of a warp form a compact bundle (coherent DDA trip counts and octree
+ * paths) while ray-table loads (16 B/pixel) and RGBA8 stores (4 B/pixel) still fill whole
+ * 128-byte / 32-byte sectors.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vr_kernels.h"
+#include "vr_trace.h"
+
+namespace {
+
+constexpr int kTileW = 32;
+constexpr int kTileH = 8;
+constexpr int kThreads = kTileW * kTileH;
+
+/* thread -> pixel inside the CTA tile: warp w = (w&3, w>>2) of 8x4 blocks, lane = (l&7, l>>3) */
+__device__ __forceinline__ void tile_xy(int tid, int &lx, int &ly) {
+    const int warp = tid >> 5, lane = tid & 31;
+    lx = ((warp & 3) << 3) | (lane & 7);
+    ly = ((warp >> 2) << 2) | (lane >> 3);
+}
+
+/* local slab row -> frame row (multi-GPU row-band interleave, see vr_types.h) */
+__device__ __forceinline__ int frame_row(const vr_frame_params &P, int ly) {
+    const int lb = ly / P.band_rows;
+    return (lb * P.band_stride + P.band_first) * P.band_rows + (ly - lb * P.band_rows);
+}
+
+struct SmemStack {
+    uint32_t *base;   /* &stack[0][tid]; level stride = kThreads */
+    __device__ __forceinline__ void set(int level, uint32_t v) { base[level * kThreads] = v; }
+    __device__ __forceinline__ uint32_t get(int level) const { return base[level * kThreads]; }
+};
+
+template <bool AUX>
+__global__ void __launch_bounds__(kThreads)
+vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
+    int lx, ly;
+    tile_xy(threadIdx.x, lx, ly);
+    const int x = blockIdx.x * kTileW + lx;
+    const int row = blockIdx.y * kTileH + ly;
+    if (x >= P.width || row >= P.local_rows) return;
+    const int y = frame_row(P, row);
+    if (y >= P.height) return;
+    const size_t local = (size_t)x + (size_t)P.width * (size_t)row;
+    uint32_t rgba;
+    vr_aux a;
+    const bool write = vr_trace_dense<AUX>(P, x, y, &rgba, &a);
+    if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
+    if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
+             reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
+}
+
+template <bool AUX>
+__global__ void __launch_bounds__(kThreads)
+vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
+    __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
+    int lx, ly;
+    tile_xy(threadIdx.x, lx, ly);
+    const int x = blockIdx.x * kTileW + lx;
+    const int row = blockIdx.y * kTileH + ly;
+    if (x >= P.width || row >= P.local_rows) return;
+    const int y = frame_row(P, row);
+    if (y >= P.height) return;
+    const size_t local = (size_t)x + (size_t)P.width * (size_t)row;
+    SmemStack stk{stack + threadIdx.x};
+    uint32_t rgba;
+    vr_aux a;
+    const bool write = vr_trace_svo<AUX>(P, x, y, &rgba, &a, stk);
+    if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
+    if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
+             reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
+}
+
+__global__ void vr_fill_kernel(uint32_t *dst, size_t n, uint32_t value) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = value;
+}
+
+}  // namespace
+
+cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_aux, cudaStream_t stream,
+                              unsigned long long *launches) {
+    if (P.width <= 0 || P.local_rows <= 0) return cudaSuccess;
+    const dim3 grid((P.width + kTileW - 1) / kTileW, (P.local_rows + kTileH - 1) / kTileH);
+    const dim3 block(kThreads);
+    if (use_svo) {
+        if (with_aux) vr_svo_kernel<true><<<grid, block, 0, stream>>>(P);
+        else vr_svo_kernel<false><<<grid, block, 0, stream>>>(P);
+    } else {
+        if (with_aux) vr_dense_kernel<true><<<grid, block, 0, stream>>>(P);
+        else vr_dense_kernel<false><<<grid, block, 0, stream>>>(P);
+    }
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t vr_launch_fill(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream,
+                           unsigned long long *launches) {
+    if (!n) return cudaSuccess;
+    vr_fill_kernel<<<148 * 4, 256, 0, stream>>>(dst, n, value);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}

@@ -1,0 +1,20 @@
+/* vr_kernels.h -- launchers of the sm_100a kernels (internal; the public boundary is include/vr_caster.h). */
+#ifndef VR_KERNELS_H
+#define VR_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vr_types.h"
+
+/* One frame (or one row-band slab of it).  use_svo selects the 64-tree traversal kernel, otherwise the
+ * dense DDA kernel.  with_aux additionally writes one vr_aux record per pixel.  *launches is bumped
+ * once per kernel launched. */
+cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_aux, cudaStream_t stream,
+                              unsigned long long *launches);
+
+cudaError_t vr_launch_fill(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream,
+                           unsigned long long *launches);
+
+#endif

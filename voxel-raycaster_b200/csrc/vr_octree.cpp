@@ -1,0 +1,319 @@
+/* vr_octree.cpp -- see vr_octree.h. */
+#include "vr_octree.h"
+
+#include <string.h>
+
+#include <functional>
+
+namespace {
+
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+/* ------------------------------------------------------------------------------------------------
+ * reference-format generator
+ * ---------------------------------------------------------------------------------------------- */
+struct TNode {
+    uint8_t valid = 0, leaf = 0;
+    bool has_block = false;           /* false for 2^3-level descriptors (children are voxels) */
+    uint32_t kid[8];
+    uint64_t subtree = 0;             /* entries (descriptors + far slots) below this node      */
+    uint8_t far_mask = 0;             /* bit j: j-th valid child is reached through a far ptr   */
+};
+
+struct RefGen {
+    const int8_t *data;
+    int dim;
+    std::vector<TNode> nodes;
+    static constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+    inline int8_t vox(int x, int y, int z) const {
+        return data[(size_t)x + (size_t)dim * ((size_t)y + (size_t)dim * (size_t)z)];
+    }
+    /* returns node id, or kNone when the cube is uniformly empty */
+    uint32_t build(int px, int py, int pz, int size) {
+        const int h = size / 2;
+        TNode n;
+        for (int i = 0; i < 8; i++) n.kid[i] = kNone;
+        if (size == 2) {
+            for (int i = 0; i < 8; i++)
+                if (vox(px + (i & 1), py + ((i >> 1) & 1), pz + ((i >> 2) & 1))) n.valid |= (uint8_t)(1u << i);
+            n.leaf = 0xFF;
+            if (!n.valid) return kNone;
+            nodes.push_back(n);
+            return (uint32_t)nodes.size() - 1;
+        }
+        for (int i = 0; i < 8; i++) {
+            const uint32_t k = build(px + (i & 1) * h, py + ((i >> 1) & 1) * h, pz + ((i >> 2) & 1) * h, h);
+            if (k == kNone) n.leaf |= (uint8_t)(1u << i);
+            else { n.valid |= (uint8_t)(1u << i); n.kid[i] = k; }
+        }
+        if (!n.valid) return kNone;
+        n.has_block = true;
+        /* block = one descriptor per valid child + far slots; far decision is pessimistic in nfar */
+        int m = __builtin_popcount(n.valid);
+        uint64_t before = 0;
+        int j = 0, nfar = 0;
+        for (int i = 0; i < 8; i++) {
+            if (n.kid[i] == kNone) continue;
+            const TNode &c = nodes[n.kid[i]];
+            if (c.has_block && (uint64_t)(m - j) + (uint64_t)m + before > 0x7fffull) { n.far_mask |= (uint8_t)(1u << j); nfar++; }
+            before += c.subtree;
+            j++;
+        }
+        n.subtree = (uint64_t)m + (uint64_t)nfar + before;
+        nodes.push_back(n);
+        return (uint32_t)nodes.size() - 1;
+    }
+
+    void place(uint32_t id, uint64_t q, std::vector<uint64_t> &buf) const {
+        const TNode &n = nodes[id];
+        const int m = __builtin_popcount(n.valid);
+        const int nfar = __builtin_popcount(n.far_mask);
+        uint64_t cursor = q + (uint64_t)m + (uint64_t)nfar;
+        int j = 0, k = 0;
+        for (int i = 0; i < 8; i++) {
+            if (n.kid[i] == kNone) continue;
+            const TNode &c = nodes[n.kid[i]];
+            uint64_t desc = ((uint64_t)c.valid << 16) | ((uint64_t)c.leaf << 24);
+            if (c.has_block) {
+                const uint64_t at = q + (uint64_t)j;
+                if (n.far_mask & (1u << j)) {
+                    const uint64_t slot = q + (uint64_t)m + (uint64_t)k;
+                    buf[slot] = cursor;                       /* absolute index (Octree.cpp:281) */
+                    desc |= 0x8000ull | (slot - at);
+                    k++;
+                } else {
+                    desc |= (cursor - at);
+                }
+                buf[at] = desc;
+                place(n.kid[i], cursor, buf);
+                cursor += c.subtree;
+            } else {
+                buf[q + (uint64_t)j] = desc;
+            }
+            j++;
+        }
+    }
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * native 64-tree emit from a mask pyramid
+ * ---------------------------------------------------------------------------------------------- */
+struct Pyramid {
+    int levels = 0;
+    std::vector<int> g;                              /* grid edge per level */
+    std::vector<std::vector<uint64_t>> M;            /* masks per level     */
+    inline uint64_t &at(int l, int x, int y, int z) { return M[l][(size_t)x + (size_t)g[l] * ((size_t)y + (size_t)g[l] * (size_t)z)]; }
+};
+
+void pyramid_init(Pyramid &p, int dim) {
+    int L = 1;
+    while ((1 << (2 * L)) < dim) L++;
+    p.levels = L;
+    p.g.assign(L, 1);
+    p.M.assign(L, {});
+    for (int l = L - 1; l >= 0; l--) {
+        const int cell = 1 << (2 * (L - l));         /* voxels covered by a node of level l */
+        p.g[l] = (dim + cell - 1) / cell;
+        p.M[l].assign((size_t)p.g[l] * p.g[l] * p.g[l], 0ull);
+    }
+}
+
+void pyramid_reduce(Pyramid &p) {
+    for (int l = p.levels - 2; l >= 0; l--) {
+        const int gc = p.g[l + 1];
+#pragma omp parallel for schedule(static)
+        for (int z = 0; z < p.g[l]; z++)
+            for (int y = 0; y < p.g[l]; y++)
+                for (int x = 0; x < p.g[l]; x++) {
+                    uint64_t m = 0;
+                    for (int ci = 0; ci < 64; ci++) {
+                        const int cx = 4 * x + (ci & 3), cy = 4 * y + ((ci >> 2) & 3), cz = 4 * z + (ci >> 4);
+                        if (cx < gc && cy < gc && cz < gc && p.at(l + 1, cx, cy, cz)) m |= 1ull << ci;
+                    }
+                    p.at(l, x, y, z) = m;
+                }
+    }
+}
+
+/* type_of(x,y,z) -> voxel value for a set leaf bit */
+void pyramid_emit(Pyramid &p, int dim, const std::function<uint8_t(int, int, int)> &type_of, vr_native_tree &out) {
+    out.nodes.clear();
+    out.leaf_types.clear();
+    out.levels = p.levels;
+    out.dim = dim;
+    out.solid_voxels = 0;
+    struct Coord { int x, y, z; };
+    std::vector<Coord> cur{{0, 0, 0}}, next;
+    for (int l = 0; l < p.levels; l++) {
+        const size_t level_start = out.nodes.size();
+        const size_t next_start = level_start + cur.size();
+        next.clear();
+        for (const Coord &c : cur) {
+            const uint64_t m = p.at(l, c.x, c.y, c.z);
+            vr_node n;
+            n.mask_lo = (uint32_t)m;
+            n.mask_hi = (uint32_t)(m >> 32);
+            n.aux = 0;
+            if (l == p.levels - 1) {
+                n.child_base = (uint32_t)out.leaf_types.size();
+                for (int ci = 0; ci < 64; ci++)
+                    if ((m >> ci) & 1ull) {
+                        out.leaf_types.push_back(type_of(4 * c.x + (ci & 3), 4 * c.y + ((ci >> 2) & 3), 4 * c.z + (ci >> 4)));
+                        out.solid_voxels++;
+                    }
+            } else {
+                n.child_base = (uint32_t)(next_start + next.size());
+                for (int ci = 0; ci < 64; ci++)
+                    if ((m >> ci) & 1ull) next.push_back({4 * c.x + (ci & 3), 4 * c.y + ((ci >> 2) & 3), 4 * c.z + (ci >> 4)});
+            }
+            out.nodes.push_back(n);
+        }
+        cur.swap(next);
+    }
+    if (out.leaf_types.empty()) out.leaf_types.push_back(0);   /* keep the device buffer non-empty */
+}
+
+}  // namespace
+
+bool vr_ref_octree_generate(const int8_t *data, int dim, std::vector<uint64_t> &out, uint64_t *root_index) {
+    if (!data || dim < 2 || !is_pow2(dim)) return false;
+    RefGen g{data, dim, {}};
+    const uint32_t root = g.build(0, 0, 0, dim);
+    out.clear();
+    if (root == RefGen::kNone) {
+        /* uniformly empty map: a root whose eight children are collapsed-empty */
+        out.push_back((0xFFull << 24) | 1ull);
+        if (root_index) *root_index = 0;
+        return true;
+    }
+    const TNode &r = g.nodes[root];
+    out.assign(1 + r.subtree, 0ull);
+    out[0] = ((uint64_t)r.valid << 16) | ((uint64_t)r.leaf << 24) | 1ull;     /* Octree.cpp:27 */
+    if (r.has_block) g.place(root, 1, out);
+    if (root_index) *root_index = 0;
+    return true;
+}
+
+int vr_ref_octree_query(const uint64_t *desc, uint64_t len, uint64_t root_index, int octdim, const int pos[3],
+                        int sub_oct_pos[3], int *resolution) {
+    uint64_t idx = root_index;
+    int dimension = octdim;
+    int res = dimension / 2;
+    int o[3] = {0, 0, 0};
+    sub_oct_pos[0] = sub_oct_pos[1] = sub_oct_pos[2] = 0;
+    *resolution = res;
+    if (!desc || idx >= len) return 0;
+    uint64_t cd = desc[idx];
+    while (dimension > 1) {
+        const int half = dimension / 2;
+        int ci = 0;
+        for (int a = 0; a < 3; a++)
+            if (pos[a] >= half + o[a]) { ci |= 1 << a; o[a] += half; }
+        sub_oct_pos[0] = o[0]; sub_oct_pos[1] = o[1]; sub_oct_pos[2] = o[2];
+        *resolution = res;
+        const bool valid = (cd >> (16 + ci)) & 1ull, leaf = (cd >> (24 + ci)) & 1ull;
+        if (!valid) return 0;
+        if (leaf) return 1;                                   /* kernel:199-205: no halving */
+        dimension = half;
+        res /= 2;
+        *resolution = res;
+        const uint64_t count = (uint64_t)__builtin_popcountll((cd >> 16) & ((2ull << ci) - 1ull)) - 1ull;
+        if (cd & 0x8000ull) {
+            const uint64_t far = idx + (cd & 0x7fffull);
+            if (far >= len) return 0;
+            idx = desc[far] + count;
+        } else {
+            idx = idx + (cd & 0x7fffull) + count;
+        }
+        if (idx >= len) return 0;
+        cd = desc[idx];
+    }
+    return 1;
+}
+
+bool vr_native_from_dense(const int8_t *map, int dim, vr_native_tree &out) {
+    if (!map || dim < 1 || !is_pow2(dim)) return false;
+    Pyramid p;
+    pyramid_init(p, dim);
+    const int L = p.levels, gl = p.g[L - 1];
+#pragma omp parallel for schedule(static)
+    for (int bz = 0; bz < gl; bz++)
+        for (int by = 0; by < gl; by++)
+            for (int bx = 0; bx < gl; bx++) {
+                uint64_t m = 0;
+                for (int cz = 0; cz < 4; cz++)
+                    for (int cy = 0; cy < 4; cy++) {
+                        const int y = 4 * by + cy, z = 4 * bz + cz;
+                        if (y >= dim || z >= dim) continue;
+                        const int8_t *row = map + (size_t)dim * ((size_t)y + (size_t)dim * (size_t)z) + 4 * (size_t)bx;
+                        for (int cx = 0; cx < 4 && 4 * bx + cx < dim; cx++)
+                            if (row[cx] == 5 || row[cx] == 6) m |= 1ull << (cx | (cy << 2) | (cz << 4));
+                    }
+                p.at(L - 1, bx, by, bz) = m;
+            }
+    pyramid_reduce(p);
+    pyramid_emit(p, dim, [&](int x, int y, int z) {
+        return (uint8_t)map[(size_t)x + (size_t)dim * ((size_t)y + (size_t)dim * (size_t)z)];
+    }, out);
+    return true;
+}
+
+bool vr_native_from_ref(const uint64_t *desc, uint64_t len, uint64_t root_index, int dim, const int8_t *types,
+                        vr_native_tree &out) {
+    if (!desc || root_index >= len || dim < 2 || !is_pow2(dim)) return false;
+    Pyramid p;
+    pyramid_init(p, dim);
+    const int L = p.levels;
+    bool ok = true;
+    std::function<void(uint64_t, int, int, int, int)> walk = [&](uint64_t idx, int ox, int oy, int oz, int size) {
+        const uint64_t cd = desc[idx];
+        const int h = size / 2;
+        for (int i = 0; i < 8; i++) {
+            if (!((cd >> (16 + i)) & 1ull)) continue;
+            const int cx = ox + (i & 1) * h, cy = oy + ((i >> 1) & 1) * h, cz = oz + ((i >> 2) & 1) * h;
+            if (((cd >> (24 + i)) & 1ull) || h == 1) {       /* solid leaf cube of edge h */
+                for (int z = cz; z < cz + h; z++)
+                    for (int y = cy; y < cy + h; y++)
+                        for (int x = cx; x < cx + h; x++)
+                            p.at(L - 1, x >> 2, y >> 2, z >> 2) |= 1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+                continue;
+            }
+            const uint64_t count = (uint64_t)__builtin_popcountll((cd >> 16) & ((2ull << i) - 1ull)) - 1ull;
+            uint64_t child;
+            if (cd & 0x8000ull) {
+                const uint64_t far = idx + (cd & 0x7fffull);
+                if (far >= len) { ok = false; return; }
+                child = desc[far] + count;
+            } else {
+                child = idx + (cd & 0x7fffull) + count;
+            }
+            if (child >= len) { ok = false; return; }
+            walk(child, cx, cy, cz, h);
+        }
+    };
+    walk(root_index, 0, 0, 0, dim);
+    if (!ok) return false;
+    pyramid_reduce(p);
+    pyramid_emit(p, dim, [&](int x, int y, int z) -> uint8_t {
+        if (!types) return 5;
+        const int8_t v = types[(size_t)x + (size_t)dim * ((size_t)y + (size_t)dim * (size_t)z)];
+        return (v == 5 || v == 6) ? (uint8_t)v : (uint8_t)5;
+    }, out);
+    return true;
+}
+
+int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shift) {
+    int s = 2 * (t.levels - 1);
+    uint32_t idx = 0;
+    for (;;) {
+        const vr_node &n = t.nodes[idx];
+        const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
+        const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
+        if (!((m >> ci) & 1ull)) { if (cell_shift) *cell_shift = s; return 0; }
+        const uint32_t rank = (uint32_t)__builtin_popcountll(m & ((1ull << ci) - 1ull));
+        if (s == 0) { if (cell_shift) *cell_shift = 0; return (int)(int8_t)t.leaf_types[n.child_base + rank]; }
+        idx = n.child_base + rank;
+        s -= 2;
+    }
+}

@@ -1,0 +1,448 @@
+/*
+ * vr_trace.h -- per-pixel ray casting core of the B200 caster (device code; also compilable for the
+ * host so tests/host_emu can single-step the same logic without a GPU -- the product never runs it
+ * on the CPU).
+ *
+ * What it computes is the reference kernel `raycaster` (kernels/ray_caster_kernel.cl:256-724):
+ * ray fetch + camera rotation, Amanatides-Woo DDA, hit UV, atlas fetch, Blinn-Phong `view_light`,
+ * shadow / reflection redirect inside the same loop, fog, RGBA8 store.  How it does it is new:
+ *   - all frame-uniform work (sin/cos, the get_oct_vox camera-cell bias) is hoisted to the host;
+ *   - the dense variant walks the char map exactly like kernel:555-570;
+ *   - the SVO variant replaces the per-step `map[]` gather by a lookup in a 16-byte-node 64-tree
+ *     whose empty cells are cached, so that steps inside a known-empty cell touch no memory, while
+ *     the float state (intersection_t) is advanced by exactly the same additions as the reference
+ *     -- every pixel, hit voxel, face and step count is bit-identical to the dense walk.
+ *
+ * Float discipline: every arithmetic op that feeds a compare, an index or the colour goes through
+ * VR_ADD/VR_MUL/... (round-to-nearest intrinsics on the device, never FMA-contracted) so the result
+ * does not depend on -fmad; division and sqrt are IEEE (__fdiv_rn/__fsqrt_rn).
+ */
+#ifndef VR_TRACE_H
+#define VR_TRACE_H
+
+#include "vr_types.h"
+#include <math.h>
+
+#if defined(__CUDA_ARCH__)
+#define VR_ADD(a, b) __fadd_rn((a), (b))
+#define VR_SUB(a, b) __fsub_rn((a), (b))
+#define VR_MUL(a, b) __fmul_rn((a), (b))
+#define VR_DIV(a, b) __fdiv_rn((a), (b))
+#define VR_SQRT(a) __fsqrt_rn((a))
+#define VR_POPC64(x) __popcll((x))
+#else
+#define VR_ADD(a, b) ((a) + (b))
+#define VR_SUB(a, b) ((a) - (b))
+#define VR_MUL(a, b) ((a) * (b))
+#define VR_DIV(a, b) ((a) / (b))
+#define VR_SQRT(a) sqrtf((a))
+#define VR_POPC64(x) __builtin_popcountll((x))
+#endif
+
+struct vf3 { float x, y, z; };
+struct vf4 { float x, y, z, w; };
+struct vi3 { int x, y, z; };
+
+VR_HD vf3 vr_add3(vf3 a, vf3 b) { return {VR_ADD(a.x, b.x), VR_ADD(a.y, b.y), VR_ADD(a.z, b.z)}; }
+VR_HD vf3 vr_sub3(vf3 a, vf3 b) { return {VR_SUB(a.x, b.x), VR_SUB(a.y, b.y), VR_SUB(a.z, b.z)}; }
+VR_HD vf3 vr_i2f3(vi3 a) { return {(float)a.x, (float)a.y, (float)a.z}; }
+VR_HD float vr_dot(vf3 a, vf3 b) { return VR_ADD(VR_ADD(VR_MUL(a.x, b.x), VR_MUL(a.y, b.y)), VR_MUL(a.z, b.z)); }
+VR_HD float vr_length(vf3 a) { return VR_SQRT(vr_dot(a, a)); }
+VR_HD vf3 vr_normalize(vf3 a) { float l = vr_length(a); return {VR_DIV(a.x, l), VR_DIV(a.y, l), VR_DIV(a.z, l)}; }
+VR_HD float vr_max(float x, float y) { return (x < y) ? y : x; }      /* OpenCL max(), NaN -> x */
+VR_HD float vr_min(float x, float y) { return (y < x) ? y : x; }
+VR_HD int vr_sign(float d) { return (d > 0.0f) - (d < 0.0f); }
+VR_HD bool vr_any_zero(vf3 d) { return d.x == 0.0f || d.y == 0.0f || d.z == 0.0f; }
+VR_HD int vr_f2i_rz(float v) {                                        /* convert_int, pinned */
+    if (!(v > -2147483648.0f && v < 2147483648.0f)) return 0;
+    return (int)v;
+}
+VR_HD uint32_t vr_unorm8(float c) {                                   /* write_imagef, kernel:717 */
+    float v = VR_MUL(c, 255.0f);
+    if (!(v > 0.0f)) return 0u;
+    if (v > 255.0f) v = 255.0f;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__float2int_rn(v);
+#else
+    return (uint32_t)nearbyintf(v);
+#endif
+}
+
+/* Everything the reference keeps in private variables across loop iterations (kernel:298-337). */
+struct RayState {
+    vf3 ray_dir;
+    vi3 step;            /* voxel_step */
+    vi3 voxel;
+    vf3 delta;           /* delta_t */
+    vf3 t;               /* intersection_t */
+    int dist;            /* distance_traveled */
+    int max_distance;
+    int bounce;          /* bounce_count */
+    int fm;              /* face_mask, bit0 x, bit1 y, bit2 z */
+    vf3 voxel_color;     /* .w stays 0 (kernel:690 subtracts 0) */
+    vf4 color;           /* color_accumulator */
+    float fog_distance;
+    bool shadow;         /* shadow_ray */
+};
+
+/* kernel:276-337 + 353.  Returns false when the pixel is skipped (kernel:293). */
+VR_HD bool vr_ray_setup(const vr_frame_params &P, int x, int y, RayState &r) {
+#if defined(__CUDA_ARCH__)
+    const float4 rt = __ldg(reinterpret_cast<const float4 *>(P.ray_table) + ((size_t)x + (size_t)P.width * (size_t)y));
+    vf3 d = {rt.x, rt.y, rt.z};
+#else
+    const float *rt = P.ray_table + 4 * ((size_t)x + (size_t)P.width * (size_t)y);
+    vf3 d = {rt[0], rt[1], rt[2]};
+#endif
+    const float sp = P.trig[0], cp = P.trig[1], sy = P.trig[2], cy = P.trig[3];
+    d = {VR_ADD(VR_MUL(d.z, sp), VR_MUL(d.x, cp)), d.y, VR_SUB(VR_MUL(d.z, cp), VR_MUL(d.x, sp))};   /* pitch */
+    d = {VR_SUB(VR_MUL(d.x, cy), VR_MUL(d.y, sy)), VR_ADD(VR_MUL(d.x, sy), VR_MUL(d.y, cy)), d.z};   /* yaw */
+    r.ray_dir = d;
+    if (vr_any_zero(d)) return false;
+
+    r.step = {vr_sign(d.x), vr_sign(d.y), vr_sign(d.z)};
+    const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
+    const vf3 fl = {floorf(cam.x), floorf(cam.y), floorf(cam.z)};
+    r.voxel = {(int)fl.x, (int)fl.y, (int)fl.z};
+    r.delta = {fabsf(VR_DIV(1.0f, d.x)), fabsf(VR_DIV(1.0f, d.y)), fabsf(VR_DIV(1.0f, d.z))};
+    vf3 off = {VR_MUL(r.delta.x, VR_SUB(cam.x, fl.x)), VR_MUL(r.delta.y, VR_SUB(cam.y, fl.y)),
+               VR_MUL(r.delta.z, VR_SUB(cam.z, fl.z))};
+    /* t = off * -step; where t < 0: t += delta (kernel:317-323) */
+    vf3 t = {VR_MUL(off.x, -(float)r.step.x), VR_MUL(off.y, -(float)r.step.y), VR_MUL(off.z, -(float)r.step.z)};
+    if (t.x < 0.0f) t.x = VR_ADD(t.x, r.delta.x);
+    if (t.y < 0.0f) t.y = VR_ADD(t.y, r.delta.y);
+    if (t.z < 0.0f) t.z = VR_ADD(t.z, r.delta.z);
+    /* get_oct_vox start bias (kernel:353-354), frame-uniform, host evaluated */
+    r.t = {VR_ADD(t.x, P.bias[0]), VR_ADD(t.y, P.bias[1]), VR_ADD(t.z, P.bias[2])};
+
+    r.dist = 0;
+    r.max_distance = P.max_distance;
+    r.bounce = 0;
+    r.fm = 0;
+    r.voxel_color = {0.0f, 0.0f, 0.0f};
+    r.color = {0.0f, 0.0f, 0.0f, 0.0f};
+    r.fog_distance = 0.0f;
+    r.shadow = false;
+    return true;
+}
+
+/* kernel:558-560: one DDA step; ties step every tied axis. */
+VR_HD void vr_dda_step(RayState &r) {
+    const int mx = (r.t.x <= vr_min(r.t.y, r.t.z)) ? 1 : 0;
+    const int my = (r.t.y <= vr_min(r.t.z, r.t.x)) ? 1 : 0;
+    const int mz = (r.t.z <= vr_min(r.t.x, r.t.y)) ? 1 : 0;
+    r.fm = mx | (my << 1) | (mz << 2);
+    r.t.x = VR_ADD(r.t.x, VR_MUL(r.delta.x, (float)mx));
+    r.t.y = VR_ADD(r.t.y, VR_MUL(r.delta.y, (float)my));
+    r.t.z = VR_ADD(r.t.z, VR_MUL(r.delta.z, (float)mz));
+    r.voxel.x += r.step.x * mx;
+    r.voxel.y += r.step.y * my;
+    r.voxel.z += r.step.z * mz;
+}
+
+/* kernel:563-568: the ray left the map. */
+VR_HD void vr_out_of_bounds(RayState &r) {
+    r.voxel.x -= r.step.x * (r.fm & 1);
+    r.voxel.y -= r.step.y * ((r.fm >> 1) & 1);
+    r.voxel.z -= r.step.z * ((r.fm >> 2) & 1);
+    const float m = VR_SUB(1.0f, vr_max(VR_DIV((float)r.dist, 700.0f), 0.0f));
+    r.color = {VR_MUL(r.voxel_color.x, m), VR_MUL(r.voxel_color.y, m), VR_MUL(r.voxel_color.z, m), VR_MUL(0.0f, m)};
+    r.color.w = VR_MUL(r.color.w, 4.0f);
+}
+
+/* kernel:652-656 / 684-688 */
+VR_HD vf3 vr_atlas_fetch(const vr_frame_params &P, float u, float v, int tile_x, int tile_y, bool &clamped) {
+    const int px = vr_f2i_rz(VR_MUL(u, (float)P.atlas_scale[0])) + vr_f2i_rz(VR_MUL((float)tile_x, (float)P.atlas_scale[0]));
+    const int py = vr_f2i_rz(VR_MUL(v, (float)P.atlas_scale[1])) + vr_f2i_rz(VR_MUL((float)tile_y, (float)P.atlas_scale[1]));
+    const int cx = px < 0 ? 0 : (px > P.atlas_dim[0] - 1 ? P.atlas_dim[0] - 1 : px);
+    const int cy = py < 0 ? 0 : (py > P.atlas_dim[1] - 1 ? P.atlas_dim[1] - 1 : py);
+    clamped = (cx != px) || (cy != py);
+#if defined(__CUDA_ARCH__)
+    const uchar4 c = tex2D<uchar4>((cudaTextureObject_t)P.atlas_tex, (float)cx + 0.5f, (float)cy + 0.5f);
+    return {VR_DIV((float)c.x, 255.0f), VR_DIV((float)c.y, 255.0f), VR_DIV((float)c.z, 255.0f)};
+#else
+    const uint8_t *c = P.atlas + 4 * ((size_t)cx + (size_t)P.atlas_dim[0] * (size_t)cy);
+    return {VR_DIV((float)c[0], 255.0f), VR_DIV((float)c[1], 255.0f), VR_DIV((float)c[2], 255.0f)};
+#endif
+}
+
+/* kernel:78-99 */
+VR_HD vf4 vr_view_light(vf3 in_color, vf3 light, const float *rgbi, vf3 view, vi3 mask) {
+    if (light.x == 0.0f && light.y == 0.0f && light.z == 0.0f) return {0.0f, 0.0f, 0.0f, 0.0f};
+    float d = VR_MUL(vr_length(light), 0.01f);
+    d = VR_MUL(d, d);
+    const vf3 nmask = vr_normalize(vr_i2f3(mask));
+    const vf3 nlight = vr_normalize(light);
+    const float diffuse = vr_max(vr_dot(nmask, nlight), 0.1f);
+    float specular = 0.0f;
+    if (diffuse > 0.0f) {
+        const vf3 halfway = vr_normalize(vr_add3(nlight, vr_normalize(view)));
+        specular = vr_max(vr_dot(nmask, halfway), 0.0f);               /* pow(x, 1) */
+    }
+    vf4 o;
+    o.x = VR_ADD(in_color.x, VR_ADD(VR_MUL(diffuse, rgbi[0]), VR_DIV(VR_MUL(specular, rgbi[0]), d)));
+    o.y = VR_ADD(in_color.y, VR_ADD(VR_MUL(diffuse, rgbi[1]), VR_DIV(VR_MUL(specular, rgbi[1]), d)));
+    o.z = VR_ADD(in_color.z, VR_ADD(VR_MUL(diffuse, rgbi[2]), VR_DIV(VR_MUL(specular, rgbi[2]), d)));
+    o.w = VR_ADD(0.0f, VR_ADD(VR_MUL(diffuse, rgbi[3]), VR_DIV(VR_MUL(specular, rgbi[3]), d)));
+    return o;
+}
+
+/* kernel:674-679 / 697-702: restart the DDA from hit_pos along r.ray_dir with the given step. */
+VR_HD void vr_restart_dda(RayState &r, vf3 hit_pos, vi3 new_step) {
+    r.voxel.x -= r.step.x * (r.fm & 1);
+    r.voxel.y -= r.step.y * ((r.fm >> 1) & 1);
+    r.voxel.z -= r.step.z * ((r.fm >> 2) & 1);
+    r.step = new_step;
+    r.delta = {fabsf(VR_DIV(1.0f, r.ray_dir.x)), fabsf(VR_DIV(1.0f, r.ray_dir.y)), fabsf(VR_DIV(1.0f, r.ray_dir.z))};
+    vf3 t = {VR_MUL(VR_MUL(r.delta.x, VR_SUB(hit_pos.x, floorf(hit_pos.x))), (float)r.step.x),
+             VR_MUL(VR_MUL(r.delta.y, VR_SUB(hit_pos.y, floorf(hit_pos.y))), (float)r.step.y),
+             VR_MUL(VR_MUL(r.delta.z, VR_SUB(hit_pos.z, floorf(hit_pos.z))), (float)r.step.z)};
+    if (t.x < 0.0f) t.x = VR_ADD(t.x, r.delta.x);
+    if (t.y < 0.0f) t.y = VR_ADD(t.y, r.delta.y);
+    if (t.z < 0.0f) t.z = VR_ADD(t.z, r.delta.z);
+    r.t = t;
+}
+
+/* kernel:575-711, entered when the voxel just stepped into holds 5 or 6.
+ * Returns -1 to continue the loop (ray was redirected), or the terminal VR_ST_* code. */
+template <bool AUX>
+VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr_aux *a, bool &first_hit_done) {
+    if (AUX && !first_hit_done) {
+        first_hit_done = true;
+        a->hit[0] = r.voxel.x; a->hit[1] = r.voxel.y; a->hit[2] = r.voxel.z;
+        a->face = (uint8_t)(r.fm | ((r.step.x < 0) << 3) | ((r.step.y < 0) << 4) | ((r.step.z < 0) << 5));
+        a->hit_type = (uint8_t)voxel_data;
+        a->steps_first = (uint32_t)r.dist;
+    }
+    vf3 fp = {0.0f, 0.0f, 0.0f};     /* face_position */
+    float tu = 0.0f, tv = 0.0f;       /* tile_face_position */
+    vf3 sgn = {1.0f, 1.0f, 1.0f};
+    if (r.fm & 1) {                   /* kernel:586 */
+        sgn.x = -1.0f;
+        const float tc = VR_SUB(r.t.x, r.delta.x);
+        const float zp = VR_DIV(VR_SUB(r.t.z, tc), r.delta.z);
+        const float yp = VR_DIV(VR_SUB(r.t.y, tc), r.delta.y);
+        fp = {1.00001f, yp, zp}; tu = yp; tv = zp;
+    } else if (r.fm & 2) {            /* kernel:601 */
+        sgn.y = -1.0f;
+        const float tc = VR_SUB(r.t.y, r.delta.y);
+        const float xp = VR_DIV(VR_SUB(r.t.x, tc), r.delta.x);
+        const float zp = VR_DIV(VR_SUB(r.t.z, tc), r.delta.z);
+        fp = {xp, 1.00001f, zp}; tu = xp; tv = zp;
+    } else if (r.fm & 4) {            /* kernel:610 */
+        sgn.z = -1.0f;
+        const float tc = VR_SUB(r.t.z, r.delta.z);
+        const float xp = VR_DIV(VR_SUB(r.t.x, tc), r.delta.x);
+        const float yp = VR_DIV(VR_SUB(r.t.y, tc), r.delta.y);
+        fp = {xp, yp, 1.00001f}; tu = xp; tv = yp;
+    }
+    /* kernel:626-643 */
+    if (r.ray_dir.x > 0.0f) fp.x = VR_ADD(-fp.x, 1.0f);
+    if (r.ray_dir.x < 0.0f) tu = VR_ADD(-tu, 1.0f);
+    if (r.ray_dir.y > 0.0f) {
+        fp.y = VR_ADD(-fp.y, 1.0f);
+    } else {
+        tu = VR_SUB(1.0f, tu);
+        if (r.fm & 4) { tu = VR_SUB(1.0f, tu); tv = VR_SUB(1.0f, tv); }
+    }
+    if (r.ray_dir.z > 0.0f) fp.z = VR_ADD(-fp.z, 1.0f);
+    if (r.ray_dir.z < 0.0f) tv = VR_ADD(-tv, 1.0f);
+
+    const vf3 hit_pos = vr_add3(vr_i2f3(r.voxel), fp);
+    const vf3 L = {P.light_pos[0], P.light_pos[1], P.light_pos[2]};
+
+    if (voxel_data == 5 && !r.shadow) {                                  /* kernel:649 */
+        r.shadow = true;
+        bool clamped;
+        const vf3 tex = vr_atlas_fetch(P, tu, tv, 5, 0, clamped);
+        if (AUX) a->flags |= VR_FL_LIT | (clamped ? VR_FL_ATLAS_CLAMP : 0);
+        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_DIV(tex.x, 2.0f));
+        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_DIV(tex.y, 2.0f));
+        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_DIV(tex.z, 2.0f));
+        const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
+        const vi3 nrm = {(r.fm & 1) * r.step.x, ((r.fm >> 1) & 1) * r.step.y, ((r.fm >> 2) & 1) * r.step.z};
+        r.color = vr_view_light(r.voxel_color, vr_sub3(hit_pos, L), P.light_rgbi, vr_sub3(hit_pos, cam), nrm);
+        r.fog_distance = (float)r.dist;
+        r.max_distance = (int)VR_ADD((float)r.dist, vr_length(vr_sub3(vr_i2f3(r.voxel), L)));   /* kernel:667 */
+        r.ray_dir = vr_normalize(vr_sub3(L, hit_pos));
+        if (vr_any_zero(r.ray_dir)) return VR_ST_SKIP_REDIRECT;          /* kernel:671 */
+        vr_restart_dda(r, hit_pos, {vr_sign(r.ray_dir.x), vr_sign(r.ray_dir.y), vr_sign(r.ray_dir.z)});
+        return -1;
+    }
+    if (voxel_data == 6 && !r.shadow) {                                  /* kernel:682 */
+        bool clamped;
+        const vf3 tex = vr_atlas_fetch(P, tu, tv, 3, 4, clamped);
+        if (AUX) a->flags |= VR_FL_REFLECTED | (clamped ? VR_FL_ATLAS_CLAMP : 0);
+        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_DIV(tex.x, 4.0f));
+        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_DIV(tex.y, 4.0f));
+        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_DIV(tex.z, 4.0f));
+        r.ray_dir = {VR_MUL(r.ray_dir.x, sgn.x), VR_MUL(r.ray_dir.y, sgn.y), VR_MUL(r.ray_dir.z, sgn.z)};
+        if (vr_any_zero(r.ray_dir)) return VR_ST_SKIP_REDIRECT;          /* kernel:694 */
+        vr_restart_dda(r, hit_pos, {1, 1, 1});                           /* kernel:698 precedence: always +1 */
+        r.bounce += 1;
+        return -1;
+    }
+    r.color.w = 0.1f;                                                    /* kernel:708 */
+    return VR_ST_SHADOW_HIT;
+}
+
+/* kernel:716-721.  Packs RGBA8 little-endian (R in the low byte). */
+VR_HD uint32_t vr_epilogue(const RayState &r) {
+    const float m = VR_SUB(1.0f, vr_max(VR_DIV(r.fog_distance, 700.0f), 0.0f));
+    return vr_unorm8(VR_MUL(r.color.x, m)) | (vr_unorm8(VR_MUL(r.color.y, m)) << 8) |
+           (vr_unorm8(VR_MUL(r.color.z, m)) << 16) | (vr_unorm8(VR_MUL(r.color.w, m)) << 24);
+}
+
+VR_HD void vr_aux_init(vr_aux *a, const vr_frame_params &P) {
+    a->hit[0] = a->hit[1] = a->hit[2] = -1;
+    a->face = 0; a->status = 0; a->flags = 0; a->hit_type = 0;
+    a->steps_first = 0; a->steps_total = 0; a->node_fetches = 0; a->lookups = 0;
+    if (P.cam_pos[0] == floorf(P.cam_pos[0]) || P.cam_pos[1] == floorf(P.cam_pos[1]) ||
+        P.cam_pos[2] == floorf(P.cam_pos[2]))
+        a->flags |= VR_FL_FRAC0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense variant: kernel:357 loop with the `else` branch (kernel:555-570).
+ * Returns true if the pixel must be written (packed colour in *rgba_out).
+ * ------------------------------------------------------------------------------------------- */
+template <bool AUX>
+VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a) {
+    RayState r;
+    if (AUX) vr_aux_init(a, P);
+    if (!vr_ray_setup(P, x, y, r)) {
+        if (AUX) a->status = VR_ST_SKIP_PRIMARY;
+        return false;
+    }
+    const int X = P.dim[0], Y = P.dim[1], Z = P.dim[2];
+    bool first_hit_done = false;
+    int status = VR_ST_MAXDIST;
+    while (r.dist < r.max_distance && r.bounce < 2) {
+        vr_dda_step(r);
+        if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
+        if (r.voxel.x >= X || r.voxel.y >= Y || r.voxel.z >= Z || r.voxel.x < 0 || r.voxel.y < 0 || r.voxel.z < 0) {
+            vr_out_of_bounds(r);
+            status = VR_ST_OOB;
+            break;
+        }
+        const int voxel_data =
+            (int)P.map[(size_t)r.voxel.x + (size_t)X * ((size_t)r.voxel.y + (size_t)Z * (size_t)r.voxel.z)];
+        if (voxel_data == 5 || voxel_data == 6) {
+            const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
+            if (st == VR_ST_SKIP_REDIRECT) {
+                if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
+                return false;
+            }
+            if (st >= 0) { status = st; break; }
+        }
+        r.dist++;
+    }
+    if (status == VR_ST_MAXDIST && r.bounce >= 2) status = VR_ST_BOUNCES;
+    if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
+    *rgba_out = vr_epilogue(r);
+    return true;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * SVO variant.  Same loop, but `map[voxel]` is answered by the 64-tree:
+ *   - the empty cell (edge 1<<cs at origin co) found by the last lookup is cached; a step that
+ *     stays inside it needs no lookup, no bounds test and no memory access;
+ *   - a lookup resumes from the lowest stacked ancestor that still contains the new voxel
+ *     (XOR of the coordinates gives the level), then descends one 16-byte node per two octree
+ *     levels until it meets an empty slot (new cached cell) or a set voxel bit (hit).
+ * Stack: node indices per level, provided by the caller (shared memory on the device).
+ * Requires a cubic power-of-two map so that cells never straddle the map boundary.
+ * ------------------------------------------------------------------------------------------- */
+struct vr_node_regs { unsigned long long mask; uint32_t base; };
+
+VR_HD vr_node_regs vr_load_node(const vr_frame_params &P, uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.nodes) + idx);          /* one 128-bit load */
+    return {(unsigned long long)v.x | ((unsigned long long)v.y << 32), v.z};
+#else
+    const vr_node &n = P.nodes[idx];
+    return {(unsigned long long)n.mask_lo | ((unsigned long long)n.mask_hi << 32), n.child_base};
+#endif
+}
+
+template <bool AUX, class Stack>
+VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
+    RayState r;
+    if (AUX) vr_aux_init(a, P);
+    if (!vr_ray_setup(P, x, y, r)) {
+        if (AUX) a->status = VR_ST_SKIP_PRIMARY;
+        return false;
+    }
+    const int N = P.dim[0];
+    /* current node of the descent */
+    int s = P.root_shift;                 /* child shift of the current node */
+    int level = 0;
+    vr_node_regs node = vr_load_node(P, 0);
+    stk.set(0, 0u);
+    vi3 nv = {0, 0, 0};                   /* a voxel inside the current node */
+    if (AUX) a->node_fetches = 1;
+    /* cached empty cell */
+    int cs = -1;
+    vi3 co = {0, 0, 0};
+
+    bool first_hit_done = false;
+    int status = VR_ST_MAXDIST;
+    while (r.dist < r.max_distance && r.bounce < 2) {
+        vr_dda_step(r);
+        if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
+        const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
+        if (cs < 0 || (cx >> cs) != 0) {
+            /* left the cached cell */
+            if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N ||
+                (unsigned)r.voxel.z >= (unsigned)N) {
+                vr_out_of_bounds(r);
+                status = VR_ST_OOB;
+                break;
+            }
+            if (AUX) a->lookups++;
+            /* pop to the lowest ancestor containing the voxel */
+            const int nx = (r.voxel.x ^ nv.x) | (r.voxel.y ^ nv.y) | (r.voxel.z ^ nv.z);
+            if ((nx >> (s + 2)) != 0) {
+                do { s += 2; level--; } while ((nx >> (s + 2)) != 0);
+                node = vr_load_node(P, stk.get(level));
+                if (AUX) a->node_fetches++;
+            }
+            nv = r.voxel;
+            int voxel_data = 0;
+            for (;;) {
+                const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
+                if (!((node.mask >> ci) & 1ull)) {                       /* empty slot: cache the cell */
+                    cs = s;
+                    co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
+                    break;
+                }
+                const uint32_t rank = (uint32_t)VR_POPC64(node.mask & ((1ull << ci) - 1ull));
+                if (s == 0) {                                            /* a set voxel bit */
+                    voxel_data = (int)(int8_t)P.leaf_types[node.base + rank];
+                    break;
+                }
+                const uint32_t child = node.base + rank;
+                level++;
+                s -= 2;
+                stk.set(level, child);
+                node = vr_load_node(P, child);
+                if (AUX) a->node_fetches++;
+            }
+            if (voxel_data == 5 || voxel_data == 6) {
+                const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
+                if (st == VR_ST_SKIP_REDIRECT) {
+                    if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
+                    return false;
+                }
+                if (st >= 0) { status = st; break; }
+            }
+        }
+        r.dist++;
+    }
+    if (status == VR_ST_MAXDIST && r.bounce >= 2) status = VR_ST_BOUNCES;
+    if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
+    *rgba_out = vr_epilogue(r);
+    return true;
+}
+
+#endif

@@ -1,0 +1,90 @@
+/*
+ * vr_types.h -- plain-old-data shared by the host runtime and the device kernels.
+ *
+ * Replaces the 16 positional OpenCL kernel arguments bound by CLCaster::validate
+ * (reference src/CLCaster.cpp:186-202 <-> kernels/ray_caster_kernel.cl:256-273) with one
+ * launch-constant parameter block.
+ */
+#ifndef VR_TYPES_H
+#define VR_TYPES_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VR_HD __host__ __device__ __forceinline__
+#else
+#define VR_HD inline
+#endif
+
+/* 64-tree node, 16 bytes, read with one 128-bit load.
+ * A node at shift s covers a (4<<s)^3 voxel cube split into 4x4x4 children of edge (1<<s).
+ * Child slot ci = cx | cy<<2 | cz<<4.  Bit ci of `mask` = child is non-empty.
+ *   s > 0 : children are nodes, stored contiguously in ascending set-bit order at
+ *           nodes[child_base + popcount(mask & ((1<<ci)-1))].
+ *   s == 0: children are voxels; voxel type at leaf_types[child_base + popcount(...)].
+ * Two levels of the reference's 2^3 / 8-byte child descriptors (kernel:49-54, Octree.h:89-94)
+ * collapse into one node: same bytes per level, half the dependent loads. */
+typedef struct vr_node {
+    uint32_t mask_lo;
+    uint32_t mask_hi;
+    uint32_t child_base;
+    uint32_t aux;          /* reserved (solid-subtree mask table index); 0 */
+} vr_node;
+
+/* Per-pixel auxiliary record (32 bytes), layout-identical to the oracle's vro_aux. */
+typedef struct vr_aux {
+    int32_t hit[3];
+    uint8_t face;
+    uint8_t status;
+    uint8_t flags;
+    uint8_t hit_type;
+    uint32_t steps_first;
+    uint32_t steps_total;
+    uint32_t node_fetches;   /* 16-byte node loads issued for this pixel (SVO kernels) */
+    uint32_t lookups;        /* octree lookups (cell changes) for this pixel          */
+} vr_aux;
+
+enum {
+    VR_ST_SKIP_PRIMARY = 0, VR_ST_OOB = 1, VR_ST_MAXDIST = 2, VR_ST_SHADOW_HIT = 3,
+    VR_ST_SKIP_REDIRECT = 4, VR_ST_BOUNCES = 5
+};
+enum { VR_FL_LIT = 1, VR_FL_REFLECTED = 2, VR_FL_TIE = 4, VR_FL_ATLAS_CLAMP = 8, VR_FL_FRAC0 = 16 };
+
+#define VR_MAX_LEVELS 8          /* 64-tree levels: dimension up to 4^8 = 65536 */
+
+typedef struct vr_frame_params {
+    /* viewport */
+    int32_t width, height;
+    /* multi-GPU screen-tile split: the frame is cut into row bands of band_rows rows; band b
+     * belongs to this launch iff b % band_stride == band_first.  The launch renders local_rows
+     * rows into a compact slab: local row ly -> frame row
+     * ((ly / band_rows) * band_stride + band_first) * band_rows + ly % band_rows. */
+    int32_t local_rows, band_rows, band_stride, band_first;
+    const float *ray_table;        /* float4 per pixel (kernel arg 3)                        */
+    uint8_t *image;                /* RGBA8, row pitch width*4; local slab when banded       */
+    vr_aux *aux;                   /* optional                                               */
+    /* dense map (args 0,1) */
+    const int8_t *map;
+    int32_t dim[3];
+    /* camera (args 4,5): trig = sinf/cosf of (inclination, azimuth), host evaluated          */
+    float cam_pos[3];
+    float trig[4];
+    float bias[3];                 /* get_oct_vox start bias (kernel:353), host evaluated     */
+    /* light 0 (arg 6): rgbi + position                                                       */
+    float light_rgbi[4];
+    float light_pos[3];
+    /* atlas (args 9-11) */
+    unsigned long long atlas_tex;  /* cudaTextureObject_t                                     */
+    const uint8_t *atlas;          /* same texels, linear RGBA8 (host emulation + fallback)   */
+    int32_t atlas_dim[2];
+    int32_t atlas_scale[2];        /* atlas_dim / tile_dim, integer (kernel:654)              */
+    /* settings */
+    int32_t max_distance;          /* kernel:326                                              */
+    /* native 64-tree */
+    const vr_node *nodes;
+    const uint8_t *leaf_types;
+    int32_t root_shift;            /* child shift of the root node = 2*(levels-1)             */
+    int32_t levels;
+} vr_frame_params;
+
+#endif
