@@ -365,6 +365,17 @@ VR_HD vr_node_regs vr_load_node(const vr_frame_params &P, uint32_t idx) {
 #endif
 }
 
+/* Packed per-axis exit counters of the in-cell walk: field a (10 bits at 0/10/20) holds
+ * 512 - (crossings of axis a still needed to leave the cached cell); a field reaching 512 sets its
+ * guard bit (9/19/29).  Cells wider than 512 voxels are clamped: the walk then "leaves" early and the
+ * lookup simply finds the same cell again. */
+#define VR_CNT_GUARD 0x20080200u
+
+VR_HD int vr_exit_count(int step, int voxel, int origin, int size) {
+    const int r = step > 0 ? origin + size - voxel : voxel - origin + 1;
+    return r > 512 ? 512 : r;
+}
+
 template <bool AUX, class Stack>
 VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
     RayState r;
@@ -381,61 +392,106 @@ VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_o
     stk.set(0, 0u);
     vi3 nv = {0, 0, 0};                   /* a voxel inside the current node */
     if (AUX) a->node_fetches = 1;
-    /* cached empty cell */
-    int cs = -1;
-    vi3 co = {0, 0, 0};
+    /* cached empty cell (edge 1 << cs at origin co).  Initially the camera voxel itself: the reference
+     * steps before it loads (kernel:555-570), so that voxel is never tested. */
+    int cs = 0;
+    vi3 co = r.voxel;
 
     bool first_hit_done = false;
     int status = VR_ST_MAXDIST;
     while (r.dist < r.max_distance && r.bounce < 2) {
-        vr_dda_step(r);
-        if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
-        const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
-        if (cs < 0 || (cx >> cs) != 0) {
-            /* left the cached cell */
-            if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N ||
-                (unsigned)r.voxel.z >= (unsigned)N) {
-                vr_out_of_bounds(r);
-                status = VR_ST_OOB;
+        /* ---- (1) walk inside the cached cell: kernel:558-560 without the map load.  Only the float
+         * state and three packed exit counters are live; no memory access, no bounds test. */
+        {
+            const int S = 1 << cs;
+            uint32_t cnt = (uint32_t)(512 - vr_exit_count(r.step.x, r.voxel.x, co.x, S)) |
+                           ((uint32_t)(512 - vr_exit_count(r.step.y, r.voxel.y, co.y, S)) << 10) |
+                           ((uint32_t)(512 - vr_exit_count(r.step.z, r.voxel.z, co.z, S)) << 20);
+            const uint32_t cnt0 = cnt;
+            const vf3 t0 = r.t;
+            const int nmax = r.max_distance - r.dist;
+            float tx = r.t.x, ty = r.t.y, tz = r.t.z;
+            int n = 0;
+            do {
+                const bool px = tx <= fminf(ty, tz);
+                const bool py = ty <= fminf(tz, tx);
+                const bool pz = tz <= fminf(tx, ty);
+                if (px) { tx = VR_ADD(tx, r.delta.x); cnt += 1u; }
+                if (py) { ty = VR_ADD(ty, r.delta.y); cnt += 1u << 10; }
+                if (pz) { tz = VR_ADD(tz, r.delta.z); cnt += 1u << 20; }
+                n++;
+            } while (!(cnt & VR_CNT_GUARD) && n < nmax);
+            const int ax = (int)(cnt & 1023u) - (int)(cnt0 & 1023u);
+            const int ay = (int)((cnt >> 10) & 1023u) - (int)((cnt0 >> 10) & 1023u);
+            const int az = (int)((cnt >> 20) & 1023u) - (int)((cnt0 >> 20) & 1023u);
+            bool exited;
+            if (ax + ay + az == n) {
+                /* one axis per step: the guard bits name the face crossed by the last step */
+                r.t = {tx, ty, tz};
+                r.voxel.x += r.step.x * ax;
+                r.voxel.y += r.step.y * ay;
+                r.voxel.z += r.step.z * az;
+                exited = (cnt & VR_CNT_GUARD) != 0u;
+                r.fm = (int)(((cnt >> 9) & 1u) | ((cnt >> 18) & 2u) | ((cnt >> 27) & 4u));
+                r.dist += exited ? n - 1 : n;
+            } else {
+                /* some step moved along two or three axes at once (exact tie of intersection_t): redo the
+                 * cell with the literal step that tracks the full face mask */
+                r.t = t0;
+                exited = false;
+                for (;;) {
+                    vr_dda_step(r);
+                    if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
+                    const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
+                    if ((cx >> cs) != 0) { exited = true; break; }
+                    r.dist++;
+                    if (!(r.dist < r.max_distance)) break;
+                }
+            }
+            if (!exited) break;                                          /* max_distance reached inside the cell */
+        }
+        /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
+        if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
+            vr_out_of_bounds(r);
+            status = VR_ST_OOB;
+            break;
+        }
+        if (AUX) a->lookups++;
+        /* pop to the lowest ancestor containing the voxel */
+        const int nx = (r.voxel.x ^ nv.x) | (r.voxel.y ^ nv.y) | (r.voxel.z ^ nv.z);
+        if ((nx >> (s + 2)) != 0) {
+            do { s += 2; level--; } while ((nx >> (s + 2)) != 0);
+            node = vr_load_node(P, stk.get(level));
+            if (AUX) a->node_fetches++;
+        }
+        nv = r.voxel;
+        int voxel_data = 0;
+        for (;;) {
+            const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
+            if (!((node.mask >> ci) & 1ull)) {                           /* empty slot: cache the cell */
+                cs = s;
+                co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
                 break;
             }
-            if (AUX) a->lookups++;
-            /* pop to the lowest ancestor containing the voxel */
-            const int nx = (r.voxel.x ^ nv.x) | (r.voxel.y ^ nv.y) | (r.voxel.z ^ nv.z);
-            if ((nx >> (s + 2)) != 0) {
-                do { s += 2; level--; } while ((nx >> (s + 2)) != 0);
-                node = vr_load_node(P, stk.get(level));
-                if (AUX) a->node_fetches++;
+            const uint32_t rank = (uint32_t)VR_POPC64(node.mask & ((1ull << ci) - 1ull));
+            if (s == 0) {                                                /* a set voxel bit */
+                voxel_data = (int)(int8_t)P.leaf_types[node.base + rank];
+                break;
             }
-            nv = r.voxel;
-            int voxel_data = 0;
-            for (;;) {
-                const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
-                if (!((node.mask >> ci) & 1ull)) {                       /* empty slot: cache the cell */
-                    cs = s;
-                    co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
-                    break;
-                }
-                const uint32_t rank = (uint32_t)VR_POPC64(node.mask & ((1ull << ci) - 1ull));
-                if (s == 0) {                                            /* a set voxel bit */
-                    voxel_data = (int)(int8_t)P.leaf_types[node.base + rank];
-                    break;
-                }
-                const uint32_t child = node.base + rank;
-                level++;
-                s -= 2;
-                stk.set(level, child);
-                node = vr_load_node(P, child);
-                if (AUX) a->node_fetches++;
+            const uint32_t child = node.base + rank;
+            level++;
+            s -= 2;
+            stk.set(level, child);
+            node = vr_load_node(P, child);
+            if (AUX) a->node_fetches++;
+        }
+        if (voxel_data == 5 || voxel_data == 6) {
+            const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
+            if (st == VR_ST_SKIP_REDIRECT) {
+                if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
+                return false;
             }
-            if (voxel_data == 5 || voxel_data == 6) {
-                const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
-                if (st == VR_ST_SKIP_REDIRECT) {
-                    if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
-                    return false;
-                }
-                if (st >= 0) { status = st; break; }
-            }
+            if (st >= 0) { status = st; break; }
         }
         r.dist++;
     }
