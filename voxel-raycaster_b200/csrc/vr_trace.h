@@ -365,15 +365,79 @@ VR_HD vr_node_regs vr_load_node(const vr_frame_params &P, uint32_t idx) {
 #endif
 }
 
-/* Packed per-axis exit counters of the in-cell walk: field a (10 bits at 0/10/20) holds
- * 512 - (crossings of axis a still needed to leave the cached cell); a field reaching 512 sets its
- * guard bit (9/19/29).  Cells wider than 512 voxels are clamped: the walk then "leaves" early and the
- * lookup simply finds the same cell again. */
-#define VR_CNT_GUARD 0x20080200u
+/* ---- in-cell walk ---------------------------------------------------------------------------------
+ * Inside a known-empty cell the reference loop (kernel:558-560) reduces to: find the smallest
+ * intersection_t, add delta_t on every axis that attains it (ties step several axes), count the step.
+ * Per axis the state is (t, k): the next crossing time and the number of crossings still needed to leave
+ * the cell along that axis; `rem` counts the steps max_distance still allows.  The walk stops when some
+ * k reaches 0 (that step left the cell) or rem reaches 0.
+ * Written so that almost all work lands on the FMA pipe (2x the ALU pipe's rate on sm_100):
+ *   m  = min3(tx,ty,tz)                         1 FMNMX3          (ALU)
+ *   ma = (ta == m) ? 1.0f : 0.0f                3 FSET.BF         (ALU)   exact tie semantics of kernel:558
+ *   ta = fma(da, ma, ta);  ka -= ma             3 FFMA + 3 FADD   (FMA)   da*ma is exact => same as ta + da*ma
+ *   stop <=> kx*ky*kz*rem == 0                  1 FADD + 3 FMUL   (FMA) + 1 FSETP (ALU)
+ * No integer work, no memory access. */
+struct vr_walk_state {
+    float tx, ty, tz, kx, ky, kz, rem;
+};
 
+VR_HD float vr_min3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float m;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+    return m;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define VR_FMA_EXACT(a, b, c) __fmaf_rn((a), (b), (c))      /* only used where a*b is exact */
+#else
+#define VR_FMA_EXACT(a, b, c) ((c) + (a) * (b))
+#endif
+
+/* one step; returns kx*ky*kz*rem (zero <=> stop) */
+VR_HD float vr_walk_step(vr_walk_state &w, const vf3 &d) {
+    const float m = vr_min3(w.tx, w.ty, w.tz);
+    const float mx = (w.tx == m) ? 1.0f : 0.0f;
+    const float my = (w.ty == m) ? 1.0f : 0.0f;
+    const float mz = (w.tz == m) ? 1.0f : 0.0f;
+    w.tx = VR_FMA_EXACT(d.x, mx, w.tx);
+    w.ty = VR_FMA_EXACT(d.y, my, w.ty);
+    w.tz = VR_FMA_EXACT(d.z, mz, w.tz);
+    w.kx = VR_SUB(w.kx, mx);
+    w.ky = VR_SUB(w.ky, my);
+    w.kz = VR_SUB(w.kz, mz);
+    w.rem = VR_SUB(w.rem, 1.0f);
+    return VR_MUL(VR_MUL(w.kx, w.ky), VR_MUL(w.kz, w.rem));
+}
+
+/* crossings of one axis needed to leave the cell [origin, origin+size) from `voxel`; clamped to 512
+ * (a wider cell is then simply left early and found again by the lookup) */
 VR_HD int vr_exit_count(int step, int voxel, int origin, int size) {
     const int r = step > 0 ? origin + size - voxel : voxel - origin + 1;
     return r > 512 ? 512 : r;
+}
+
+/* The literal walk of one cell (kernel:558-560 step by step, full face mask): used when the float state
+ * is not finite (the packed walk assumes ordered compares) and to recover the face mask of a hit that
+ * follows a cell in which a multi-axis (tie) step occurred.  Returns true if the last step left the cell. */
+template <bool AUX>
+VR_HD bool vr_walk_literal(RayState &r, int cs, vi3 co, vr_aux *a) {
+    for (;;) {
+        vr_dda_step(r);
+        if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
+        const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
+        if ((cx >> cs) != 0) return true;
+        r.dist++;
+        if (!(r.dist < r.max_distance)) return false;
+    }
+}
+
+VR_HD bool vr_ray_finite(const RayState &r) {
+    const float s = ((r.t.x + r.t.y) + r.t.z) + ((r.delta.x + r.delta.y) + r.delta.z);
+    return s - s == 0.0f;             /* false for inf / NaN */
 }
 
 template <bool AUX, class Stack>
@@ -396,59 +460,39 @@ VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_o
      * steps before it loads (kernel:555-570), so that voxel is never tested. */
     int cs = 0;
     vi3 co = r.voxel;
+    bool finite = vr_ray_finite(r);
 
     bool first_hit_done = false;
     int status = VR_ST_MAXDIST;
     while (r.dist < r.max_distance && r.bounce < 2) {
-        /* ---- (1) walk inside the cached cell: kernel:558-560 without the map load.  Only the float
-         * state and three packed exit counters are live; no memory access, no bounds test. */
-        {
+        /* ---- (1) walk inside the cached cell: no memory access, no bounds test */
+        bool tie_cell = false;
+        vf3 t0 = r.t;                                                    /* state at cell entry, for a replay */
+        int n = 0, ax = 0, ay = 0, az = 0;
+        if (finite) {
             const int S = 1 << cs;
-            uint32_t cnt = (uint32_t)(512 - vr_exit_count(r.step.x, r.voxel.x, co.x, S)) |
-                           ((uint32_t)(512 - vr_exit_count(r.step.y, r.voxel.y, co.y, S)) << 10) |
-                           ((uint32_t)(512 - vr_exit_count(r.step.z, r.voxel.z, co.z, S)) << 20);
-            const uint32_t cnt0 = cnt;
-            const vf3 t0 = r.t;
+            const int rx = vr_exit_count(r.step.x, r.voxel.x, co.x, S);
+            const int ry = vr_exit_count(r.step.y, r.voxel.y, co.y, S);
+            const int rz = vr_exit_count(r.step.z, r.voxel.z, co.z, S);
             const int nmax = r.max_distance - r.dist;
-            float tx = r.t.x, ty = r.t.y, tz = r.t.z;
-            int n = 0;
-            do {
-                const bool px = tx <= fminf(ty, tz);
-                const bool py = ty <= fminf(tz, tx);
-                const bool pz = tz <= fminf(tx, ty);
-                if (px) { tx = VR_ADD(tx, r.delta.x); cnt += 1u; }
-                if (py) { ty = VR_ADD(ty, r.delta.y); cnt += 1u << 10; }
-                if (pz) { tz = VR_ADD(tz, r.delta.z); cnt += 1u << 20; }
-                n++;
-            } while (!(cnt & VR_CNT_GUARD) && n < nmax);
-            const int ax = (int)(cnt & 1023u) - (int)(cnt0 & 1023u);
-            const int ay = (int)((cnt >> 10) & 1023u) - (int)((cnt0 >> 10) & 1023u);
-            const int az = (int)((cnt >> 20) & 1023u) - (int)((cnt0 >> 20) & 1023u);
-            bool exited;
-            if (ax + ay + az == n) {
-                /* one axis per step: the guard bits name the face crossed by the last step */
-                r.t = {tx, ty, tz};
-                r.voxel.x += r.step.x * ax;
-                r.voxel.y += r.step.y * ay;
-                r.voxel.z += r.step.z * az;
-                exited = (cnt & VR_CNT_GUARD) != 0u;
-                r.fm = (int)(((cnt >> 9) & 1u) | ((cnt >> 18) & 2u) | ((cnt >> 27) & 4u));
-                r.dist += exited ? n - 1 : n;
-            } else {
-                /* some step moved along two or three axes at once (exact tie of intersection_t): redo the
-                 * cell with the literal step that tracks the full face mask */
-                r.t = t0;
-                exited = false;
-                for (;;) {
-                    vr_dda_step(r);
-                    if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
-                    const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
-                    if ((cx >> cs) != 0) { exited = true; break; }
-                    r.dist++;
-                    if (!(r.dist < r.max_distance)) break;
-                }
-            }
-            if (!exited) break;                                          /* max_distance reached inside the cell */
+            vr_walk_state w = {r.t.x, r.t.y, r.t.z, (float)rx, (float)ry, (float)rz, (float)nmax};
+            while (vr_walk_step(w, r.delta) != 0.0f) {}
+            r.t = {w.tx, w.ty, w.tz};
+            const float kx = w.kx, ky = w.ky, kz = w.kz;
+            ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;     /* crossings done per axis */
+            n = nmax - (int)w.rem;                                       /* steps done */
+            r.voxel.x += r.step.x * ax;
+            r.voxel.y += r.step.y * ay;
+            r.voxel.z += r.step.z * az;
+            /* without ties exactly one axis moved per step, and the axis whose k hit 0 is the face crossed by
+             * the last step; with a tie somewhere in the cell the mask is recovered by a replay if needed */
+            tie_cell = (ax + ay + az) != n;
+            r.fm = (kx == 0.0f ? 1 : 0) | (ky == 0.0f ? 2 : 0) | (kz == 0.0f ? 4 : 0);
+            if (AUX && tie_cell) a->flags |= VR_FL_TIE;
+            if (r.fm == 0) { r.dist += n; break; }                       /* max_distance reached inside the cell */
+            r.dist += n - 1;
+        } else if (!vr_walk_literal<AUX>(r, cs, co, a)) {
+            break;
         }
         /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
         if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
@@ -486,12 +530,23 @@ VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_o
             if (AUX) a->node_fetches++;
         }
         if (voxel_data == 5 || voxel_data == 6) {
+            if (tie_cell) {
+                /* a multi-axis step happened in the cell just left: the hit's face mask may have more than the
+                 * exit axis set.  Replay the cell literally from its entry state (same t, voxel, dist; exact fm). */
+                r.voxel.x -= r.step.x * ax;
+                r.voxel.y -= r.step.y * ay;
+                r.voxel.z -= r.step.z * az;
+                r.dist -= n - 1;
+                r.t = t0;
+                vr_walk_literal<false>(r, cs, co, a);
+            }
             const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
             if (st == VR_ST_SKIP_REDIRECT) {
                 if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
                 return false;
             }
             if (st >= 0) { status = st; break; }
+            finite = vr_ray_finite(r);                                   /* the ray was redirected */
         }
         r.dist++;
     }
