@@ -148,7 +148,7 @@ def run_reference(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3"])
@@ -223,11 +223,10 @@ def main() -> None:
     must(c.validate(), "validate")
 
     W, H = scene.width, scene.height
-    nbands = (H + BAND_ROWS - 1) // BAND_ROWS
-    local_bands = (nbands - rank + world - 1) // world
-    max_bands = (nbands + world - 1) // world
-    slab = torch.full((max_bands * BAND_ROWS, W, 4), 0, dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, max_bands * BAND_ROWS, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
+    layout = pkg.tiles.BandLayout(H, W, BAND_ROWS, world)
+    max_bands = layout.max_bands
+    slab = torch.full((layout.slab_rows, W, 4), 0, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world * layout.slab_rows, W, 4), dtype=torch.uint8, device=dev) if world > 1 else None
     frame = torch.empty((max_bands * world * BAND_ROWS, W, 4), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
     host_frame = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
 
@@ -235,16 +234,13 @@ def main() -> None:
         """device-resident step: render this rank's bands, gather the slabs on rank 0, un-interleave."""
         must(c.compute_into(slab.data_ptr()), "compute_into")
         if world > 1:
-            dist.all_gather_into_tensor(gathered, slab)
-            if rank == 0:
-                # band b lives at gathered[b % world, b // world]; one strided copy restores frame order
-                frame.view(max_bands, world, BAND_ROWS, W, 4).copy_(gathered.view(world, max_bands, BAND_ROWS, W, 4).permute(1, 0, 2, 3, 4))
+            pkg.tiles.gather_frame(layout, slab, gathered, frame, dist, rank)
 
     # rays per frame, counted on the device from the aux records of one untimed frame
     must(c.enable_aux(True), "enable_aux")
     render_step()
     torch.cuda.synchronize()
-    aux = c.read_aux()[: local_bands * BAND_ROWS]
+    aux = c.read_aux()[: layout.local_rows(rank)]
     counts = torch.tensor([int((aux["status"] != 0).sum()), int(((aux["flags"] & 1) != 0).sum()),
                            int(aux["node_fetches"].astype(np.int64).sum()), int(aux["lookups"].astype(np.int64).sum()),
                            int(aux["steps_total"].astype(np.int64).sum())], dtype=torch.int64, device=dev)
@@ -274,9 +270,7 @@ def main() -> None:
             must(c.compute_into(slab.data_ptr()), "compute_into")
             kev[i][1].record(stream)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, slab)
-                if rank == 0:
-                    frame.view(max_bands, world, BAND_ROWS, W, 4).copy_(gathered.view(world, max_bands, BAND_ROWS, W, 4).permute(1, 0, 2, 3, 4))
+                pkg.tiles.gather_frame(layout, slab, gathered, frame, dist, rank)
         ev1.record(stream)
         barrier()
     launches = c.stats().kernel_launches - launches0

@@ -7,5 +7,5 @@ The directory name contains a hyphen, so import it with
     caster.py   ctypes binding and `CUDACaster`, the host-side mirror of CLCaster
     scene.py    deterministic synthetic scenes (maps, cameras, lights, atlas)
 """
-from . import scene  # noqa: F401
+from . import scene, tiles  # noqa: F401
 from .caster import AUX_DTYPE, SYMBOLS, CUDACaster, VrStats, load_library, octree_generate, octree_get_voxel  # noqa: F401
