@@ -156,6 +156,9 @@ def main() -> None:
     ap.add_argument("--cpu-row-stride", type=int, default=16, help="oracle sample for cpu_baseline")
     ap.add_argument("--ref-row-stride", type=int, default=16, help="oracle sample per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--persistent", type=int, default=0, help="1 = persistent-warp octree kernel")
+    ap.add_argument("--refill-min", type=int, default=8)
+    ap.add_argument("--ctas-per-sm", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -221,6 +224,8 @@ def main() -> None:
     must(c.assign_lights(scene.lights), "assign_lights")
     must(c.create_texture_atlas(scene.atlas, (scene.tile, scene.tile)), "create_texture_atlas")
     must(c.validate(), "validate")
+    must(c.set_option("persistent", args.persistent) and c.set_option("refill_min", args.refill_min)
+         and c.set_option("ctas_per_sm", args.ctas_per_sm), "set_option")
 
     W, H = scene.width, scene.height
     layout = pkg.tiles.BandLayout(H, W, BAND_ROWS, world)
@@ -331,7 +336,7 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}",
-                       "mode": args.mode, "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, NCCL all_gather" if world > 1 else "1 GPU",
+                       "mode": args.mode, "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, NCCL all_gather" if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),

@@ -128,6 +128,9 @@ int vr_frame_end(vr_ctx *ctx, const uint8_t **rgba);
  * (band = band_rows consecutive rows) into a compact slab.  (1,1,0) = whole frame. */
 int vr_set_bands(vr_ctx *ctx, int band_rows, int stride, int first);
 int vr_local_rows(const vr_ctx *ctx);
+/* Kernel variant knobs: "persistent" (0/1: persistent warps with warp-level pixel refill for the octree
+ * kernel), "refill_min" (idle lanes before a warp refills, 1..32), "ctas_per_sm" (persistent grid size). */
+int vr_set_option(vr_ctx *ctx, const char *name, int64_t value);
 /* Use an externally owned CUDA stream (e.g. the host framework's current stream); NULL restores the own stream. */
 int vr_set_stream(vr_ctx *ctx, void *cuda_stream);
 /* Per-pixel auxiliary records (hit voxel, face, status, step counts; 32 B/pixel) for parity tests. */

@@ -252,3 +252,28 @@ def test_full_size_c3_properties(pkg, oracle):
         assert np.array_equal(frames[True][1][f], frames[False][1][f]), f
     ref_rgba, ref_aux, _ = oracle.raycast(scene, row_stride=90)
     assert_same_frame(ref_rgba[::90], ref_aux[::90], frames[True][0][::90], frames[True][1][::90], "c3 rows")
+
+
+@pytest.mark.parametrize("refill_min", [1, 8, 24])
+def test_persistent_warps(pkg, oracle, refill_min):
+    """Persistent-warp variant of the octree kernel (warp-level pixel refill through __ballot_sync/__shfl_sync):
+    same pixels and aux records as the oracle, whatever the refill threshold."""
+    for name in ("features", "features-low", "small"):
+        scene = pkg.scene.make_scene(name)
+        desc, root = pkg.octree_generate(scene.volume)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+        c = make_caster(pkg, scene, True)
+        assert c.set_option("persistent", 1) and c.set_option("refill_min", refill_min)
+        assert c.compute(), c.last_error()
+        assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"persistent {name} refill={refill_min}")
+        c.close()
+    S = pkg.scene
+    vol = S.terrain_map(64, "shell", reflect_fraction=0.05)
+    pos, direction = S.make_camera(64, S.heightfield(64), 3)
+    scene = S.Scene(64, vol, 1280, 720, pos, direction, S.make_lights(64), max_distance=192)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene)
+    c = make_caster(pkg, scene, True, assign_octree=False)
+    assert c.set_option("persistent", 1) and c.set_option("refill_min", refill_min)
+    assert c.compute(), c.last_error()
+    assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"persistent c1 refill={refill_min}")
+    c.close()

@@ -79,6 +79,7 @@ struct vr_ctx {
 
     int used_svo = 0;
     int bias[3] = {0, 0, 0};
+    vr_launch_options opt = {0, 8, 3, 148, nullptr};
 };
 
 namespace {
@@ -266,7 +267,7 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
     int use_svo = 0;
     if (!build_params(c, P, image, &use_svo)) return 0;
     if (timed) VR_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
-    VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches));
+    VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &c->opt));
     if (timed) {
         VR_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
         c->timing_pending = true;
@@ -320,6 +321,8 @@ int vr_init(vr_ctx **out, int device, unsigned flags) {
         cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
     }
     c->stream = c->own_stream;
+    cudaDeviceGetAttribute(&c->opt.num_sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (cudaMalloc(&c->opt.counter, sizeof(unsigned int)) != cudaSuccess) { fail(c, "cudaMalloc failed"); delete c; return 0; }
     if (!vr_create_settings_buffer(c)) { delete c; return 0; }
     *out = c;
     return 1;
@@ -336,6 +339,7 @@ void vr_destroy(vr_ctx *c) {
     if (c->atlas_tex) cudaDestroyTextureObject(c->atlas_tex);
     if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
     if (c->d_atlas) cudaFree(c->d_atlas);
+    if (c->opt.counter) cudaFree(c->opt.counter);
     for (int i = 0; i < 2; i++) {
         if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -675,6 +679,16 @@ int vr_set_bands(vr_ctx *c, int band_rows, int stride, int first) {
     c->band_rows = band_rows;
     c->band_stride = stride;
     c->band_first = first;
+    return 1;
+}
+
+int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
+    if (!c || !name) return 0;
+    const std::string n(name);
+    if (n == "persistent") c->opt.persistent = value != 0;
+    else if (n == "refill_min") c->opt.refill_min = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
+    else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
+    else return fail(c, "set_option: unknown option [%s]", name);
     return 1;
 }
 

@@ -21,6 +21,9 @@ namespace {
 constexpr int kTileW = 32;
 constexpr int kTileH = 8;
 constexpr int kThreads = kTileW * kTileH;
+#ifndef VR_SVO_MIN_CTAS
+#define VR_SVO_MIN_CTAS 3      /* CTAs per SM the register allocation of vr_svo_kernel targets (measured: see DESIGN.md) */
+#endif
 
 /* thread -> pixel inside the CTA tile: warp w = (w&3, w>>2) of 8x4 blocks, lane = (l&7, l>>3) */
 __device__ __forceinline__ void tile_xy(int tid, int &lx, int &ly) {
@@ -61,7 +64,7 @@ vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
 }
 
 template <bool AUX>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, VR_SVO_MIN_CTAS)
 vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
     int lx, ly;
@@ -81,6 +84,72 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
 }
 
+/* Persistent-warp variant (Aila/Laine style): the grid is sized to the machine (ctas_per_sm * #SM CTAs), every
+ * warp pulls pixels from a global counter.  When at least `refill_min` lanes of a warp have finished their
+ * pixel, ONE lane reserves that many new pixels with a single atomicAdd and the reservation is handed out to
+ * the idle lanes with __ballot_sync / __shfl_sync / popc-prefix, so lanes never idle behind the slowest ray of
+ * their tile.  Pixel order: index -> 8x4 tile -> 32x8 super tile (same as the static kernel), so one refill
+ * batch is a compact screen block. */
+template <bool AUX>
+__global__ void __launch_bounds__(kThreads)
+vr_svo_persistent_kernel(const __grid_constant__ vr_frame_params P, unsigned int *counter, int refill_min) {
+    __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned stiles_x = (unsigned)(P.width + kTileW - 1) / kTileW;
+    const unsigned stiles_y = (unsigned)(P.local_rows + kTileH - 1) / kTileH;
+    const unsigned total = stiles_x * stiles_y * (unsigned)kThreads;
+    vr_svo_ray<SmemStack> q;
+    q.stk = SmemStack{stack + threadIdx.x};
+    vr_aux a;
+    bool active = false, more = true;
+    size_t local = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu || (more && __popc(idle) >= refill_min)) {
+            if (!more) break;                                   /* every lane idle and the counter is exhausted */
+            const int nidle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned)nidle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (unsigned)nidle >= total) more = false;
+            if (!active) {
+                const unsigned idx = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (idx < total) {
+                    const unsigned st = idx / (unsigned)kThreads, in = idx % (unsigned)kThreads;
+                    int lx, ly;
+                    tile_xy((int)in, lx, ly);
+                    const int x = (int)(st % stiles_x) * kTileW + lx;
+                    const int row = (int)(st / stiles_x) * kTileH + ly;
+                    if (x < P.width && row < P.local_rows) {
+                        const int y = frame_row(P, row);
+                        if (y < P.height) {
+                            local = (size_t)x + (size_t)P.width * (size_t)row;
+                            active = vr_svo_begin<AUX>(P, x, y, q, &a);
+                            if (AUX && !active) {
+                                reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a);
+                                reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
+                            }
+                        }
+                    }
+                }
+            }
+            if (idle == 0xffffffffu && !more && !__any_sync(0xffffffffu, active)) break;
+        }
+        if (active) {
+            const int rc = vr_svo_cell<AUX>(P, q, &a);
+            if (rc != VR_CELL_CONTINUE) {
+                if (rc != VR_CELL_NO_WRITE) reinterpret_cast<uint32_t *>(P.image)[local] = vr_svo_finish<AUX>(q, rc, &a);
+                if (AUX) {
+                    reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a);
+                    reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
+                }
+                active = false;
+            }
+        }
+    }
+}
+
 __global__ void vr_fill_kernel(uint32_t *dst, size_t n, uint32_t value) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = value;
@@ -89,11 +158,18 @@ __global__ void vr_fill_kernel(uint32_t *dst, size_t n, uint32_t value) {
 }  // namespace
 
 cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_aux, cudaStream_t stream,
-                              unsigned long long *launches) {
+                              unsigned long long *launches, const vr_launch_options *opt) {
     if (P.width <= 0 || P.local_rows <= 0) return cudaSuccess;
     const dim3 grid((P.width + kTileW - 1) / kTileW, (P.local_rows + kTileH - 1) / kTileH);
     const dim3 block(kThreads);
-    if (use_svo) {
+    if (use_svo && opt && opt->persistent) {
+        cudaError_t e = cudaMemsetAsync(opt->counter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        unsigned ctas = (unsigned)(opt->num_sms * opt->ctas_per_sm);
+        if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
+        if (with_aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
+        else vr_svo_persistent_kernel<false><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
+    } else if (use_svo) {
         if (with_aux) vr_svo_kernel<true><<<grid, block, 0, stream>>>(P);
         else vr_svo_kernel<false><<<grid, block, 0, stream>>>(P);
     } else {

@@ -440,119 +440,158 @@ VR_HD bool vr_ray_finite(const RayState &r) {
     return s - s == 0.0f;             /* false for inf / NaN */
 }
 
-template <bool AUX, class Stack>
-VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
+/* Per-ray traversal state of the SVO variant: everything that lives across cells. */
+template <class Stack>
+struct vr_svo_ray {
     RayState r;
+    vr_node_regs node;        /* current node of the descent */
+    int s;                    /* its child shift */
+    int level;
+    vi3 nv;                   /* a voxel inside the current node */
+    int cs;                   /* cached empty cell: edge 1 << cs at origin co */
+    vi3 co;
+    bool finite;
+    bool first_hit_done;
+    Stack stk;
+};
+
+enum { VR_CELL_CONTINUE = -1, VR_CELL_NO_WRITE = -2 };   /* otherwise: terminal VR_ST_* status */
+
+/* kernel:276-354 for one pixel.  Returns false when the pixel is skipped (kernel:293). */
+template <bool AUX, class Stack>
+VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack> &q, vr_aux *a) {
     if (AUX) vr_aux_init(a, P);
-    if (!vr_ray_setup(P, x, y, r)) {
+    if (!vr_ray_setup(P, x, y, q.r)) {
         if (AUX) a->status = VR_ST_SKIP_PRIMARY;
         return false;
     }
-    const int N = P.dim[0];
-    /* current node of the descent */
-    int s = P.root_shift;                 /* child shift of the current node */
-    int level = 0;
-    vr_node_regs node = vr_load_node(P, 0);
-    stk.set(0, 0u);
-    vi3 nv = {0, 0, 0};                   /* a voxel inside the current node */
+    q.s = P.root_shift;
+    q.level = 0;
+    q.node = vr_load_node(P, 0);
+    q.stk.set(0, 0u);
+    q.nv = {0, 0, 0};
     if (AUX) a->node_fetches = 1;
-    /* cached empty cell (edge 1 << cs at origin co).  Initially the camera voxel itself: the reference
-     * steps before it loads (kernel:555-570), so that voxel is never tested. */
-    int cs = 0;
-    vi3 co = r.voxel;
-    bool finite = vr_ray_finite(r);
+    /* the first "cell" is the camera voxel itself: the reference steps before it loads (kernel:555-570),
+     * so that voxel is never tested */
+    q.cs = 0;
+    q.co = q.r.voxel;
+    q.finite = vr_ray_finite(q.r);
+    q.first_hit_done = false;
+    return true;
+}
 
-    bool first_hit_done = false;
-    int status = VR_ST_MAXDIST;
-    while (r.dist < r.max_distance && r.bounce < 2) {
-        /* ---- (1) walk inside the cached cell: no memory access, no bounds test */
-        bool tie_cell = false;
-        vf3 t0 = r.t;                                                    /* state at cell entry, for a replay */
-        int n = 0, ax = 0, ay = 0, az = 0;
-        if (finite) {
-            const int S = 1 << cs;
-            const int rx = vr_exit_count(r.step.x, r.voxel.x, co.x, S);
-            const int ry = vr_exit_count(r.step.y, r.voxel.y, co.y, S);
-            const int rz = vr_exit_count(r.step.z, r.voxel.z, co.z, S);
-            const int nmax = r.max_distance - r.dist;
-            vr_walk_state w = {r.t.x, r.t.y, r.t.z, (float)rx, (float)ry, (float)rz, (float)nmax};
-            while (vr_walk_step(w, r.delta) != 0.0f) {}
-            r.t = {w.tx, w.ty, w.tz};
-            const float kx = w.kx, ky = w.ky, kz = w.kz;
-            ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;     /* crossings done per axis */
-            n = nmax - (int)w.rem;                                       /* steps done */
-            r.voxel.x += r.step.x * ax;
-            r.voxel.y += r.step.y * ay;
-            r.voxel.z += r.step.z * az;
-            /* without ties exactly one axis moved per step, and the axis whose k hit 0 is the face crossed by
-             * the last step; with a tie somewhere in the cell the mask is recovered by a replay if needed */
-            tie_cell = (ax + ay + az) != n;
-            r.fm = (kx == 0.0f ? 1 : 0) | (ky == 0.0f ? 2 : 0) | (kz == 0.0f ? 4 : 0);
-            if (AUX && tie_cell) a->flags |= VR_FL_TIE;
-            if (r.fm == 0) { r.dist += n; break; }                       /* max_distance reached inside the cell */
-            r.dist += n - 1;
-        } else if (!vr_walk_literal<AUX>(r, cs, co, a)) {
-            break;
-        }
-        /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
-        if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
-            vr_out_of_bounds(r);
-            status = VR_ST_OOB;
-            break;
-        }
-        if (AUX) a->lookups++;
-        /* pop to the lowest ancestor containing the voxel */
-        const int nx = (r.voxel.x ^ nv.x) | (r.voxel.y ^ nv.y) | (r.voxel.z ^ nv.z);
-        if ((nx >> (s + 2)) != 0) {
-            do { s += 2; level--; } while ((nx >> (s + 2)) != 0);
-            node = vr_load_node(P, stk.get(level));
-            if (AUX) a->node_fetches++;
-        }
-        nv = r.voxel;
-        int voxel_data = 0;
-        for (;;) {
-            const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
-            if (!((node.mask >> ci) & 1ull)) {                           /* empty slot: cache the cell */
-                cs = s;
-                co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
-                break;
-            }
-            const uint32_t rank = (uint32_t)VR_POPC64(node.mask & ((1ull << ci) - 1ull));
-            if (s == 0) {                                                /* a set voxel bit */
-                voxel_data = (int)(int8_t)P.leaf_types[node.base + rank];
-                break;
-            }
-            const uint32_t child = node.base + rank;
-            level++;
-            s -= 2;
-            stk.set(level, child);
-            node = vr_load_node(P, child);
-            if (AUX) a->node_fetches++;
-        }
-        if (voxel_data == 5 || voxel_data == 6) {
-            if (tie_cell) {
-                /* a multi-axis step happened in the cell just left: the hit's face mask may have more than the
-                 * exit axis set.  Replay the cell literally from its entry state (same t, voxel, dist; exact fm). */
-                r.voxel.x -= r.step.x * ax;
-                r.voxel.y -= r.step.y * ay;
-                r.voxel.z -= r.step.z * az;
-                r.dist -= n - 1;
-                r.t = t0;
-                vr_walk_literal<false>(r, cs, co, a);
-            }
-            const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
-            if (st == VR_ST_SKIP_REDIRECT) {
-                if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
-                return false;
-            }
-            if (st >= 0) { status = st; break; }
-            finite = vr_ray_finite(r);                                   /* the ray was redirected */
-        }
-        r.dist++;
+/* One iteration of the cell loop: walk the cached cell, then look the new voxel up.
+ * Returns VR_CELL_CONTINUE, VR_CELL_NO_WRITE (pixel skipped after a redirect, kernel:671/694) or the
+ * terminal status. */
+template <bool AUX, class Stack>
+VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
+    RayState &r = q.r;
+    if (!(r.dist < r.max_distance && r.bounce < 2)) return r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST;
+    const int N = P.dim[0];
+    /* ---- (1) walk inside the cached cell: no memory access, no bounds test */
+    bool tie_cell = false;
+    const vf3 t0 = r.t;                                                  /* state at cell entry, for a replay */
+    int n = 0, ax = 0, ay = 0, az = 0;
+    if (q.finite) {
+        const int S = 1 << q.cs;
+        const int rx = vr_exit_count(r.step.x, r.voxel.x, q.co.x, S);
+        const int ry = vr_exit_count(r.step.y, r.voxel.y, q.co.y, S);
+        const int rz = vr_exit_count(r.step.z, r.voxel.z, q.co.z, S);
+        const int nmax = r.max_distance - r.dist;
+        vr_walk_state w = {r.t.x, r.t.y, r.t.z, (float)rx, (float)ry, (float)rz, (float)nmax};
+        while (vr_walk_step(w, r.delta) != 0.0f) {}
+        r.t = {w.tx, w.ty, w.tz};
+        const float kx = w.kx, ky = w.ky, kz = w.kz;
+        ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;         /* crossings done per axis */
+        n = nmax - (int)w.rem;                                           /* steps done */
+        r.voxel.x += r.step.x * ax;
+        r.voxel.y += r.step.y * ay;
+        r.voxel.z += r.step.z * az;
+        /* without ties exactly one axis moved per step, and the axis whose k hit 0 is the face crossed by the
+         * last step; with a tie somewhere in the cell the mask is recovered by a replay if it is needed */
+        tie_cell = (ax + ay + az) != n;
+        r.fm = (kx == 0.0f ? 1 : 0) | (ky == 0.0f ? 2 : 0) | (kz == 0.0f ? 4 : 0);
+        if (AUX && tie_cell) a->flags |= VR_FL_TIE;
+        if (r.fm == 0) { r.dist += n; return VR_ST_MAXDIST; }            /* max_distance reached inside the cell */
+        r.dist += n - 1;
+    } else if (!vr_walk_literal<AUX>(r, q.cs, q.co, a)) {
+        return VR_ST_MAXDIST;
     }
-    if (status == VR_ST_MAXDIST && r.bounce >= 2) status = VR_ST_BOUNCES;
-    if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
-    *rgba_out = vr_epilogue(r);
+    /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
+    if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
+        vr_out_of_bounds(r);
+        return VR_ST_OOB;
+    }
+    if (AUX) a->lookups++;
+    /* pop to the lowest ancestor containing the voxel */
+    const int nx = (r.voxel.x ^ q.nv.x) | (r.voxel.y ^ q.nv.y) | (r.voxel.z ^ q.nv.z);
+    if ((nx >> (q.s + 2)) != 0) {
+        do { q.s += 2; q.level--; } while ((nx >> (q.s + 2)) != 0);
+        q.node = vr_load_node(P, q.stk.get(q.level));
+        if (AUX) a->node_fetches++;
+    }
+    q.nv = r.voxel;
+    int voxel_data = 0;
+    for (;;) {
+        const int s = q.s;
+        const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
+        if (!((q.node.mask >> ci) & 1ull)) {                             /* empty slot: cache the cell */
+            q.cs = s;
+            q.co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
+            break;
+        }
+        const uint32_t rank = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
+        if (s == 0) {                                                    /* a set voxel bit */
+            voxel_data = (int)(int8_t)P.leaf_types[q.node.base + rank];
+            break;
+        }
+        const uint32_t child = q.node.base + rank;
+        q.level++;
+        q.s -= 2;
+        q.stk.set(q.level, child);
+        q.node = vr_load_node(P, child);
+        if (AUX) a->node_fetches++;
+    }
+    if (voxel_data == 5 || voxel_data == 6) {
+        if (tie_cell) {
+            /* a multi-axis step happened in the cell just left: the hit's face mask may have more than the exit
+             * axis set.  Replay the cell literally from its entry state (same t, voxel, dist; exact fm). */
+            r.voxel.x -= r.step.x * ax;
+            r.voxel.y -= r.step.y * ay;
+            r.voxel.z -= r.step.z * az;
+            r.dist -= n - 1;
+            r.t = t0;
+            vr_walk_literal<false>(r, q.cs, q.co, a);
+        }
+        const int st = vr_hit_block<AUX>(P, r, voxel_data, a, q.first_hit_done);
+        if (st == VR_ST_SKIP_REDIRECT) {
+            if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
+            return VR_CELL_NO_WRITE;
+        }
+        if (st >= 0) return st;
+        q.finite = vr_ray_finite(r);                                     /* the ray was redirected */
+    }
+    r.dist++;
+    return VR_CELL_CONTINUE;
+}
+
+/* kernel:716-721 + aux bookkeeping for a finished ray */
+template <bool AUX, class Stack>
+VR_HD uint32_t vr_svo_finish(vr_svo_ray<Stack> &q, int status, vr_aux *a) {
+    if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)q.r.dist; }
+    return vr_epilogue(q.r);
+}
+
+/* whole pixel, static pixel->thread mapping */
+template <bool AUX, class Stack>
+VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
+    vr_svo_ray<Stack> q;
+    q.stk = stk;
+    if (!vr_svo_begin<AUX>(P, x, y, q, a)) return false;
+    int rc;
+    while ((rc = vr_svo_cell<AUX>(P, q, a)) == VR_CELL_CONTINUE) {}
+    if (rc == VR_CELL_NO_WRITE) return false;
+    *rgba_out = vr_svo_finish<AUX>(q, rc, a);
     return true;
 }
 
