@@ -159,6 +159,8 @@ def main() -> None:
     ap.add_argument("--persistent", type=int, default=0, help="1 = persistent-warp octree kernel")
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -261,9 +263,14 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: K steps bracketed by barrier + synchronize, CUDA events on the launch stream
+    # ---- device-resident timing: K steps bracketed by barrier + synchronize, CUDA events on the launch stream.
+    # N > 1: the gather of frame k overlaps the rendering of frame k+1 (tiles.FramePipeline, double buffered).
+    pipe = pkg.tiles.FramePipeline(layout, dev, dist, rank, lambda ptr: must(c.compute_into(ptr), "compute_into"),
+                                   caster=c if args.gather == "p2p" else None) if world > 1 else None
     for _ in range(args.warmup):
-        render_step()
+        pipe.step() if pipe else render_step()
+    if pipe:
+        pipe.drain()
     barrier()
     launches0 = c.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,11 +278,20 @@ def main() -> None:
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for i in range(args.steps):
-            kev[i][0].record(stream)
-            must(c.compute_into(slab.data_ptr()), "compute_into")
-            kev[i][1].record(stream)
-            if world > 1:
-                pkg.tiles.gather_frame(layout, slab, gathered, frame, dist, rank)
+            if pipe:
+                def timed_render(ptr, i=i):               # events hug the kernel, not the wait for a free slab
+                    kev[i][0].record(stream)
+                    must(c.compute_into(ptr), "compute_into")
+                    kev[i][1].record(stream)
+                pipe.render = timed_render
+                pipe.step()
+            else:
+                kev[i][0].record(stream)
+                must(c.compute_into(slab.data_ptr()), "compute_into")
+                kev[i][1].record(stream)
+        if pipe:
+            pipe.render = lambda ptr: must(c.compute_into(ptr), "compute_into")
+            pipe.drain()
         ev1.record(stream)
         barrier()
     launches = c.stats().kernel_launches - launches0
@@ -299,10 +315,10 @@ def main() -> None:
         host = c.frame_end()
         checksum = int(host[::64, ::64].astype(np.int64).sum())
     else:
+        pipe.host_frame = host_frame                  # rank 0 copies every gathered frame to pinned host memory
         for i in range(args.steps):
-            render_step()
-            if rank == 0:
-                host_frame.copy_(frame[:H], non_blocking=True)
+            pipe.step()
+        pipe.drain()
         torch.cuda.synchronize()
         checksum = int(host_frame[::64, ::64].sum().item()) if rank == 0 else 0
     barrier()
@@ -336,7 +352,7 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}",
-                       "mode": args.mode, "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, NCCL all_gather" if world > 1 else "1 GPU",
+                       "mode": args.mode, "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),

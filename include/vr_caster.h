@@ -149,6 +149,18 @@ int vr_native_tree_copy(vr_ctx *ctx, void *device_nodes, void *device_types);
 int vr_assign_native_tree(vr_ctx *ctx, const void *device_nodes, uint64_t node_bytes, const void *device_types,
                           uint64_t type_bytes, int32_t levels, int32_t dim);
 
+/* Multi-GPU frame assembly without SM involvement: every rank pushes its band slab straight into the frame
+ * buffer that lives on the root GPU with ONE strided copy-engine transfer over NVLink (cudaMemcpy2DAsync
+ * through a CUDA-IPC mapping), so the ray casting kernel of the next frame is not disturbed by a gather kernel.
+ * vr_ipc_get_handle: 64-byte cudaIpcMemHandle of a device allocation (root side).
+ * vr_ipc_open_handle / vr_ipc_close_handle: map / unmap it in another process.
+ * vr_push_bands: enqueue on `cuda_stream` the copy of this context's slab (band layout of vr_set_bands) into
+ * `frame` (device pointer, local or IPC-mapped; rows padded to a multiple of band_rows * stride). */
+int vr_ipc_get_handle(vr_ctx *ctx, void *device_ptr, void *handle64);
+int vr_ipc_open_handle(vr_ctx *ctx, const void *handle64, void **device_ptr);
+int vr_ipc_close_handle(vr_ctx *ctx, void *device_ptr);
+int vr_push_bands(vr_ctx *ctx, const void *slab, void *frame, void *cuda_stream);
+
 typedef struct vr_stats {
     uint64_t kernel_launches;      /* kernels launched by this context so far                */
     uint64_t frames;

@@ -81,6 +81,10 @@ SYMBOLS = {
     "vr_native_tree_info": (_i, [_vp, _u64p, _u64p, _i32p, _i32p]),
     "vr_native_tree_copy": (_i, [_vp, _vp, _vp]),
     "vr_assign_native_tree": (_i, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int32, C.c_int32]),
+    "vr_ipc_get_handle": (_i, [_vp, _vp, _vp]),
+    "vr_ipc_open_handle": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "vr_ipc_close_handle": (_i, [_vp, _vp]),
+    "vr_push_bands": (_i, [_vp, _vp, _vp, _vp]),
     "vr_get_stats": (_i, [_vp, C.POINTER(VrStats)]),
     "vr_octree_generate": (_i, [_i8p, _i, _u64p, _u64p, _u64p]),
     "vr_octree_get_voxel": (_i, [_u64p, C.c_uint64, C.c_uint64, _i, _i32p, _i32p, _i32p]),
@@ -315,6 +319,24 @@ class CUDACaster:
 
     def assign_native_tree(self, device_nodes: int, node_bytes: int, device_types: int, type_bytes: int, levels: int, dim: int) -> bool:
         return bool(self._lib.vr_assign_native_tree(self._ctx, _vp(device_nodes), node_bytes, _vp(device_types), type_bytes, levels, dim))
+
+    def ipc_get_handle(self, device_ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        if not self._lib.vr_ipc_get_handle(self._ctx, _vp(device_ptr), buf):
+            raise RuntimeError(self.last_error())
+        return buf.raw
+
+    def ipc_open_handle(self, handle: bytes) -> int:
+        out = _vp()
+        if not self._lib.vr_ipc_open_handle(self._ctx, C.c_char_p(handle), C.byref(out)):
+            raise RuntimeError(self.last_error())
+        return int(out.value)
+
+    def ipc_close_handle(self, device_ptr: int) -> bool:
+        return bool(self._lib.vr_ipc_close_handle(self._ctx, _vp(device_ptr)))
+
+    def push_bands(self, slab_ptr: int, frame_ptr: int, cuda_stream: int | None = None) -> bool:
+        return bool(self._lib.vr_push_bands(self._ctx, _vp(slab_ptr), _vp(frame_ptr), _vp(cuda_stream or 0)))
 
     def stats(self) -> VrStats:
         s = VrStats()

@@ -767,6 +767,44 @@ int vr_assign_native_tree(vr_ctx *c, const void *device_nodes, uint64_t node_byt
     return 1;
 }
 
+int vr_ipc_get_handle(vr_ctx *c, void *device_ptr, void *handle64) {
+    if (!c || !device_ptr || !handle64) return 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    VR_CUDA(c, cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle64, &h, sizeof(h));
+    return 1;
+}
+
+int vr_ipc_open_handle(vr_ctx *c, const void *handle64, void **device_ptr) {
+    if (!c || !handle64 || !device_ptr) return 0;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    VR_CUDA(c, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 1;
+}
+
+int vr_ipc_close_handle(vr_ctx *c, void *device_ptr) {
+    if (!c || !device_ptr) return 0;
+    VR_CUDA(c, cudaIpcCloseMemHandle(device_ptr));
+    return 1;
+}
+
+int vr_push_bands(vr_ctx *c, const void *slab, void *frame, void *cuda_stream) {
+    if (!c || !slab || !frame) return 0;
+    if (c->width <= 0) return fail(c, "push_bands: viewport not created");
+    cudaSetDevice(c->device);
+    const size_t band_bytes = (size_t)c->band_rows * (size_t)c->width * 4;
+    const int bands = local_rows_padded(c) / c->band_rows;
+    if (!bands) return 1;
+    /* band j of the slab -> frame band j * stride + first: one 2-D copy, pitch = stride bands */
+    VR_CUDA(c, cudaMemcpy2DAsync(static_cast<uint8_t *>(frame) + (size_t)c->band_first * band_bytes,
+                                 (size_t)c->band_stride * band_bytes, slab, band_bytes, band_bytes, (size_t)bands,
+                                 cudaMemcpyDefault, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream));
+    return 1;
+}
+
 int vr_get_stats(vr_ctx *c, vr_stats *out) {
     if (!c || !out) return 0;
     memset(out, 0, sizeof(*out));

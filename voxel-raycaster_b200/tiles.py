@@ -53,3 +53,70 @@ def gather_frame(layout: BandLayout, slab, gathered, frame, dist=None, rank: int
         # band b lives at gathered[b % world, b // world]: one strided copy restores frame order
         frame.view(mb, w, br, W, 4).copy_(gathered.view(w, mb, br, W, 4).permute(1, 0, 2, 3, 4))
     return frame
+
+
+class FramePipeline:
+    """Double-buffered multi-GPU frame loop: the gather (+ un-interleave, + optional device->host copy on rank 0)
+    of frame k runs on a communication stream while the compute stream already renders frame k+1 into the
+    other slab.  `render(ptr)` must enqueue the rendering of this rank's bands into device memory at `ptr`
+    on the CURRENT torch stream (CUDACaster.compute_into after set_stream)."""
+
+    def __init__(self, layout: BandLayout, device, dist, rank: int, render, host_frame=None, caster=None):
+        """caster != None selects the copy-engine gather: every rank pushes its slab into the root's frame buffer
+        through a CUDA-IPC mapping (CUDACaster.push_bands), followed by a one-element all_reduce as the "frame
+        complete" signal; otherwise the slabs go through NCCL all_gather + one un-interleave copy."""
+        import torch
+
+        self.torch, self.layout, self.dist, self.rank, self.render, self.host_frame = torch, layout, dist, rank, render, host_frame
+        self.caster = caster
+        W = layout.width
+        self.slabs = [torch.zeros((layout.slab_rows, W, 4), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.gathered = torch.empty((layout.world * layout.slab_rows, W, 4), dtype=torch.uint8, device=device)
+        self.frame = torch.empty((layout.max_bands * layout.world * layout.band_rows, W, 4), dtype=torch.uint8, device=device) if rank == 0 else None
+        self.comm = torch.cuda.Stream(device=device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.frames = None
+        if caster is not None:
+            # two frame buffers on the root, mapped into every other rank
+            if rank == 0:
+                self.frames = [self.frame, torch.empty_like(self.frame)]
+                # torch sub-allocates: export (IPC handle of the underlying cudaMalloc block, byte offset)
+                handles = []
+                for f in self.frames:
+                    shared = f.untyped_storage()._share_cuda_()
+                    handles.append((bytes(shared[1]), int(shared[3]) + f.storage_offset()))
+            else:
+                handles = [None, None]
+            dist.broadcast_object_list(handles, src=0)
+            self.frame_ptrs = ([f.data_ptr() for f in self.frames] if rank == 0
+                               else [caster.ipc_open_handle(h) + off for h, off in handles])
+        self.rendered = [torch.cuda.Event() for _ in range(2)]
+        self.collected = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+
+    def step(self) -> None:
+        torch = self.torch
+        i = self.k & 1
+        cur = torch.cuda.current_stream()
+        if self.k >= 2:
+            cur.wait_event(self.collected[i])            # slab i has left for the gather of frame k-2
+        self.render(self.slabs[i].data_ptr())
+        self.rendered[i].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.rendered[i])
+            if self.caster is not None:
+                if not self.caster.push_bands(self.slabs[i].data_ptr(), self.frame_ptrs[i], self.comm.cuda_stream):
+                    raise RuntimeError(self.caster.last_error())
+                self.dist.all_reduce(self.token)          # completes on the root only after every push has landed
+                if self.rank == 0:
+                    self.frame = self.frames[i]
+            else:
+                gather_frame(self.layout, self.slabs[i], self.gathered, self.frame, self.dist, self.rank)
+            if self.host_frame is not None and self.rank == 0:
+                self.host_frame.copy_(self.frame[: self.layout.height], non_blocking=True)
+            self.collected[i].record(self.comm)
+        self.k += 1
+
+    def drain(self) -> None:
+        """make the current stream wait for every gather issued so far"""
+        self.torch.cuda.current_stream().wait_stream(self.comm)
