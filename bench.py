@@ -334,11 +334,16 @@ def main() -> None:
         key = "bytes_svo" if use_svo else "bytes_dense"
         algo_bytes = float(ab[key]) if ab else None
         st = c.stats()
+        traffic = None
+        tp = ROOT / "profiles" / "ncu_traffic.json"
+        if world == 1 and tp.exists():
+            t = json.loads(tp.read_text()).get(args.config, {}).get("vr_svo_kernel" if use_svo else "vr_dense_kernel")
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
         roofline = None
         if algo_bytes:
             achieved = algo_bytes / world / (kernel_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_how, "kernel": "vr_svo_kernel" if use_svo else "vr_dense_kernel",
+                        "traffic": traffic, "peak_source": peak_how, "kernel": "vr_svo_kernel" if use_svo else "vr_dense_kernel",
                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes / world,
                         "bytes_model": "P*(16+4) + 8*D_svo + 4*T from oracle counters (profiles/algorithmic_bytes_%s.json)" % args.config,
                         "node_bytes_fetched_per_launch": 16.0 * node_fetches / world}

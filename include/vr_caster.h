@@ -152,10 +152,14 @@ int vr_assign_native_tree(vr_ctx *ctx, const void *device_nodes, uint64_t node_b
 /* Multi-GPU frame assembly without SM involvement: every rank pushes its band slab straight into the frame
  * buffer that lives on the root GPU with ONE strided copy-engine transfer over NVLink (cudaMemcpy2DAsync
  * through a CUDA-IPC mapping), so the ray casting kernel of the next frame is not disturbed by a gather kernel.
- * vr_ipc_get_handle: 64-byte cudaIpcMemHandle of a device allocation (root side).
+ * vr_device_alloc / vr_device_free: cudaMalloc'ed memory (framework caching allocators may hand out
+ * sub-allocations or VMM memory that legacy IPC cannot export).
+ * vr_ipc_get_handle: 64-byte cudaIpcMemHandle of such an allocation (root side).
  * vr_ipc_open_handle / vr_ipc_close_handle: map / unmap it in another process.
  * vr_push_bands: enqueue on `cuda_stream` the copy of this context's slab (band layout of vr_set_bands) into
  * `frame` (device pointer, local or IPC-mapped; rows padded to a multiple of band_rows * stride). */
+int vr_device_alloc(vr_ctx *ctx, size_t bytes, void **device_ptr);   /* plain cudaMalloc: IPC-exportable */
+int vr_device_free(vr_ctx *ctx, void *device_ptr);
 int vr_ipc_get_handle(vr_ctx *ctx, void *device_ptr, void *handle64);
 int vr_ipc_open_handle(vr_ctx *ctx, const void *handle64, void **device_ptr);
 int vr_ipc_close_handle(vr_ctx *ctx, void *device_ptr);

@@ -81,6 +81,8 @@ SYMBOLS = {
     "vr_native_tree_info": (_i, [_vp, _u64p, _u64p, _i32p, _i32p]),
     "vr_native_tree_copy": (_i, [_vp, _vp, _vp]),
     "vr_assign_native_tree": (_i, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int32, C.c_int32]),
+    "vr_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "vr_device_free": (_i, [_vp, _vp]),
     "vr_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "vr_ipc_open_handle": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "vr_ipc_close_handle": (_i, [_vp, _vp]),
@@ -319,6 +321,15 @@ class CUDACaster:
 
     def assign_native_tree(self, device_nodes: int, node_bytes: int, device_types: int, type_bytes: int, levels: int, dim: int) -> bool:
         return bool(self._lib.vr_assign_native_tree(self._ctx, _vp(device_nodes), node_bytes, _vp(device_types), type_bytes, levels, dim))
+
+    def device_alloc(self, nbytes: int) -> int:
+        out = _vp()
+        if not self._lib.vr_device_alloc(self._ctx, nbytes, C.byref(out)):
+            raise RuntimeError(self.last_error())
+        return int(out.value)
+
+    def device_free(self, device_ptr: int) -> bool:
+        return bool(self._lib.vr_device_free(self._ctx, _vp(device_ptr)))
 
     def ipc_get_handle(self, device_ptr: int) -> bytes:
         buf = C.create_string_buffer(64)

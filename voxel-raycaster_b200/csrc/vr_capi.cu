@@ -767,6 +767,19 @@ int vr_assign_native_tree(vr_ctx *c, const void *device_nodes, uint64_t node_byt
     return 1;
 }
 
+int vr_device_alloc(vr_ctx *c, size_t bytes, void **device_ptr) {
+    if (!c || !device_ptr || !bytes) return 0;
+    cudaSetDevice(c->device);
+    VR_CUDA(c, cudaMalloc(device_ptr, bytes));
+    return 1;
+}
+
+int vr_device_free(vr_ctx *c, void *device_ptr) {
+    if (!c || !device_ptr) return 0;
+    VR_CUDA(c, cudaFree(device_ptr));
+    return 1;
+}
+
 int vr_ipc_get_handle(vr_ctx *c, void *device_ptr, void *handle64) {
     if (!c || !device_ptr || !handle64) return 0;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");

@@ -55,6 +55,13 @@ def gather_frame(layout: BandLayout, slab, gathered, frame, dist=None, rank: int
     return frame
 
 
+class _RawCuda:
+    """uint8 device memory owned elsewhere, exposed to torch via the CUDA array interface"""
+
+    def __init__(self, ptr: int, shape) -> None:
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
 class FramePipeline:
     """Double-buffered multi-GPU frame loop: the gather (+ un-interleave, + optional device->host copy on rank 0)
     of frame k runs on a communication stream while the compute stream already renders frame k+1 into the
@@ -79,17 +86,19 @@ class FramePipeline:
         if caster is not None:
             # two frame buffers on the root, mapped into every other rank
             if rank == 0:
-                self.frames = [self.frame, torch.empty_like(self.frame)]
-                # torch sub-allocates: export (IPC handle of the underlying cudaMalloc block, byte offset)
-                handles = []
-                for f in self.frames:
-                    shared = f.untyped_storage()._share_cuda_()
-                    handles.append((bytes(shared[1]), int(shared[3]) + f.storage_offset()))
+                # cudaMalloc'ed by the caster (torch's caching allocator memory is not reliably IPC-exportable),
+                # wrapped as torch tensors through __cuda_array_interface__
+                shape = tuple(self.frame.shape)
+                nbytes = self.frame.numel()
+                self.frame_ptrs = [caster.device_alloc(nbytes) for _ in range(2)]
+                self.frames = [torch.as_tensor(_RawCuda(p, shape), device=device) for p in self.frame_ptrs]
+                self.frame = self.frames[0]
+                handles = [caster.ipc_get_handle(p) for p in self.frame_ptrs]
             else:
                 handles = [None, None]
             dist.broadcast_object_list(handles, src=0)
-            self.frame_ptrs = ([f.data_ptr() for f in self.frames] if rank == 0
-                               else [caster.ipc_open_handle(h) + off for h, off in handles])
+            if rank != 0:
+                self.frame_ptrs = [caster.ipc_open_handle(h) for h in handles]
         self.rendered = [torch.cuda.Event() for _ in range(2)]
         self.collected = [torch.cuda.Event() for _ in range(2)]
         self.k = 0
