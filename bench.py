@@ -153,8 +153,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3"])
     ap.add_argument("--mode", default="svo", choices=["svo", "dense"])
-    ap.add_argument("--cpu-row-stride", type=int, default=16, help="oracle sample for cpu_baseline")
-    ap.add_argument("--ref-row-stride", type=int, default=16, help="oracle sample per step for --impl reference")
+    ap.add_argument("--cpu-row-stride", type=int, default=2, help="oracle sample for cpu_baseline (every Nth row; ~25 core-seconds at c3)")
+    ap.add_argument("--ref-row-stride", type=int, default=4, help="oracle sample per step for --impl reference (every Nth row)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--persistent", type=int, default=0, help="1 = persistent-warp octree kernel")
     ap.add_argument("--refill-min", type=int, default=8)
