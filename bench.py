@@ -43,6 +43,14 @@ def bench_scene(config: str = "c3", with_volume: bool = True):
     """The named workload.  c3 = BASELINE.json configs[2]: 1024^3 sparse (shell) terrain, 3840x2160,
     one shadow light (light 0 is the only one the reference kernel reads), max_distance 3N."""
     S = package().scene
+    if config == "c4":
+        # BASELINE configs[3]: 4096^3 deep SVO (12 levels), 7680x4320, 1 shadow light; the volume (64 GiB) is never
+        # materialised: the octree is built from the solid z-range of every column
+        n = 4096
+        lo, hi = S.terrain_columns(n, "shell")
+        pos, direction = S.make_camera(n, hi, BENCH_CAMERA)
+        return S.Scene(n, None, 7680, 4320, pos, direction, S.make_lights(n, 1), max_distance=3 * n, name="c4-shell",
+                       columns=(lo, hi) if with_volume else None)
     if not with_volume:
         # camera / lights / atlas only (ranks > 0 receive the octree by broadcast)
         table = {"c1": (64, 1280, 720), "c2": (256, 1920, 1080), "c3": (1024, 3840, 2160)}
@@ -151,7 +159,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--mode", default="svo", choices=["svo", "dense"])
     ap.add_argument("--cpu-row-stride", type=int, default=2, help="oracle sample for cpu_baseline (every Nth row; ~25 core-seconds at c3)")
     ap.add_argument("--ref-row-stride", type=int, default=4, help="oracle sample per step for --impl reference (every Nth row)")
@@ -200,6 +208,8 @@ def main() -> None:
     t_build = time.perf_counter()
     if scene.volume is not None:
         must(c.assign_map(scene.volume), "assign_map")          # dense upload + 64-tree build
+    elif scene.columns is not None:
+        must(c.assign_columns(scene.columns[0], scene.columns[1]), "assign_columns")   # 64-tree from column z-ranges
     t_build = time.perf_counter() - t_build
     bcast_bytes = 0
     if world > 1 and use_svo:
@@ -349,14 +359,14 @@ def main() -> None:
                         "node_bytes_fetched_per_launch": 16.0 * node_fetches / world}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            dt, sample_rays, threads = oracle_sample(bench_scene(args.config) if scene.volume is None else scene, args.cpu_row_stride)
+            dt, sample_rays, threads = oracle_sample(scene, args.cpu_row_stride * (8 if args.config == "c4" else 1))
             cpu = {"value": sample_rays / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                    "sample": f"every {args.cpu_row_stride}th row of the frame ({sample_rays} rays, {dt:.1f} s); dense DDA restatement of the OpenCL kernel"}
         out = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
-            "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}",
+            "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
                        "mode": args.mode, "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,

@@ -63,6 +63,11 @@ int vr_assign_lights(vr_ctx *ctx, const float *packed, int count);
 int vr_assign_map(vr_ctx *ctx, const int8_t *voxels, int nx, int ny, int nz);
 int vr_release_map(vr_ctx *ctx);
 
+/* Extension: a map given as solid z-ranges per column -- lo/hi are dim*dim int32 arrays indexed
+ * x + dim*y, column solid for lo <= z <= hi, every solid voxel has value `type` (5 or 6).  Builds the octree
+ * without materialising the dim^3 volume (4096^3 would be 64 GiB); only the octree traversal is then available. */
+int vr_assign_columns(vr_ctx *ctx, const int32_t *lo, const int32_t *hi, int dim, int type);
+
 /* CLCaster::assign_octree / release_octree (ref include/CLCaster.h:127-128, src/CLCaster.cpp:102-131):
  * copies the reference-format child-descriptor buffer (ref include/map/Octree.h:89-94) and registers
  * the OCTREE_ROOT_INDEX setting.  attach_lookup / attach may be NULL (the reference uploads zeros). */

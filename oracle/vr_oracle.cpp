@@ -299,7 +299,12 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
             status = VRO_ST_OOB;
             break;
         }
-        voxel_data = (int)s->map[(size_t)voxel.x + (size_t)X * ((size_t)voxel.y + (size_t)Z * (size_t)voxel.z)]; /* :569 */
+        if (s->map) {
+            voxel_data = (int)s->map[(size_t)voxel.x + (size_t)X * ((size_t)voxel.y + (size_t)Z * (size_t)voxel.z)]; /* :569 */
+        } else {                                                          /* column-table map, vr_oracle.h */
+            const size_t c = (size_t)voxel.x + (size_t)X * (size_t)voxel.y;
+            voxel_data = (voxel.z >= s->col_lo[c] && voxel.z <= s->col_hi[c]) ? 5 : 0;
+        }
         if (COUNT) {
             k.dda_steps++;
             if (count_svo) svo_lookup(s, voxel, cell, k);
@@ -479,7 +484,7 @@ void vro_get_oct_vox(const uint64_t *desc, int64_t root_index, int64_t octdim, c
 
 int vro_raycast(const vro_scene *s, int y0, int y1, int row_stride, uint8_t *rgba, vro_aux *aux,
                 vro_counters *counters, int count_svo, int num_threads) {
-    if (!s || !s->ray_table || !s->map || !s->lights || !s->atlas || !rgba) return -1;
+    if (!s || !s->ray_table || (!s->map && !(s->col_lo && s->col_hi)) || !s->lights || !s->atlas || !rgba) return -1;
     if (count_svo && !s->oct_desc) return -2;
     y0 = std::max(y0, 0);
     y1 = std::min(y1, (int)s->height);

@@ -63,6 +63,11 @@ typedef struct vro_scene {
     int32_t max_distance;
     /* extension beyond the reference: number of shadow lights, 1 = reference      */
     int32_t shadow_lights;
+    /* widened map access for volumes too large to materialise (4096^3 = 64 GiB): when `map` is
+     * NULL, voxel (x,y,z) holds 5 iff col_lo[x + X*y] <= z <= col_hi[x + X*y], else 0.  Same loop, same arithmetic;
+     * only the `map[...]` load of kernel:569 is answered by the column table. */
+    const int32_t *col_lo;
+    const int32_t *col_hi;
 } vro_scene;
 
 /* Per-pixel auxiliary record, 32 bytes.  The reference kernel only writes RGBA8; these expose

@@ -43,3 +43,27 @@ def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False,
     if rc != 0:
         raise RuntimeError(f"emu_raycast failed: {rc}")
     return rgba, aux
+
+
+def _tree(fn, *args):
+    cap_nodes, cap_types = 1 << 22, 1 << 26
+    nodes = np.zeros((cap_nodes, 4), dtype=np.uint32)
+    types = np.zeros(cap_types, dtype=np.uint8)
+    ntypes, levels = C.c_long(0), C.c_int(0)
+    fn.restype = C.c_long
+    n = fn(*args, nodes.ctypes.data_as(C.c_void_p), C.c_long(cap_nodes), types.ctypes.data_as(C.c_void_p), C.c_long(cap_types),
+           C.byref(ntypes), C.byref(levels))
+    if n < 0:
+        raise RuntimeError(f"tree build failed: {n}")
+    return nodes[:n].copy(), types[: ntypes.value].copy(), levels.value
+
+
+def tree_from_dense(volume: np.ndarray):
+    vol = np.ascontiguousarray(volume, dtype=np.int8)
+    return _tree(lib().emu_tree_from_dense, vol.ctypes.data_as(C.c_void_p), C.c_int(vol.shape[0]))
+
+
+def tree_from_columns(lo: np.ndarray, hi: np.ndarray, voxel_type: int = 5):
+    lo = np.ascontiguousarray(lo, dtype=np.int32)
+    hi = np.ascontiguousarray(hi, dtype=np.int32)
+    return _tree(lib().emu_tree_from_columns, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), C.c_int(lo.shape[0]), C.c_int(voxel_type))

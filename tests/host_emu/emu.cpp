@@ -54,3 +54,26 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
         }
     return 0;
 }
+
+/* 64-tree builders exposed for CPU tests: both write up to cap_nodes 16-byte nodes / cap_types bytes and return
+ * the node count (types count in *ntypes, levels in *levels); -1 on failure. */
+static long emu_export(const vr_native_tree &t, void *nodes, long cap_nodes, uint8_t *types, long cap_types, long *ntypes, int *levels) {
+    if ((long)t.nodes.size() > cap_nodes || (long)t.leaf_types.size() > cap_types) return -2;
+    memcpy(nodes, t.nodes.data(), t.nodes.size() * sizeof(vr_node));
+    memcpy(types, t.leaf_types.data(), t.leaf_types.size());
+    *ntypes = (long)t.leaf_types.size();
+    *levels = t.levels;
+    return (long)t.nodes.size();
+}
+
+extern "C" long emu_tree_from_dense(const int8_t *map, int n, void *nodes, long cap_nodes, uint8_t *types, long cap_types, long *ntypes, int *levels) {
+    vr_native_tree t;
+    if (!vr_native_from_dense(map, n, t)) return -1;
+    return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
+}
+
+extern "C" long emu_tree_from_columns(const int32_t *lo, const int32_t *hi, int n, int type, void *nodes, long cap_nodes, uint8_t *types, long cap_types, long *ntypes, int *levels) {
+    vr_native_tree t;
+    if (!vr_native_from_columns(lo, hi, n, (uint8_t)type, t)) return -1;
+    return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
+}

@@ -35,6 +35,7 @@ class VroScene(C.Structure):
         ("oct_desc", C.POINTER(C.c_uint64)), ("oct_desc_len", C.c_uint64),
         ("octdim", C.c_int64), ("oct_root_index", C.c_int64),
         ("max_distance", C.c_int32), ("shadow_lights", C.c_int32),
+        ("col_lo", C.POINTER(C.c_int32)), ("col_hi", C.POINTER(C.c_int32)),
     ]
 
 
@@ -115,14 +116,22 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
     w, h = scene.width, scene.height
     if ray_table is None:
         ray_table = make_ray_table(w, h)
-    vol = np.ascontiguousarray(scene.volume, dtype=np.int8)
+    columns = getattr(scene, "columns", None)
+    vol = np.ascontiguousarray(scene.volume, dtype=np.int8) if scene.volume is not None else None
     lights = np.ascontiguousarray(scene.lights, dtype=np.float32)
     atlas = np.ascontiguousarray(scene.atlas, dtype=np.uint8)
     s = VroScene()
     s.width, s.height = w, h
     s.ray_table = ray_table.ctypes.data_as(C.POINTER(C.c_float))
-    s.map = vol.ctypes.data_as(C.POINTER(C.c_int8))
-    s.map_dim[:] = [vol.shape[2], vol.shape[1], vol.shape[0]]
+    if vol is not None:
+        s.map = vol.ctypes.data_as(C.POINTER(C.c_int8))
+        s.map_dim[:] = [vol.shape[2], vol.shape[1], vol.shape[0]]
+    else:
+        col_lo = np.ascontiguousarray(columns[0], dtype=np.int32)
+        col_hi = np.ascontiguousarray(columns[1], dtype=np.int32)
+        s.col_lo = col_lo.ctypes.data_as(C.POINTER(C.c_int32))
+        s.col_hi = col_hi.ctypes.data_as(C.POINTER(C.c_int32))
+        s.map_dim[:] = [scene.n, scene.n, scene.n]
     s.cam_dir[:] = [float(v) for v in scene.cam_dir]
     s.cam_pos[:] = [float(v) for v in scene.cam_pos]
     s.trig[:] = [float(v) for v in trig_of(scene.cam_dir)]

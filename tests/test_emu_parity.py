@@ -55,3 +55,33 @@ def test_native_tree_matches_dense(pkg, oracle):
     ref_rgba, ref_aux, _ = oracle.raycast(scene, table)
     rgba, aux = emu_lib.raycast(scene, table, use_svo=True)
     assert_same_frame(ref_rgba, ref_aux, rgba, aux, "random16")
+
+
+@pytest.mark.parametrize("n,variant", [(16, "shell"), (64, "shell"), (64, "solid"), (128, "shell"), (256, "shell")])
+def test_column_builder_equals_dense_builder(pkg, n, variant):
+    """vr_native_from_columns (no N^3 volume, needed for 4096^3) must emit exactly the arrays
+    vr_native_from_dense emits for the materialised map: same nodes, same order, same leaf types."""
+    S = pkg.scene
+    lo, hi = S.terrain_columns(n, variant)
+    vol = S.terrain_map(n, variant)
+    a_nodes, a_types, a_levels = emu_lib.tree_from_dense(vol)
+    b_nodes, b_types, b_levels = emu_lib.tree_from_columns(lo, hi)
+    assert a_levels == b_levels and a_nodes.shape == b_nodes.shape
+    assert np.array_equal(a_nodes, b_nodes) and np.array_equal(a_types, b_types)
+
+
+def test_column_builder_irregular(pkg):
+    rng = np.random.default_rng(11)
+    n = 32
+    lo = rng.integers(0, n, size=(n, n)).astype(np.int32)
+    hi = lo + rng.integers(-3, 6, size=(n, n)).astype(np.int32)       # some empty columns (hi < lo), some past the top
+    vol = np.zeros((n, n, n), np.int8)
+    for y in range(n):
+        for x in range(n):
+            if hi[y, x] >= lo[y, x]:
+                vol[lo[y, x] : min(hi[y, x], n - 1) + 1, y, x] = 6
+    a = emu_lib.tree_from_dense(vol)
+    b = emu_lib.tree_from_columns(lo, hi, 6)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    empty = emu_lib.tree_from_columns(np.ones((16, 16), np.int32), np.zeros((16, 16), np.int32))
+    assert empty[0].shape == (1, 4) and not empty[0][0, :2].any()

@@ -277,3 +277,43 @@ def test_persistent_warps(pkg, oracle, refill_min):
     assert c.compute(), c.last_error()
     assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"persistent c1 refill={refill_min}")
     c.close()
+
+
+def test_columns_equal_dense_1024(pkg):
+    """assign_columns (octree built from solid z-ranges per column, no N^3 volume) renders the same frame as
+    assign_map on the materialised 1024^3 volume."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    S = pkg.scene
+    a = make_caster(pkg, scene, True, assign_octree=False)
+    assert a.compute()
+    want, want_aux = a.draw(), a.read_aux()
+    a.close()
+    cols = S.Scene(scene.n, None, scene.width, scene.height, scene.cam_pos, scene.cam_dir, scene.lights,
+                   max_distance=scene.max_distance, columns=S.terrain_columns(scene.n, "shell"))
+    b = make_caster(pkg, cols, True)
+    assert b.compute(), b.last_error()
+    assert np.array_equal(b.draw(), want)
+    got_aux = b.read_aux()
+    for f in AUX_FIELDS:
+        assert np.array_equal(got_aux[f], want_aux[f]), f
+    b.close()
+
+
+def test_deep_tree_4096(pkg, oracle):
+    """BASELINE config 4 depth: 4096^3 (12 octree levels = 6 levels of the 64-tree), octree built from columns.
+    Checker: the oracle walking the same column table (vr_oracle.h: widened map access), every 40th row."""
+    S = pkg.scene
+    n = 4096
+    lo, hi = S.terrain_columns(n, "shell")
+    pos, direction = S.make_camera(n, hi, 9)
+    scene = S.Scene(n, None, 1920, 1080, pos, direction, S.make_lights(n), max_distance=3 * n, columns=(lo, hi))
+    c = make_caster(pkg, scene, True)
+    assert c.stats().levels == 6
+    assert c.compute(), c.last_error()
+    got, aux = c.draw(), c.read_aux()
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, row_stride=40)
+    assert_same_frame(ref_rgba[::40], ref_aux[::40], got[::40], aux[::40], "4096^3 rows")
+    assert (aux["flags"] & 1).mean() > 0.3 and aux["steps_total"].max() > 2000
+    c.close()

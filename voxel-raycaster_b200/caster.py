@@ -48,6 +48,7 @@ SYMBOLS = {
     "vr_assign_lights": (_i, [_vp, _f32p, _i]),
     "vr_assign_map": (_i, [_vp, _i8p, _i, _i, _i]),
     "vr_release_map": (_i, [_vp]),
+    "vr_assign_columns": (_i, [_vp, _i32p, _i32p, _i, _i]),
     "vr_assign_octree": (_i, [_vp, _u64p, C.POINTER(C.c_uint32), _u64p, C.c_uint64, C.c_uint64]),
     "vr_release_octree": (_i, [_vp]),
     "vr_assign_camera": (_i, [_vp, _f32p, _f32p]),
@@ -184,6 +185,12 @@ class CUDACaster:
         vol = np.ascontiguousarray(volume, dtype=np.int8)
         nz, ny, nx = vol.shape
         return bool(self._lib.vr_assign_map(self._ctx, _ptr(vol, C.c_int8), nx, ny, nz))
+
+    def assign_columns(self, lo: np.ndarray, hi: np.ndarray, voxel_type: int = 5) -> bool:
+        """lo, hi: int32 [y, x]; column (x, y) is solid for lo <= z <= hi.  Octree traversal only."""
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        return bool(self._lib.vr_assign_columns(self._ctx, _ptr(lo, C.c_int32), _ptr(hi, C.c_int32), lo.shape[0], voxel_type))
 
     def release_map(self) -> bool:
         return bool(self._lib.vr_release_map(self._ctx))
@@ -364,10 +371,13 @@ class CUDACaster:
         must(self.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n), "add OCTDIM")
         must(self.add_to_settings_buffer("using_octree", "OCTENABLED", 0 if use_octree else 1), "add OCTENABLED")
         must(self.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance), "add MAX_DISTANCE")
-        if assign_octree:
-            desc, root = octree_generate(scene.volume)
-            must(self.assign_octree(desc, root), "assign_octree")
-        must(self.assign_map(scene.volume), "assign_map")
+        if scene.volume is None:
+            must(self.assign_columns(scene.columns[0], scene.columns[1]), "assign_columns")
+        else:
+            if assign_octree:
+                desc, root = octree_generate(scene.volume)
+                must(self.assign_octree(desc, root), "assign_octree")
+            must(self.assign_map(scene.volume), "assign_map")
         must(self.assign_camera(scene.cam_dir, scene.cam_pos), "assign_camera")
         must(self.create_viewport(scene.width, scene.height, 0.625 * 90.0, 90.0), "create_viewport")
         must(self.assign_lights(scene.lights), "assign_lights")

@@ -469,6 +469,16 @@ int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
     return 1;
 }
 
+int vr_assign_columns(vr_ctx *c, const int32_t *lo, const int32_t *hi, int dim, int type) {
+    if (!c) return 0;
+    if (!lo || !hi || dim < 1 || (dim & (dim - 1)) || (type != 5 && type != 6)) return fail(c, "assign_columns: bad arguments");
+    cudaSetDevice(c->device);
+    if (c->d_map) vr_release_map(c);
+    vr_native_tree t;
+    if (!vr_native_from_columns(lo, hi, dim, (uint8_t)type, t)) return fail(c, "assign_columns: 64-tree build failed");
+    return upload_tree(c, t, true);
+}
+
 int vr_release_map(vr_ctx *c) {
     if (!c) return 0;
     const bool had = c->d_map != nullptr;

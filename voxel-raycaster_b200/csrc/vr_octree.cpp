@@ -3,6 +3,7 @@
 
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 
 namespace {
@@ -300,6 +301,104 @@ bool vr_native_from_ref(const uint64_t *desc, uint64_t len, uint64_t root_index,
         const int8_t v = types[(size_t)x + (size_t)dim * ((size_t)y + (size_t)dim * (size_t)z)];
         return (v == 5 || v == 6) ? (uint8_t)v : (uint8_t)5;
     }, out);
+    return true;
+}
+
+bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8_t type, vr_native_tree &out) {
+    if (!lo || !hi || dim < 1 || !is_pow2(dim)) return false;
+    int L = 1;
+    while ((1 << (2 * L)) < dim) L++;
+    const int gl = (dim + 3) / 4;                         /* leaf bricks per axis */
+    struct Leaf { uint64_t key, mask; };
+    /* BFS order inside a level == lexicographic order of the root-to-node child-slot path; the path of a leaf
+     * brick (bx,by,bz) packs one 6-bit slot per level */
+    auto key_of = [L](int bx, int by, int bz) {
+        uint64_t k = 0;
+        for (int j = L - 2; j >= 0; j--) {
+            const int sx = (bx >> (2 * j)) & 3, sy = (by >> (2 * j)) & 3, sz = (bz >> (2 * j)) & 3;
+            k = (k << 6) | (uint64_t)(sx | (sy << 2) | (sz << 4));
+        }
+        return k;
+    };
+    std::vector<std::vector<Leaf>> rows((size_t)gl);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int by = 0; by < gl; by++) {
+        std::vector<Leaf> &acc = rows[(size_t)by];
+        for (int bx = 0; bx < gl; bx++) {
+            int zmin = dim, zmax = -1;
+            int clo[16], chi[16];
+            for (int c = 0; c < 16; c++) {
+                const int x = 4 * bx + (c & 3), y = 4 * by + (c >> 2);
+                clo[c] = 1; chi[c] = 0;
+                if (x >= dim || y >= dim) continue;
+                int a = lo[(size_t)x + (size_t)dim * (size_t)y], b = hi[(size_t)x + (size_t)dim * (size_t)y];
+                if (a < 0) a = 0;
+                if (b > dim - 1) b = dim - 1;
+                if (a > b) continue;
+                clo[c] = a; chi[c] = b;
+                if (a < zmin) zmin = a;
+                if (b > zmax) zmax = b;
+            }
+            for (int bz = zmin >> 2; zmax >= 0 && bz <= (zmax >> 2); bz++) {
+                uint64_t m = 0;
+                for (int c = 0; c < 16; c++)
+                    for (int cz = 0; cz < 4; cz++) {
+                        const int z = 4 * bz + cz;
+                        if (z >= clo[c] && z <= chi[c]) m |= 1ull << (c | (cz << 4));
+                    }
+                if (m) acc.push_back({key_of(bx, by, bz), m});
+            }
+        }
+    }
+    std::vector<Leaf> level;
+    {
+        size_t total = 0;
+        for (auto &r : rows) total += r.size();
+        level.reserve(total);
+        for (auto &r : rows) { level.insert(level.end(), r.begin(), r.end()); std::vector<Leaf>().swap(r); }
+    }
+    std::sort(level.begin(), level.end(), [](const Leaf &a, const Leaf &b) { return a.key < b.key; });
+    /* levels[l] = (key, mask) of the nodes of level l, sorted; built bottom-up by grouping on key >> 6 */
+    std::vector<std::vector<Leaf>> levels((size_t)L);
+    levels[(size_t)L - 1].swap(level);
+    for (int l = L - 2; l >= 0; l--) {
+        const std::vector<Leaf> &kids = levels[(size_t)l + 1];
+        std::vector<Leaf> &mine = levels[(size_t)l];
+        for (const Leaf &k : kids) {
+            const uint64_t pk = k.key >> 6;
+            if (mine.empty() || mine.back().key != pk) mine.push_back({pk, 0});
+            mine.back().mask |= 1ull << (k.key & 63);
+        }
+    }
+    if (levels[0].empty()) levels[0].push_back({0, 0});          /* empty map: a root without children */
+    out.nodes.clear();
+    out.leaf_types.clear();
+    out.levels = L;
+    out.dim = dim;
+    out.solid_voxels = 0;
+    size_t start = 0;
+    for (int l = 0; l < L; l++) {
+        const std::vector<Leaf> &cur = levels[(size_t)l];
+        const size_t next_start = start + cur.size();
+        size_t child = 0;
+        for (const Leaf &n : cur) {
+            vr_node v;
+            v.mask_lo = (uint32_t)n.mask;
+            v.mask_hi = (uint32_t)(n.mask >> 32);
+            v.aux = 0;
+            const int pc = __builtin_popcountll(n.mask);
+            if (l == L - 1) {
+                v.child_base = (uint32_t)out.solid_voxels;
+                out.solid_voxels += (uint64_t)pc;
+            } else {
+                v.child_base = (uint32_t)(next_start + child);
+                child += (size_t)pc;
+            }
+            out.nodes.push_back(v);
+        }
+        start = next_start;
+    }
+    out.leaf_types.assign(out.solid_voxels ? (size_t)out.solid_voxels : 1, out.solid_voxels ? type : (uint8_t)0);
     return true;
 }
 

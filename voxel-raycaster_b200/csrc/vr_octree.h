@@ -44,6 +44,11 @@ bool vr_native_from_dense(const int8_t *map, int dim, vr_native_tree &out);
 bool vr_native_from_ref(const uint64_t *desc, uint64_t len, uint64_t root_index, int dim, const int8_t *types,
                         vr_native_tree &out);
 
+/* Native tree straight from a column description, without materialising the N^3 volume (4096^3 = 64 GiB):
+ * column (x, y) is solid for lo[x + dim*y] <= z <= hi[x + dim*y] (empty when lo > hi), every solid voxel has
+ * value `type`.  Produces exactly the arrays vr_native_from_dense gives for the equivalent dense map. */
+bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8_t type, vr_native_tree &out);
+
 /* Point query on the native tree: voxel value (5/6) or 0, and the empty-cell shift if empty. */
 int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shift);
 

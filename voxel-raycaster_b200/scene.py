@@ -73,6 +73,20 @@ def heightfield(n: int, seed: int = SEED_MAP) -> np.ndarray:
     return np.clip(h, 1, n - 2)
 
 
+def terrain_columns(n: int, variant: str = "shell", seed: int = SEED_MAP) -> tuple[np.ndarray, np.ndarray]:
+    """Column description (lo, hi) int32 [y, x] of terrain_map(n, variant): voxel (x, y, z) is 5 for lo <= z <= hi."""
+    h = heightfield(n, seed)
+    if variant == "solid":
+        lo = np.zeros_like(h)
+    elif variant == "shell":
+        hp = np.pad(h, 1, mode="edge")
+        nb = np.minimum(np.minimum(hp[:-2, 1:-1], hp[2:, 1:-1]), np.minimum(hp[1:-1, :-2], hp[1:-1, 2:]))
+        lo = np.minimum(h - 1, nb)
+    else:
+        raise ValueError(variant)
+    return np.maximum(lo, 0).astype(np.int32), h.astype(np.int32)
+
+
 def terrain_map(n: int, variant: str = "shell", seed: int = SEED_MAP, reflect_fraction: float = 0.0) -> np.ndarray:
     """Dense voxel volume as int8 array [z, y, x] (flat index x + n*(y + n*z), ref ArrayMap.cpp:39-46).
 
@@ -120,7 +134,7 @@ class Scene:
     """Everything `CLCaster` is given before `validate()` (ref src/Application.cpp:27-88)."""
 
     n: int
-    volume: np.ndarray                     # int8 [z, y, x]
+    volume: np.ndarray | None              # int8 [z, y, x]; None when only `columns` is given (4096^3)
     width: int
     height: int
     cam_pos: np.ndarray                    # float32[3]
@@ -130,6 +144,7 @@ class Scene:
     tile: int = 16
     max_distance: int = 20                 # kernel:326
     name: str = ""
+    columns: tuple | None = None           # (lo, hi) int32 [y, x] when the volume is given as solid z-ranges per column
 
 
 def make_lights(n: int, count: int = 1) -> np.ndarray:
