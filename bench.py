@@ -153,13 +153,110 @@ def run_reference(args) -> None:
     }))
 
 
+def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
+    """--config c5 (BASELINE configs[4], not the headline): 64 cameras x 1920x1080 over the 1024^3 SVO, view-batch
+    split: view v is rendered by rank v % world with vr_compute_views; a step is the whole batch."""
+    S = pkg.scene
+    n, W, H, views = 1024, 1920, 1080, 64
+    h = S.heightfield(n)
+    cams = np.array([np.concatenate([d, p]) for p, d in (S.make_camera(n, h, i) for i in range(views))], dtype=np.float32)
+    mine = cams[rank::world].copy()
+    c = pkg.CUDACaster()
+
+    def must(ok, what):
+        if not ok:
+            raise RuntimeError(f"{what}: {c.last_error()}")
+
+    must(c.init(local_rank), "init")
+    must(c.add_to_settings_buffer("octree_dimensions", "OCTDIM", n), "OCTDIM")
+    must(c.add_to_settings_buffer("using_octree", "OCTENABLED", 0), "OCTENABLED")
+    must(c.add_to_settings_buffer("max_distance", "MAX_DISTANCE", 3 * n), "MAX_DISTANCE")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    must(c.set_stream(stream.cuda_stream), "set_stream")
+    lo, hi = S.terrain_columns(n, "shell")
+    must(c.assign_columns(lo, hi), "assign_columns")        # every rank builds the 3.9 MB octree itself (0.2 s)
+    cam_dir, cam_pos = mine[0, :2].copy(), mine[0, 2:].copy()
+    must(c.assign_camera(cam_dir, cam_pos), "assign_camera")
+    must(c.create_viewport(W, H, 56.25, 90.0), "create_viewport")
+    lights = S.make_lights(n, 1)
+    must(c.assign_lights(lights), "assign_lights")
+    must(c.create_texture_atlas(S.synthetic_atlas(), (16, 16)), "atlas")
+    must(c.validate(), "validate")
+    frames = torch.empty((len(mine), H, W, 4), dtype=torch.uint8, device=dev)
+    # rays per batch from one untimed aux pass per view
+    must(c.enable_aux(True), "aux")
+    rays = 0
+    for cam in mine:
+        cam_dir[:], cam_pos[:] = cam[:2], cam[2:]
+        must(c.compute_into(frames[0].data_ptr()), "compute_into")
+        torch.cuda.synchronize()
+        aux = c.read_aux()
+        rays += int((aux["status"] != 0).sum() + ((aux["flags"] & 1) != 0).sum())
+    must(c.enable_aux(False), "aux off")
+    total = torch.tensor([rays], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(total)
+    rays = int(total.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        must(c.compute_views(mine, frames.data_ptr()), "compute_views")
+    barrier()
+    l0 = c.stats().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            must(c.compute_views(mine, frames.data_ptr()), "compute_views")
+        ev1.record(stream)
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    launches = c.stats().kernel_launches - l0
+    # e2e: every frame of the batch is copied to pinned host memory inside the timed region
+    host = torch.empty((len(mine), H, W, 4), dtype=torch.uint8).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        must(c.compute_views(mine, frames.data_ptr()), "compute_views")
+        host.copy_(frames, non_blocking=True)
+    barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = 1e3 * float(e2e.item()) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mrays/s (primary + shadow rays), 64 views x 1920x1080 over 1024^3 SVO", "value": rays / (ms / 1e3) / 1e6,
+            "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gpu_launches": int(launches),
+            "config": {"workload": "c5: 64 random cameras x 1920x1080, 1024^3 shell terrain SVO, primary + 1 shadow light (BASELINE configs[4], not the headline)",
+                       "parallelism": f"views{world}: view v on rank v % {world}", "views": views, "rays_per_batch": rays,
+                       "ms_per_view": ms / (views / world) if world else None},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": int(frames.numel())},
+            "clocks": clocks.summary()}))
+    c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--mode", default="svo", choices=["svo", "dense"])
     ap.add_argument("--cpu-row-stride", type=int, default=2, help="oracle sample for cpu_baseline (every Nth row; ~25 core-seconds at c3)")
     ap.add_argument("--ref-row-stride", type=int, default=4, help="oracle sample per step for --impl reference (every Nth row)")
@@ -190,6 +287,9 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = package()
+    if args.config == "c5":
+        run_views(args, pkg, torch, dist, rank, world, local_rank, dev)
+        return
     use_svo = args.mode == "svo"
     scene = bench_scene(args.config, with_volume=(rank == 0 or not use_svo))
     c = pkg.CUDACaster()

@@ -118,6 +118,11 @@ int vr_sync(vr_ctx *ctx);
  * image, asynchronously on the context stream: used by the multi-GPU gather. */
 int vr_compute_into(vr_ctx *ctx, void *device_rgba);
 
+/* View batches (BASELINE config 5): renders `count` frames of the same scene, one per camera, back to back on
+ * the context stream into `device_rgba` (count consecutive frames).  cameras = count x 5 floats
+ * {inclination, azimuth, x, y, z}; the assigned camera is not touched.  Asynchronous like vr_compute_into. */
+int vr_compute_views(vr_ctx *ctx, const float *cameras, int count, void *device_rgba);
+
 /* CLCaster::draw (ref include/CLCaster.h:145): headless replacement.  Copies the last frame to host
  * memory (width*height*4 bytes, or the local slab when banded). */
 int vr_read_framebuffer(vr_ctx *ctx, uint8_t *rgba_out, size_t bytes);

@@ -317,3 +317,27 @@ def test_deep_tree_4096(pkg, oracle):
     assert_same_frame(ref_rgba[::40], ref_aux[::40], got[::40], aux[::40], "4096^3 rows")
     assert (aux["flags"] & 1).mean() > 0.3 and aux["steps_total"].max() > 2000
     c.close()
+
+
+def test_view_batch(pkg, oracle):
+    """BASELINE config 5 mechanism: a batch of cameras over one scene (vr_compute_views); every frame equals the
+    oracle's frame for that camera."""
+    import torch
+
+    S = pkg.scene
+    n = 64
+    vol = S.terrain_map(n, "shell", reflect_fraction=0.03)
+    h = S.heightfield(n)
+    cams = np.array([np.concatenate([d, p]) for p, d in (S.make_camera(n, h, i) for i in range(6))], dtype=np.float32)
+    scene = S.Scene(n, vol, 320, 200, cams[0, 2:].copy(), cams[0, :2].copy(), S.make_lights(n), max_distance=3 * n)
+    c = make_caster(pkg, scene, True, assign_octree=False, aux=False)
+    out = torch.zeros((len(cams), 200, 320, 4), dtype=torch.uint8, device="cuda:0")
+    out[...] = torch.tensor([255, 255, 255, 100], dtype=torch.uint8, device="cuda:0")
+    assert c.compute_views(cams, out.data_ptr()) and c.sync()
+    frames = out.cpu().numpy()
+    for i, cam in enumerate(cams):
+        scene.cam_dir[:] = cam[:2]
+        scene.cam_pos[:] = cam[2:]
+        ref, _, _ = oracle.raycast(scene, want_aux=False)
+        assert np.array_equal(frames[i], ref), f"view {i}"
+    c.close()

@@ -68,6 +68,7 @@ SYMBOLS = {
     "vr_compute_async": (_i, [_vp]),
     "vr_sync": (_i, [_vp]),
     "vr_compute_into": (_i, [_vp, _vp]),
+    "vr_compute_views": (_i, [_vp, _f32p, _i, _vp]),
     "vr_read_framebuffer": (_i, [_vp, _u8p, C.c_size_t]),
     "vr_frame_begin": (_i, [_vp]),
     "vr_frame_end": (_i, [_vp, C.POINTER(_u8p)]),
@@ -267,6 +268,12 @@ class CUDACaster:
 
     def compute_into(self, device_ptr: int) -> bool:
         return bool(self._lib.vr_compute_into(self._ctx, _vp(device_ptr)))
+
+    def compute_views(self, cameras: np.ndarray, device_ptr: int) -> bool:
+        """cameras float32 [count, 5] = {inclination, azimuth, x, y, z}; frames land consecutively at device_ptr."""
+        cams = np.ascontiguousarray(cameras, dtype=np.float32)
+        self._keep["views"] = cams
+        return bool(self._lib.vr_compute_views(self._ctx, _ptr(cams, C.c_float), cams.shape[0], _vp(device_ptr)))
 
     def draw(self) -> np.ndarray:
         """Headless `draw`: the last frame as uint8 [rows, width, 4] (rows = local slab when banded)."""

@@ -643,6 +643,22 @@ int vr_compute_into(vr_ctx *c, void *device_rgba) {
     return launch_frame(c, static_cast<uint8_t *>(device_rgba), false);
 }
 
+int vr_compute_views(vr_ctx *c, const float *cameras, int count, void *device_rgba) {
+    if (!c || !cameras || count < 1 || !device_rgba) return 0;
+    cudaSetDevice(c->device);
+    const float *keep_dir = c->cam_dir, *keep_pos = c->cam_pos;
+    const size_t frame_bytes = (size_t)c->width * 4 * (size_t)local_rows_padded(c);
+    int ok = 1;
+    for (int v = 0; v < count && ok; v++) {
+        c->cam_dir = cameras + 5 * (size_t)v;                  /* {inclination, azimuth, x, y, z} */
+        c->cam_pos = cameras + 5 * (size_t)v + 2;
+        ok = launch_frame(c, static_cast<uint8_t *>(device_rgba) + (size_t)v * frame_bytes, false);
+    }
+    c->cam_dir = keep_dir;
+    c->cam_pos = keep_pos;
+    return ok;
+}
+
 int vr_read_framebuffer(vr_ctx *c, uint8_t *rgba_out, size_t bytes) {
     if (!c || !rgba_out) return 0;
     if (!c->d_image[0]) return fail(c, "read_framebuffer: viewport not created");
