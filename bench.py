@@ -264,6 +264,7 @@ def main() -> None:
     ap.add_argument("--persistent", type=int, default=0, help="1 = persistent-warp octree kernel")
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
+    ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
@@ -338,6 +339,8 @@ def main() -> None:
     must(c.validate(), "validate")
     must(c.set_option("persistent", args.persistent) and c.set_option("refill_min", args.refill_min)
          and c.set_option("ctas_per_sm", args.ctas_per_sm), "set_option")
+    if args.l2_persist and use_svo:
+        must(c.set_option("l2_persist", 1), "l2_persist")
 
     W, H = scene.width, scene.height
     layout = pkg.tiles.BandLayout(H, W, BAND_ROWS, world)

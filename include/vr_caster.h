@@ -175,6 +175,11 @@ int vr_ipc_open_handle(vr_ctx *ctx, const void *handle64, void **device_ptr);
 int vr_ipc_close_handle(vr_ctx *ctx, void *device_ptr);
 int vr_push_bands(vr_ctx *ctx, const void *slab, void *frame, void *cuda_stream);
 
+/* Octree::Load (declared, never defined in the reference: include/map/Octree.h:38) and its counterpart: the
+ * traversal octree of this context to / from a file ("VR64" header + node array + leaf types). */
+int vr_octree_save(vr_ctx *ctx, const char *path);
+int vr_octree_load(vr_ctx *ctx, const char *path);
+
 typedef struct vr_stats {
     uint64_t kernel_launches;      /* kernels launched by this context so far                */
     uint64_t frames;

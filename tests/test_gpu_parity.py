@@ -341,3 +341,29 @@ def test_view_batch(pkg, oracle):
         ref, _, _ = oracle.raycast(scene, want_aux=False)
         assert np.array_equal(frames[i], ref), f"view {i}"
     c.close()
+
+
+def test_octree_save_load_and_l2_window(pkg, oracle, tmp_path):
+    """Octree::Load replacement (ref include/map/Octree.h:38, never defined there): a context that only loads the
+    saved octree renders the frame of the context that built it; the L2 access-policy window changes nothing."""
+    scene = pkg.scene.make_scene("features-low")
+    ref_rgba, _, _ = oracle.raycast(scene, want_aux=False)
+    a = make_caster(pkg, scene, True, assign_octree=False, aux=False)
+    path = tmp_path / "scene.vr64"
+    assert a.octree_save(str(path)) and path.stat().st_size > 64
+    assert a.set_option("l2_persist", 1) and a.compute() and np.array_equal(a.draw(), ref_rgba)
+    assert a.set_option("l2_persist", 0) and a.compute() and np.array_equal(a.draw(), ref_rgba)
+    a.close()
+    b = pkg.CUDACaster()
+    assert b.init(0)
+    assert b.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n)
+    assert b.add_to_settings_buffer("using_octree", "OCTENABLED", 0)
+    assert b.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance)
+    assert b.octree_load(str(path)), b.last_error()
+    assert b.assign_camera(scene.cam_dir, scene.cam_pos) and b.create_viewport(scene.width, scene.height)
+    assert b.assign_lights(scene.lights) and b.create_texture_atlas(scene.atlas) and b.validate(), b.last_error()
+    assert b.compute() and np.array_equal(b.draw(), ref_rgba)
+    bad = tmp_path / "bad.vr64"
+    bad.write_bytes(b"VR64" + bytes(40))
+    assert not b.octree_load(str(bad)) and "not a valid octree" in b.last_error()
+    b.close()

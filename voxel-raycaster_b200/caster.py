@@ -89,6 +89,8 @@ SYMBOLS = {
     "vr_ipc_open_handle": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "vr_ipc_close_handle": (_i, [_vp, _vp]),
     "vr_push_bands": (_i, [_vp, _vp, _vp, _vp]),
+    "vr_octree_save": (_i, [_vp, C.c_char_p]),
+    "vr_octree_load": (_i, [_vp, C.c_char_p]),
     "vr_get_stats": (_i, [_vp, C.POINTER(VrStats)]),
     "vr_octree_generate": (_i, [_i8p, _i, _u64p, _u64p, _u64p]),
     "vr_octree_get_voxel": (_i, [_u64p, C.c_uint64, C.c_uint64, _i, _i32p, _i32p, _i32p]),
@@ -362,6 +364,12 @@ class CUDACaster:
 
     def push_bands(self, slab_ptr: int, frame_ptr: int, cuda_stream: int | None = None) -> bool:
         return bool(self._lib.vr_push_bands(self._ctx, _vp(slab_ptr), _vp(frame_ptr), _vp(cuda_stream or 0)))
+
+    def octree_save(self, path: str) -> bool:
+        return bool(self._lib.vr_octree_save(self._ctx, str(path).encode()))
+
+    def octree_load(self, path: str) -> bool:
+        return bool(self._lib.vr_octree_load(self._ctx, str(path).encode()))
 
     def stats(self) -> VrStats:
         s = VrStats()

@@ -714,6 +714,27 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     if (n == "persistent") c->opt.persistent = value != 0;
     else if (n == "refill_min") c->opt.refill_min = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
+    else if (n == "l2_persist") {
+        /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
+        if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");
+        cudaSetDevice(c->device);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        if (value) {
+            int max_win = 0;
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+            size_t bytes = c->n_nodes * sizeof(vr_node);
+            if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;      /* BFS order: top levels first */
+            VR_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+            attr.accessPolicyWindow.base_ptr = c->d_nodes;
+            attr.accessPolicyWindow.num_bytes = bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        }
+        VR_CUDA(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        if (!value) cudaCtxResetPersistingL2Cache();
+    }
     else return fail(c, "set_option: unknown option [%s]", name);
     return 1;
 }
@@ -842,6 +863,59 @@ int vr_push_bands(vr_ctx *c, const void *slab, void *frame, void *cuda_stream) {
                                  (size_t)c->band_stride * band_bytes, slab, band_bytes, band_bytes, (size_t)bands,
                                  cudaMemcpyDefault, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream));
     return 1;
+}
+
+/* On-disk octree: "VR64" | u32 version | i32 dim | i32 levels | u64 nodes | u64 types | vr_node[] | u8[] */
+int vr_octree_save(vr_ctx *c, const char *path) {
+    if (!c || !path) return 0;
+    if (!c->tree_valid && !ensure_tree(c)) return 0;
+    cudaSetDevice(c->device);
+    std::vector<vr_node> nodes(c->n_nodes);
+    std::vector<uint8_t> types(c->n_leaf_types);
+    VR_CUDA(c, cudaMemcpy(nodes.data(), c->d_nodes, nodes.size() * sizeof(vr_node), cudaMemcpyDeviceToHost));
+    VR_CUDA(c, cudaMemcpy(types.data(), c->d_leaf_types, types.size(), cudaMemcpyDeviceToHost));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(c, "octree_save: cannot open %s", path);
+    const uint32_t version = 1;
+    const int32_t dim = c->tree_dim, levels = c->levels;
+    const uint64_t nn = nodes.size(), nt = types.size();
+    bool ok = fwrite("VR64", 1, 4, f) == 4 && fwrite(&version, 4, 1, f) == 1 && fwrite(&dim, 4, 1, f) == 1 &&
+              fwrite(&levels, 4, 1, f) == 1 && fwrite(&nn, 8, 1, f) == 1 && fwrite(&nt, 8, 1, f) == 1 &&
+              fwrite(nodes.data(), sizeof(vr_node), nn, f) == nn && fwrite(types.data(), 1, nt, f) == nt;
+    fclose(f);
+    return ok ? 1 : fail(c, "octree_save: short write to %s", path);
+}
+
+int vr_octree_load(vr_ctx *c, const char *path) {
+    if (!c || !path) return 0;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(c, "octree_load: cannot open %s", path);
+    char magic[4];
+    uint32_t version = 0;
+    int32_t dim = 0, levels = 0;
+    uint64_t nn = 0, nt = 0;
+    bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "VR64", 4) == 0 && fread(&version, 4, 1, f) == 1 && version == 1 &&
+              fread(&dim, 4, 1, f) == 1 && fread(&levels, 4, 1, f) == 1 && fread(&nn, 8, 1, f) == 1 && fread(&nt, 8, 1, f) == 1 &&
+              nn >= 1 && nn < (1ull << 32) && nt >= 1 && levels >= 1 && levels <= VR_MAX_LEVELS && dim >= 1 &&
+              !(dim & (dim - 1)) && (1 << (2 * levels)) >= dim;
+    vr_native_tree t;
+    if (ok) {
+        t.nodes.resize(nn);
+        t.leaf_types.resize(nt);
+        ok = fread(t.nodes.data(), sizeof(vr_node), nn, f) == nn && fread(t.leaf_types.data(), 1, nt, f) == nt;
+    }
+    fclose(f);
+    if (!ok) return fail(c, "octree_load: %s is not a valid octree file", path);
+    /* every child pointer must stay inside the arrays */
+    for (const vr_node &n : t.nodes) {
+        const uint64_t pc = (uint64_t)__builtin_popcountll((uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32));
+        if ((uint64_t)n.child_base + pc > (nn > nt ? nn : nt)) return fail(c, "octree_load: corrupt child pointer in %s", path);
+    }
+    t.levels = levels;
+    t.dim = dim;
+    t.solid_voxels = nt;
+    cudaSetDevice(c->device);
+    return upload_tree(c, t, true);
 }
 
 int vr_get_stats(vr_ctx *c, vr_stats *out) {
