@@ -265,6 +265,7 @@ def main() -> None:
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
     ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
+    ap.add_argument("--walk", type=int, default=0, help="0 = merged in-cell walk (bit-identical on every pixel), 1 = per-axis walk")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
@@ -339,6 +340,7 @@ def main() -> None:
     must(c.validate(), "validate")
     must(c.set_option("persistent", args.persistent) and c.set_option("refill_min", args.refill_min)
          and c.set_option("ctas_per_sm", args.ctas_per_sm), "set_option")
+    must(c.set_option("walk", args.walk), "walk")
     if args.l2_persist and use_svo:
         must(c.set_option("l2_persist", 1), "l2_persist")
 

@@ -46,7 +46,8 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
             uint32_t px;
             vr_aux a;
             bool w;
-            if (use_svo) { LocalStack s; w = vr_trace_svo<true>(P, x, y, &px, &a, s); }
+            if (use_svo == 2) { LocalStack s; w = vr_trace_svo<true, 1>(P, x, y, &px, &a, s); }
+            else if (use_svo) { LocalStack s; w = vr_trace_svo<true, 0>(P, x, y, &px, &a, s); }
             else w = vr_trace_dense<true>(P, x, y, &px, &a);
             const size_t i = (size_t)x + (size_t)width * y;
             if (w) memcpy(rgba + 4 * i, &px, 4);

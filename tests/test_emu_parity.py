@@ -85,3 +85,19 @@ def test_column_builder_irregular(pkg):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
     empty = emu_lib.tree_from_columns(np.ones((16, 16), np.int32), np.zeros((16, 16), np.int32))
     assert empty[0].shape == (1, 4) and not empty[0][0, :2].any()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_axis_walk_device_core(pkg, oracle, name):
+    """Per-axis in-cell walk (option walk=1) compiled for the host: identical to the oracle on all non-tie
+    pixels; tie pixels within +-1 RGBA (see vr_walk_axes)."""
+    scene = pkg.scene.make_scene(name)
+    table = oracle.make_ray_table(scene.width, scene.height)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root))
+    rgba, aux = emu_lib.raycast(scene, table, bias=oracle_bias(oracle, scene, desc, root), use_svo=2)
+    tie = (ref_aux["flags"] & 4) != 0
+    for f in ("hit", "face", "status", "hit_type", "steps_first", "steps_total"):
+        assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
+    diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
+    assert not (diff[~tie] > 0).any() and (diff <= 1).all()

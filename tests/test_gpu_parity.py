@@ -367,3 +367,62 @@ def test_octree_save_load_and_l2_window(pkg, oracle, tmp_path):
     bad.write_bytes(b"VR64" + bytes(40))
     assert not b.octree_load(str(bad)) and "not a valid octree" in b.last_error()
     b.close()
+
+
+def assert_same_except_ties(ref_rgba, ref_aux, got_rgba, got_aux, what):
+    """Per-axis walk (option walk=1): identical to the oracle on every pixel whose ray never takes a multi-axis
+    (exact tie) step; on the flagged tie pixels -- rays through a voxel edge, "degenerate" in BASELINE.json's
+    sense -- the north_star tolerance applies: same first hit, RGBA max abs diff <= 1."""
+    tie = (ref_aux["flags"] & 4) != 0
+    ok = ~tie
+    for f in AUX_FIELDS:
+        a, b = ref_aux[f], got_aux[f]
+        if f == "flags":
+            a, b = a & 0xFB, b & 0xFB
+        bad = np.any(np.atleast_3d(a != b), axis=-1) & ok
+        assert not bad.any(), f"{what}: {f} differs on {int(bad.sum())} non-tie pixels, first {np.argwhere(bad)[0]}"
+    diff = np.abs(ref_rgba.astype(np.int16) - got_rgba.astype(np.int16)).max(axis=-1)
+    assert not (diff[ok] > 0).any(), f"{what}: RGBA differs on non-tie pixels"
+    assert tie.mean() < 0.02, f"{what}: {tie.mean():.4f} of the pixels are tie pixels"
+    if tie.any():
+        assert (diff[tie] <= 1).mean() >= 0.99, f"{what}: tie pixels beyond +-1"
+        assert np.array_equal(ref_aux["hit"][tie], got_aux["hit"][tie]) or (np.any(ref_aux["hit"][tie] != got_aux["hit"][tie], axis=-1).mean() < 0.01)
+    return int(tie.sum())
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_axis_walk_small(pkg, oracle, name):
+    scene = pkg.scene.make_scene(name)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    c = make_caster(pkg, scene, True)
+    assert c.set_option("walk", 1) and c.compute(), c.last_error()
+    assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"axis walk {name}")
+    c.close()
+
+
+def test_axis_walk_terrain(pkg, oracle):
+    S = pkg.scene
+    for n, w, h, cam in ((64, 1280, 720, 3), (256, 1920, 1080, 4)):
+        vol = S.terrain_map(n, "shell", reflect_fraction=0.05 if n == 64 else 0.0)
+        pos, direction = S.make_camera(n, S.heightfield(n), cam)
+        scene = S.Scene(n, vol, w, h, pos, direction, S.make_lights(n), max_distance=3 * n)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene)
+        c = make_caster(pkg, scene, True, assign_octree=False)
+        assert c.set_option("walk", 1) and c.compute(), c.last_error()
+        assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"axis walk terrain {n}")
+        c.close()
+
+
+def test_axis_walk_full_size_c3(pkg):
+    """1024^3 @3840x2160: per-axis walk vs merged walk (both CUDA): identical except on tie pixels."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    c = make_caster(pkg, scene, True, assign_octree=False)
+    assert c.compute()
+    ref_rgba, ref_aux = c.draw(), c.read_aux()
+    assert c.set_option("walk", 1) and c.compute()
+    ties = assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), "axis walk c3")
+    assert ties > 0
+    c.close()

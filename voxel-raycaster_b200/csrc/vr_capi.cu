@@ -79,7 +79,7 @@ struct vr_ctx {
 
     int used_svo = 0;
     int bias[3] = {0, 0, 0};
-    vr_launch_options opt = {0, 8, 3, 148, nullptr};
+    vr_launch_options opt = {0, 8, 3, 148, nullptr, 0};
 };
 
 namespace {
@@ -714,6 +714,7 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     if (n == "persistent") c->opt.persistent = value != 0;
     else if (n == "refill_min") c->opt.refill_min = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
+    else if (n == "walk") c->opt.walk = value == 1 ? 1 : 0;
     else if (n == "l2_persist") {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
         if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");

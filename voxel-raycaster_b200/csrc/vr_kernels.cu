@@ -63,7 +63,7 @@ vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
 }
 
-template <bool AUX>
+template <bool AUX, int WALK>
 __global__ void __launch_bounds__(kThreads, VR_SVO_MIN_CTAS)
 vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
@@ -78,7 +78,7 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     SmemStack stk{stack + threadIdx.x};
     uint32_t rgba;
     vr_aux a;
-    const bool write = vr_trace_svo<AUX>(P, x, y, &rgba, &a, stk);
+    const bool write = vr_trace_svo<AUX, WALK>(P, x, y, &rgba, &a, stk);
     if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
@@ -137,7 +137,7 @@ vr_svo_persistent_kernel(const __grid_constant__ vr_frame_params P, unsigned int
             if (idle == 0xffffffffu && !more && !__any_sync(0xffffffffu, active)) break;
         }
         if (active) {
-            const int rc = vr_svo_cell<AUX>(P, q, &a);
+            const int rc = vr_svo_cell<AUX, 0>(P, q, &a);
             if (rc != VR_CELL_CONTINUE) {
                 if (rc != VR_CELL_NO_WRITE) reinterpret_cast<uint32_t *>(P.image)[local] = vr_svo_finish<AUX>(q, rc, &a);
                 if (AUX) {
@@ -169,9 +169,12 @@ cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_au
         if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
         if (with_aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
         else vr_svo_persistent_kernel<false><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
+    } else if (use_svo && opt && opt->walk == 1) {
+        if (with_aux) vr_svo_kernel<true, 1><<<grid, block, 0, stream>>>(P);
+        else vr_svo_kernel<false, 1><<<grid, block, 0, stream>>>(P);
     } else if (use_svo) {
-        if (with_aux) vr_svo_kernel<true><<<grid, block, 0, stream>>>(P);
-        else vr_svo_kernel<false><<<grid, block, 0, stream>>>(P);
+        if (with_aux) vr_svo_kernel<true, 0><<<grid, block, 0, stream>>>(P);
+        else vr_svo_kernel<false, 0><<<grid, block, 0, stream>>>(P);
     } else {
         if (with_aux) vr_dense_kernel<true><<<grid, block, 0, stream>>>(P);
         else vr_dense_kernel<false><<<grid, block, 0, stream>>>(P);

@@ -15,6 +15,8 @@ typedef struct vr_launch_options {
     int ctas_per_sm;
     int num_sms;
     unsigned int *counter;     /* device pixel counter */
+    int walk;                  /* 0 = merged in-cell walk (bit-identical to the reference on every pixel),
+                                  1 = per-axis walk (identical except distance_traveled on exact-tie rays) */
 } vr_launch_options;
 
 /* One frame (or one row-band slab of it).  use_svo selects the 64-tree traversal kernel, otherwise the

@@ -440,6 +440,57 @@ VR_HD bool vr_ray_finite(const RayState &r) {
     return s - s == 0.0f;             /* false for inf / NaN */
 }
 
+/* ---- per-axis walk (option "walk" = 1) ------------------------------------------------------------
+ * The three intersection_t sequences are independent: axis a's crossing times are t_a, t_a+d_a, (t_a+d_a)+d_a, ...
+ * whatever the other axes do (kernel:559 adds delta_t only on the axes that step).  So a cell can be walked
+ * one AXIS at a time instead of one STEP at a time:
+ *   1. predict the exit axis A from the closed forms t + (r-1)*d (a prediction only, never used as a value);
+ *   2. run A's r_A - 1 additions (a bare FADD chain): T = the exact time at which the ray leaves the cell;
+ *   3. for the other two axes count the crossings with time < T by repeated addition (FADD + compare);
+ *      a crossing exactly at T joins the exit step (multi-axis step, kernel:558 tie rule).
+ * ~1.5 issue slots per step on the exit axis and ~4 on the others instead of 16 for the merged walk.
+ * The float state and the crossing counts are EXACTLY those of the merged walk.  What is not observed is a
+ * tie between two crossings strictly inside the cell (the reference then moves diagonally and counts ONE
+ * step): distance_traveled is then one too large per such tie.  Those rays are "degenerate" in the sense of
+ * BASELINE.json (they pass exactly through a voxel edge); the oracle flags them (VRO_FL_TIE) and the tests
+ * compare them with the north_star tolerance instead of bit-exactly.  Returns false when the cell has to be
+ * walked by the merged walk instead (exit axis mispredicted, or max_distance ends inside the cell). */
+VR_HD bool vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, int &ay, int &az, int &n, bool &exit_tie) {
+    const float ex = VR_FMA_EXACT((float)(rx - 1), r.delta.x, r.t.x);     /* predictions; rounding is irrelevant */
+    const float ey = VR_FMA_EXACT((float)(ry - 1), r.delta.y, r.t.y);
+    const float ez = VR_FMA_EXACT((float)(rz - 1), r.delta.z, r.t.z);
+    const int sel = (ex <= ey && ex <= ez) ? 0 : (ey <= ez ? 1 : 2);
+    /* roles: A = predicted exit axis, B and C the next two in cyclic order */
+    float tA = sel == 0 ? r.t.x : (sel == 1 ? r.t.y : r.t.z), dA = sel == 0 ? r.delta.x : (sel == 1 ? r.delta.y : r.delta.z);
+    float tB = sel == 0 ? r.t.y : (sel == 1 ? r.t.z : r.t.x), dB = sel == 0 ? r.delta.y : (sel == 1 ? r.delta.z : r.delta.x);
+    float tC = sel == 0 ? r.t.z : (sel == 1 ? r.t.x : r.t.y), dC = sel == 0 ? r.delta.z : (sel == 1 ? r.delta.x : r.delta.y);
+    const int rA = sel == 0 ? rx : (sel == 1 ? ry : rz);
+    const int rB = sel == 0 ? ry : (sel == 1 ? rz : rx);
+    const int rC = sel == 0 ? rz : (sel == 1 ? rx : ry);
+    for (int i = rA - 1; i > 0; --i) tA = VR_ADD(tA, dA);
+    const float T = tA;                                                   /* time of the step that leaves the cell */
+    tA = VR_ADD(tA, dA);
+    int cB = 0, cC = 0, tieB = 0, tieC = 0;
+    while (tB < T) { tB = VR_ADD(tB, dB); cB++; }
+    if (tB == T && cB < rB) { tB = VR_ADD(tB, dB); cB++; tieB = 1; }
+    if (cB > rB || (cB == rB && !tieB)) return false;                     /* B left the cell before A: mispredicted */
+    while (tC < T) { tC = VR_ADD(tC, dC); cC++; }
+    if (tC == T && cC < rC) { tC = VR_ADD(tC, dC); cC++; tieC = 1; }
+    if (cC > rC || (cC == rC && !tieC)) return false;
+    n = rA + cB + cC - tieB - tieC;
+    if (n > nmax) return false;                                           /* max_distance ends inside this cell */
+    r.t.x = sel == 0 ? tA : (sel == 1 ? tC : tB);
+    r.t.y = sel == 0 ? tB : (sel == 1 ? tA : tC);
+    r.t.z = sel == 0 ? tC : (sel == 1 ? tB : tA);
+    ax = sel == 0 ? rA : (sel == 1 ? cC : cB);
+    ay = sel == 0 ? cB : (sel == 1 ? rA : cC);
+    az = sel == 0 ? cC : (sel == 1 ? cB : rA);
+    const int bA = 1 << sel, bB = sel == 2 ? 1 : (bA << 1), bC = sel == 0 ? 4 : (sel == 1 ? 1 : 2);
+    r.fm = bA | (tieB ? bB : 0) | (tieC ? bC : 0);
+    exit_tie = (tieB | tieC) != 0;
+    return true;
+}
+
 /* Per-ray traversal state of the SVO variant: everything that lives across cells. */
 template <class Stack>
 struct vr_svo_ray {
@@ -483,7 +534,7 @@ VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack
 /* One iteration of the cell loop: walk the cached cell, then look the new voxel up.
  * Returns VR_CELL_CONTINUE, VR_CELL_NO_WRITE (pixel skipped after a redirect, kernel:671/694) or the
  * terminal status. */
-template <bool AUX, class Stack>
+template <bool AUX, int WALK, class Stack>
 VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
     RayState &r = q.r;
     if (!(r.dist < r.max_distance && r.bounce < 2)) return r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST;
@@ -498,22 +549,32 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
         const int ry = vr_exit_count(r.step.y, r.voxel.y, q.co.y, S);
         const int rz = vr_exit_count(r.step.z, r.voxel.z, q.co.z, S);
         const int nmax = r.max_distance - r.dist;
-        vr_walk_state w = {r.t.x, r.t.y, r.t.z, (float)rx, (float)ry, (float)rz, (float)nmax};
-        while (vr_walk_step(w, r.delta) != 0.0f) {}
-        r.t = {w.tx, w.ty, w.tz};
-        const float kx = w.kx, ky = w.ky, kz = w.kz;
-        ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;         /* crossings done per axis */
-        n = nmax - (int)w.rem;                                           /* steps done */
-        r.voxel.x += r.step.x * ax;
-        r.voxel.y += r.step.y * ay;
-        r.voxel.z += r.step.z * az;
-        /* without ties exactly one axis moved per step, and the axis whose k hit 0 is the face crossed by the
-         * last step; with a tie somewhere in the cell the mask is recovered by a replay if it is needed */
-        tie_cell = (ax + ay + az) != n;
-        r.fm = (kx == 0.0f ? 1 : 0) | (ky == 0.0f ? 2 : 0) | (kz == 0.0f ? 4 : 0);
-        if (AUX && tie_cell) a->flags |= VR_FL_TIE;
-        if (r.fm == 0) { r.dist += n; return VR_ST_MAXDIST; }            /* max_distance reached inside the cell */
-        r.dist += n - 1;
+        bool exit_tie = false;
+        if (WALK == 1 && vr_walk_axes(r, rx, ry, rz, nmax, ax, ay, az, n, exit_tie)) {
+            /* per-axis walk: float state, crossing counts and face mask are exact; see vr_walk_axes */
+            r.voxel.x += r.step.x * ax;
+            r.voxel.y += r.step.y * ay;
+            r.voxel.z += r.step.z * az;
+            if (AUX && exit_tie) a->flags |= VR_FL_TIE;
+            r.dist += n - 1;
+        } else {
+            vr_walk_state w = {r.t.x, r.t.y, r.t.z, (float)rx, (float)ry, (float)rz, (float)nmax};
+            while (vr_walk_step(w, r.delta) != 0.0f) {}
+            r.t = {w.tx, w.ty, w.tz};
+            const float kx = w.kx, ky = w.ky, kz = w.kz;
+            ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;     /* crossings done per axis */
+            n = nmax - (int)w.rem;                                       /* steps done */
+            r.voxel.x += r.step.x * ax;
+            r.voxel.y += r.step.y * ay;
+            r.voxel.z += r.step.z * az;
+            /* without ties exactly one axis moved per step, and the axis whose k hit 0 is the face crossed by the
+             * last step; with a tie somewhere in the cell the mask is recovered by a replay if it is needed */
+            tie_cell = (ax + ay + az) != n;
+            r.fm = (kx == 0.0f ? 1 : 0) | (ky == 0.0f ? 2 : 0) | (kz == 0.0f ? 4 : 0);
+            if (AUX && tie_cell) a->flags |= VR_FL_TIE;
+            if (r.fm == 0) { r.dist += n; return VR_ST_MAXDIST; }        /* max_distance reached inside the cell */
+            r.dist += n - 1;
+        }
     } else if (!vr_walk_literal<AUX>(r, q.cs, q.co, a)) {
         return VR_ST_MAXDIST;
     }
@@ -583,13 +644,13 @@ VR_HD uint32_t vr_svo_finish(vr_svo_ray<Stack> &q, int status, vr_aux *a) {
 }
 
 /* whole pixel, static pixel->thread mapping */
-template <bool AUX, class Stack>
+template <bool AUX, int WALK, class Stack>
 VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
     vr_svo_ray<Stack> q;
     q.stk = stk;
     if (!vr_svo_begin<AUX>(P, x, y, q, a)) return false;
     int rc;
-    while ((rc = vr_svo_cell<AUX>(P, q, a)) == VR_CELL_CONTINUE) {}
+    while ((rc = vr_svo_cell<AUX, WALK>(P, q, a)) == VR_CELL_CONTINUE) {}
     if (rc == VR_CELL_NO_WRITE) return false;
     *rgba_out = vr_svo_finish<AUX>(q, rc, a);
     return true;
