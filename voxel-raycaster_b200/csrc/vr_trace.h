@@ -445,17 +445,37 @@ VR_HD bool vr_ray_finite(const RayState &r) {
  * whatever the other axes do (kernel:559 adds delta_t only on the axes that step).  So a cell can be walked
  * one AXIS at a time instead of one STEP at a time:
  *   1. predict the exit axis A from the closed forms t + (r-1)*d (a prediction only, never used as a value);
- *   2. run A's r_A - 1 additions (a bare FADD chain): T = the exact time at which the ray leaves the cell;
- *   3. for the other two axes count the crossings with time < T by repeated addition (FADD + compare);
+ *   2. run A's r_A - 1 additions as a bare, unrolled FADD chain: T = the exact time of the step that leaves
+ *      the cell;
+ *   3. for each of the other two axes estimate the number of crossings before T by a division, run that many
+ *      additions minus a safety margin as a bare chain, and finish with a compare-per-step loop (2-3 rounds);
  *      a crossing exactly at T joins the exit step (multi-axis step, kernel:558 tie rule).
- * ~1.5 issue slots per step on the exit axis and ~4 on the others instead of 16 for the merged walk.
- * The float state and the crossing counts are EXACTLY those of the merged walk.  What is not observed is a
- * tie between two crossings strictly inside the cell (the reference then moves diagonally and counts ONE
- * step): distance_traveled is then one too large per such tie.  Those rays are "degenerate" in the sense of
- * BASELINE.json (they pass exactly through a voxel edge); the oracle flags them (VRO_FL_TIE) and the tests
- * compare them with the north_star tolerance instead of bit-exactly.  Returns false when the cell has to be
- * walked by the merged walk instead (exit axis mispredicted, or max_distance ends inside the cell). */
-VR_HD bool vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, int &ay, int &az, int &n, bool &exit_tie) {
+ * About 1.3 issue slots per step instead of 16 for the merged walk, and the float state / crossing counts are
+ * EXACTLY those of the merged walk (same additions, same order per axis).  What is not observed is a tie
+ * between two crossings strictly inside the cell (the reference then moves diagonally and counts ONE step):
+ * distance_traveled is then one too large per such tie.  Those rays are "degenerate" in BASELINE.json's sense
+ * (they pass exactly through a voxel edge); the oracle flags them (VRO_FL_TIE) and the tests compare them with
+ * the north_star tolerance instead of bit-exactly.
+ * Returns VR_AXES_DONE, VR_AXES_FALLBACK (exit axis mispredicted: use the merged walk) or VR_AXES_MAXDIST
+ * (max_distance is reached inside the cell: the ray ends here and nothing of its state is needed any more). */
+enum { VR_AXES_FALLBACK = 0, VR_AXES_DONE = 1, VR_AXES_MAXDIST = 2 };
+
+VR_HD float vr_add_chain(float t, float d, int n) {
+    for (; n >= 4; n -= 4) t = VR_ADD(VR_ADD(VR_ADD(VR_ADD(t, d), d), d), d);
+    for (; n > 0; --n) t = VR_ADD(t, d);
+    return t;
+}
+
+/* crossings of one non-exit axis strictly before T; t ends at the first crossing time >= T */
+VR_HD int vr_count_before(float &t, float d, float inv_d, float T) {
+    int c = (int)(VR_MUL(VR_SUB(T, t), inv_d)) - 2;       /* estimate minus margin: never overshoots */
+    c = c < 0 ? 0 : c;
+    t = vr_add_chain(t, d, c);
+    while (t < T) { t = VR_ADD(t, d); c++; }
+    return c;
+}
+
+VR_HD int vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, int &ay, int &az, int &n, bool &exit_tie) {
     const float ex = VR_FMA_EXACT((float)(rx - 1), r.delta.x, r.t.x);     /* predictions; rounding is irrelevant */
     const float ey = VR_FMA_EXACT((float)(ry - 1), r.delta.y, r.t.y);
     const float ez = VR_FMA_EXACT((float)(rz - 1), r.delta.z, r.t.z);
@@ -464,21 +484,23 @@ VR_HD bool vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, 
     float tA = sel == 0 ? r.t.x : (sel == 1 ? r.t.y : r.t.z), dA = sel == 0 ? r.delta.x : (sel == 1 ? r.delta.y : r.delta.z);
     float tB = sel == 0 ? r.t.y : (sel == 1 ? r.t.z : r.t.x), dB = sel == 0 ? r.delta.y : (sel == 1 ? r.delta.z : r.delta.x);
     float tC = sel == 0 ? r.t.z : (sel == 1 ? r.t.x : r.t.y), dC = sel == 0 ? r.delta.z : (sel == 1 ? r.delta.x : r.delta.y);
+    const float iB = fabsf(sel == 0 ? r.ray_dir.y : (sel == 1 ? r.ray_dir.z : r.ray_dir.x));   /* ~ 1 / dB */
+    const float iC = fabsf(sel == 0 ? r.ray_dir.z : (sel == 1 ? r.ray_dir.x : r.ray_dir.y));
     const int rA = sel == 0 ? rx : (sel == 1 ? ry : rz);
     const int rB = sel == 0 ? ry : (sel == 1 ? rz : rx);
     const int rC = sel == 0 ? rz : (sel == 1 ? rx : ry);
-    for (int i = rA - 1; i > 0; --i) tA = VR_ADD(tA, dA);
+    tA = vr_add_chain(tA, dA, rA - 1);
     const float T = tA;                                                   /* time of the step that leaves the cell */
     tA = VR_ADD(tA, dA);
-    int cB = 0, cC = 0, tieB = 0, tieC = 0;
-    while (tB < T) { tB = VR_ADD(tB, dB); cB++; }
+    int tieB = 0, tieC = 0;
+    int cB = vr_count_before(tB, dB, iB, T);
     if (tB == T && cB < rB) { tB = VR_ADD(tB, dB); cB++; tieB = 1; }
-    if (cB > rB || (cB == rB && !tieB)) return false;                     /* B left the cell before A: mispredicted */
-    while (tC < T) { tC = VR_ADD(tC, dC); cC++; }
+    if (cB > rB || (cB == rB && !tieB)) return VR_AXES_FALLBACK;          /* B left the cell before A: mispredicted */
+    int cC = vr_count_before(tC, dC, iC, T);
     if (tC == T && cC < rC) { tC = VR_ADD(tC, dC); cC++; tieC = 1; }
-    if (cC > rC || (cC == rC && !tieC)) return false;
+    if (cC > rC || (cC == rC && !tieC)) return VR_AXES_FALLBACK;
     n = rA + cB + cC - tieB - tieC;
-    if (n > nmax) return false;                                           /* max_distance ends inside this cell */
+    if (n > nmax) return VR_AXES_MAXDIST;
     r.t.x = sel == 0 ? tA : (sel == 1 ? tC : tB);
     r.t.y = sel == 0 ? tB : (sel == 1 ? tA : tC);
     r.t.z = sel == 0 ? tC : (sel == 1 ? tB : tA);
@@ -488,7 +510,7 @@ VR_HD bool vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, 
     const int bA = 1 << sel, bB = sel == 2 ? 1 : (bA << 1), bC = sel == 0 ? 4 : (sel == 1 ? 1 : 2);
     r.fm = bA | (tieB ? bB : 0) | (tieC ? bC : 0);
     exit_tie = (tieB | tieC) != 0;
-    return true;
+    return VR_AXES_DONE;
 }
 
 /* Per-ray traversal state of the SVO variant: everything that lives across cells. */
@@ -550,7 +572,12 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
         const int rz = vr_exit_count(r.step.z, r.voxel.z, q.co.z, S);
         const int nmax = r.max_distance - r.dist;
         bool exit_tie = false;
-        if (WALK == 1 && vr_walk_axes(r, rx, ry, rz, nmax, ax, ay, az, n, exit_tie)) {
+        const int axes = WALK == 1 ? vr_walk_axes(r, rx, ry, rz, nmax, ax, ay, az, n, exit_tie) : VR_AXES_FALLBACK;
+        if (axes == VR_AXES_MAXDIST) {
+            r.dist = r.max_distance;                                     /* kernel:357 ends the loop; t / voxel are dead */
+            return VR_ST_MAXDIST;
+        }
+        if (axes == VR_AXES_DONE) {
             /* per-axis walk: float state, crossing counts and face mask are exact; see vr_walk_axes */
             r.voxel.x += r.step.x * ax;
             r.voxel.y += r.step.y * ay;
