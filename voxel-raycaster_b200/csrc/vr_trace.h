@@ -459,6 +459,9 @@ VR_HD bool vr_ray_finite(const RayState &r) {
  * Returns VR_AXES_DONE, VR_AXES_FALLBACK (exit axis mispredicted: use the merged walk) or VR_AXES_MAXDIST
  * (max_distance is reached inside the cell: the ray ends here and nothing of its state is needed any more). */
 enum { VR_AXES_FALLBACK = 0, VR_AXES_DONE = 1, VR_AXES_MAXDIST = 2 };
+#ifndef VR_AXES_MIN_COUNT
+#define VR_AXES_MIN_COUNT 12     /* rx+ry+rz above which a cell is walked per axis (measured) */
+#endif
 
 VR_HD float vr_add_chain(float t, float d, int n) {
     for (; n >= 4; n -= 4) t = VR_ADD(VR_ADD(VR_ADD(VR_ADD(t, d), d), d), d);
@@ -572,7 +575,10 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
         const int rz = vr_exit_count(r.step.z, r.voxel.z, q.co.z, S);
         const int nmax = r.max_distance - r.dist;
         bool exit_tie = false;
-        const int axes = WALK == 1 ? vr_walk_axes(r, rx, ry, rz, nmax, ax, ay, az, n, exit_tie) : VR_AXES_FALLBACK;
+        /* short walks (cells of a few voxels next to surfaces) are cheaper step by step: 16 slots per step against
+         * ~200 of fixed cost for the per-axis machinery */
+        const int axes = (WALK == 1 && rx + ry + rz > VR_AXES_MIN_COUNT)
+                             ? vr_walk_axes(r, rx, ry, rz, nmax, ax, ay, az, n, exit_tie) : VR_AXES_FALLBACK;
         if (axes == VR_AXES_MAXDIST) {
             r.dist = r.max_distance;                                     /* kernel:357 ends the loop; t / voxel are dead */
             return VR_ST_MAXDIST;
@@ -624,8 +630,11 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
         const int s = q.s;
         const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
         if (!((q.node.mask >> ci) & 1ull)) {                             /* empty slot: cache the cell */
-            q.cs = s;
-            q.co = {(r.voxel.x >> s) << s, (r.voxel.y >> s) << s, (r.voxel.z >> s) << s};
+            /* if the whole 2x2x2 octant of slots around it is empty the cell is twice as wide -- the odd levels of
+             * the reference's 2^3 octree, recovered from the 4^3 mask (slots ci&0x2A + {0,1,4,5,16,17,20,21}) */
+            const int cs = s + ((((q.node.mask >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
+            q.cs = cs;
+            q.co = {(r.voxel.x >> cs) << cs, (r.voxel.y >> cs) << cs, (r.voxel.z >> cs) << cs};
             break;
         }
         const uint32_t rank = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
