@@ -265,7 +265,7 @@ def main() -> None:
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
     ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
-    ap.add_argument("--walk", type=int, default=0, help="0 = merged in-cell walk (bit-identical on every pixel), 1 = per-axis walk")
+    ap.add_argument("--walk", type=int, default=1, help="in-cell walk of the octree kernel: 1 = per-axis (default here; exact except the step count of exact-tie rays), 0 = merged (bit-identical on every pixel; the library default)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
@@ -417,6 +417,20 @@ def main() -> None:
     ms_per_step = total_ms / args.steps
     value = rays / (ms_per_step / 1e3) / 1e6
 
+    # the other in-cell walk, for the record (a few untimed-region frames, kernel only)
+    other_walk_ms = None
+    if use_svo and world == 1:
+        must(c.set_option("walk", 1 - args.walk), "walk")
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3 + 10):
+            if i == 3:
+                o0.record(stream)
+            must(c.compute_into(slab.data_ptr()), "compute_into")
+        o1.record(stream)
+        torch.cuda.synchronize()
+        other_walk_ms = o0.elapsed_time(o1) / 10
+        must(c.set_option("walk", args.walk), "walk")
+
     # ---- end to end through the public API with HOST buffers: camera/lights are read from host memory at every
     # call, the frame is copied back to pinned host memory inside the timed region (double buffered at N = 1)
     barrier()
@@ -472,7 +486,10 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
-                       "mode": args.mode, "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
+                       "mode": args.mode,
+                       "walk": ("per-axis in-cell walk: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)" if args.walk == 1 else "merged in-cell walk: bit-identical to the reference restatement on every pixel") if use_svo else "dense DDA",
+                       "other_walk_ms_per_frame": other_walk_ms,
+                       "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
