@@ -516,6 +516,52 @@ VR_HD int vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, i
     return VR_AXES_DONE;
 }
 
+/* ---- leaf-brick walk --------------------------------------------------------------------------------
+ * Inside a leaf node (a brick of 4^3 voxels whose occupancy is the node's 64-bit mask, held in registers) the
+ * merged step is followed by a bit test of the voxel just entered, so that the empty voxels of the brick cost no
+ * lookup at all: rays that skim a surface visit one brick after the other instead of one 1^3 / 2^3 cell after the
+ * other.  Stops when a step leaves the brick (VR_BRICK_EXIT) or lands on a solid voxel (VR_BRICK_HIT, `bit` = its
+ * slot).  The caller guarantees that max_distance cannot be reached inside the brick (a brick holds at most 10
+ * steps).  All masks of the last step are known here, so the face mask is exact even with ties. */
+enum { VR_BRICK_EXIT = 0, VR_BRICK_HIT = 1 };
+
+VR_HD int vr_walk_brick(RayState &r, unsigned long long mask, vi3 co, int &n, int &bit, bool &tie) {
+    const int lx = r.voxel.x - co.x, ly = r.voxel.y - co.y, lz = r.voxel.z - co.z;
+    const int rx = r.step.x > 0 ? 4 - lx : lx + 1, ry = r.step.y > 0 ? 4 - ly : ly + 1, rz = r.step.z > 0 ? 4 - lz : lz + 1;
+    float tx = r.t.x, ty = r.t.y, tz = r.t.z;
+    float kx = (float)rx, ky = (float)ry, kz = (float)rz, steps = 0.0f;
+    float bitf = (float)(lx | (ly << 2) | (lz << 4));
+    const float sx = (float)r.step.x, sy = (float)(4 * r.step.y), sz = (float)(16 * r.step.z);
+    float mx, my, mz;
+    int res;
+    for (;;) {
+        const float m = vr_min3(tx, ty, tz);
+        mx = (tx == m) ? 1.0f : 0.0f;
+        my = (ty == m) ? 1.0f : 0.0f;
+        mz = (tz == m) ? 1.0f : 0.0f;
+        tx = VR_FMA_EXACT(r.delta.x, mx, tx);
+        ty = VR_FMA_EXACT(r.delta.y, my, ty);
+        tz = VR_FMA_EXACT(r.delta.z, mz, tz);
+        kx = VR_SUB(kx, mx);
+        ky = VR_SUB(ky, my);
+        kz = VR_SUB(kz, mz);
+        bitf = VR_FMA_EXACT(mx, sx, VR_FMA_EXACT(my, sy, VR_FMA_EXACT(mz, sz, bitf)));   /* small integers: exact */
+        steps = VR_ADD(steps, 1.0f);
+        if (VR_MUL(VR_MUL(kx, ky), kz) == 0.0f) { res = VR_BRICK_EXIT; break; }
+        if ((mask >> (int)bitf) & 1ull) { res = VR_BRICK_HIT; break; }
+    }
+    const int ax = rx - (int)kx, ay = ry - (int)ky, az = rz - (int)kz;
+    r.t = {tx, ty, tz};
+    r.voxel.x += r.step.x * ax;
+    r.voxel.y += r.step.y * ay;
+    r.voxel.z += r.step.z * az;
+    r.fm = (mx != 0.0f ? 1 : 0) | (my != 0.0f ? 2 : 0) | (mz != 0.0f ? 4 : 0);
+    n = (int)steps;
+    bit = (int)bitf;
+    tie = (ax + ay + az) != n;
+    return res;
+}
+
 /* Per-ray traversal state of the SVO variant: everything that lives across cells. */
 template <class Stack>
 struct vr_svo_ray {
@@ -526,6 +572,7 @@ struct vr_svo_ray {
     vi3 nv;                   /* a voxel inside the current node */
     int cs;                   /* cached empty cell: edge 1 << cs at origin co */
     vi3 co;
+    bool brick;               /* the cached cell is the leaf brick of `node` (4^3 voxels, occupancy = node.mask) */
     bool finite;
     bool first_hit_done;
     Stack stk;
@@ -551,6 +598,7 @@ VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack
      * so that voxel is never tested */
     q.cs = 0;
     q.co = q.r.voxel;
+    q.brick = false;
     q.finite = vr_ray_finite(q.r);
     q.first_hit_done = false;
     return true;
@@ -568,12 +616,28 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
     bool tie_cell = false;
     const vf3 t0 = r.t;                                                  /* state at cell entry, for a replay */
     int n = 0, ax = 0, ay = 0, az = 0;
-    if (q.finite) {
-        const int S = 1 << q.cs;
-        const int rx = vr_exit_count(r.step.x, r.voxel.x, q.co.x, S);
-        const int ry = vr_exit_count(r.step.y, r.voxel.y, q.co.y, S);
-        const int rz = vr_exit_count(r.step.z, r.voxel.z, q.co.z, S);
-        const int nmax = r.max_distance - r.dist;
+    int voxel_data = 0;
+    bool known = false;                      /* the brick walk already knows what the voxel just entered holds */
+    const int nmax = r.max_distance - r.dist;
+    /* a brick is walked as such unless the ray is about to end (then voxel by voxel, like any 1^3 cell) */
+    const bool as_brick = q.brick && q.finite && nmax > 12;
+    const int wcs = q.brick && !as_brick ? 0 : q.cs;
+    const vi3 wco = q.brick && !as_brick ? r.voxel : q.co;
+    if (as_brick) {
+        int bit;
+        bool tie;
+        const int res = vr_walk_brick(r, q.node.mask, q.co, n, bit, tie);
+        if (AUX && tie) a->flags |= VR_FL_TIE;
+        r.dist += n - 1;
+        if (res == VR_BRICK_HIT) {
+            voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
+            known = true;
+        }
+    } else if (q.finite) {
+        const int S = 1 << wcs;
+        const int rx = vr_exit_count(r.step.x, r.voxel.x, wco.x, S);
+        const int ry = vr_exit_count(r.step.y, r.voxel.y, wco.y, S);
+        const int rz = vr_exit_count(r.step.z, r.voxel.z, wco.z, S);
         bool exit_tie = false;
         /* short walks (cells of a few voxels next to surfaces) are cheaper step by step: 16 slots per step against
          * ~200 of fixed cost for the per-axis machinery */
@@ -608,46 +672,55 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             if (r.fm == 0) { r.dist += n; return VR_ST_MAXDIST; }        /* max_distance reached inside the cell */
             r.dist += n - 1;
         }
-    } else if (!vr_walk_literal<AUX>(r, q.cs, q.co, a)) {
+    } else if (!vr_walk_literal<AUX>(r, wcs, wco, a)) {
         return VR_ST_MAXDIST;
     }
     /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
-    if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
-        vr_out_of_bounds(r);
-        return VR_ST_OOB;
-    }
-    if (AUX) a->lookups++;
-    /* pop to the lowest ancestor containing the voxel */
-    const int nx = (r.voxel.x ^ q.nv.x) | (r.voxel.y ^ q.nv.y) | (r.voxel.z ^ q.nv.z);
-    if ((nx >> (q.s + 2)) != 0) {
-        do { q.s += 2; q.level--; } while ((nx >> (q.s + 2)) != 0);
-        q.node = vr_load_node(P, q.stk.get(q.level));
-        if (AUX) a->node_fetches++;
-    }
-    q.nv = r.voxel;
-    int voxel_data = 0;
-    for (;;) {
-        const int s = q.s;
-        const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
-        if (!((q.node.mask >> ci) & 1ull)) {                             /* empty slot: cache the cell */
-            /* if the whole 2x2x2 octant of slots around it is empty the cell is twice as wide -- the odd levels of
-             * the reference's 2^3 octree, recovered from the 4^3 mask (slots ci&0x2A + {0,1,4,5,16,17,20,21}) */
-            const int cs = s + ((((q.node.mask >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
-            q.cs = cs;
-            q.co = {(r.voxel.x >> cs) << cs, (r.voxel.y >> cs) << cs, (r.voxel.z >> cs) << cs};
-            break;
+    if (!known) {
+        if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
+            vr_out_of_bounds(r);
+            return VR_ST_OOB;
         }
-        const uint32_t rank = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
-        if (s == 0) {                                                    /* a set voxel bit */
-            voxel_data = (int)(int8_t)P.leaf_types[q.node.base + rank];
-            break;
+        if (AUX) a->lookups++;
+        /* pop to the lowest ancestor containing the voxel */
+        const int nx = (r.voxel.x ^ q.nv.x) | (r.voxel.y ^ q.nv.y) | (r.voxel.z ^ q.nv.z);
+        if ((nx >> (q.s + 2)) != 0) {
+            do { q.s += 2; q.level--; } while ((nx >> (q.s + 2)) != 0);
+            q.node = vr_load_node(P, q.stk.get(q.level));
+            if (AUX) a->node_fetches++;
         }
-        const uint32_t child = q.node.base + rank;
-        q.level++;
-        q.s -= 2;
-        q.stk.set(q.level, child);
-        q.node = vr_load_node(P, child);
-        if (AUX) a->node_fetches++;
+        q.nv = r.voxel;
+        for (;;) {
+            const int s = q.s;
+            const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
+            if (!((q.node.mask >> ci) & 1ull)) {                         /* empty slot: cache the cell */
+                if (s == 0) {
+                    /* an empty voxel of a leaf brick: the whole brick becomes the cell, walked with bit tests */
+                    q.brick = true;
+                    q.cs = 2;
+                    q.co = {r.voxel.x & ~3, r.voxel.y & ~3, r.voxel.z & ~3};
+                    break;
+                }
+                /* if the whole 2x2x2 octant of slots around it is empty the cell is twice as wide -- the odd levels
+                 * of the reference's 2^3 octree, recovered from the 4^3 mask (slots ci&0x2A + {0,1,4,5,16,17,20,21}) */
+                const int cs = s + ((((q.node.mask >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
+                q.brick = false;
+                q.cs = cs;
+                q.co = {(r.voxel.x >> cs) << cs, (r.voxel.y >> cs) << cs, (r.voxel.z >> cs) << cs};
+                break;
+            }
+            const uint32_t rank = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
+            if (s == 0) {                                                /* a set voxel bit */
+                voxel_data = (int)(int8_t)P.leaf_types[q.node.base + rank];
+                break;
+            }
+            const uint32_t child = q.node.base + rank;
+            q.level++;
+            q.s -= 2;
+            q.stk.set(q.level, child);
+            q.node = vr_load_node(P, child);
+            if (AUX) a->node_fetches++;
+        }
     }
     if (voxel_data == 5 || voxel_data == 6) {
         if (tie_cell) {
@@ -658,7 +731,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             r.voxel.z -= r.step.z * az;
             r.dist -= n - 1;
             r.t = t0;
-            vr_walk_literal<false>(r, q.cs, q.co, a);
+            vr_walk_literal<false>(r, wcs, wco, a);
         }
         const int st = vr_hit_block<AUX>(P, r, voxel_data, a, q.first_hit_done);
         if (st == VR_ST_SKIP_REDIRECT) {
@@ -666,7 +739,12 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             return VR_CELL_NO_WRITE;
         }
         if (st >= 0) return st;
-        q.finite = vr_ray_finite(r);                                     /* the ray was redirected */
+        /* the ray was redirected and restarts from the voxel it came from, which is known to be empty: that voxel
+         * is the cell (the previous cell may have been a brick whose node is no longer the current one) */
+        q.finite = vr_ray_finite(r);
+        q.brick = false;
+        q.cs = 0;
+        q.co = r.voxel;
     }
     r.dist++;
     return VR_CELL_CONTINUE;
