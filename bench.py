@@ -69,7 +69,33 @@ class ClockSampler:
     def __init__(self, index: int) -> None:
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
+    def _run_nvml(self) -> bool:
+        """fast path: NVML in-process (sub-millisecond per sample), same counters as the nvidia-smi recipe"""
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = N.nvmlDeviceGetHandleByIndex(phys)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            while not self._stop.is_set():
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    reasons = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if reasons & bits[k] else "Not Active" for k in order])
+                self._stop.wait(0.005)
+            return True
+        except Exception:
+            return False
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
