@@ -515,7 +515,7 @@ def main() -> None:
                        "mode": args.mode,
                        "walk": ("per-axis in-cell walk: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)" if args.walk == 1 else "merged in-cell walk: bit-identical to the reference restatement on every pixel") if use_svo else "dense DDA",
                        "other_walk_ms_per_frame": other_walk_ms,
-                       "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x8 tiles"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
+                       "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),

@@ -67,3 +67,11 @@ def tree_from_columns(lo: np.ndarray, hi: np.ndarray, voxel_type: int = 5):
     lo = np.ascontiguousarray(lo, dtype=np.int32)
     hi = np.ascontiguousarray(hi, dtype=np.int32)
     return _tree(lib().emu_tree_from_columns, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), C.c_int(lo.shape[0]), C.c_int(voxel_type))
+
+
+def add_chain(t: np.ndarray, d: np.ndarray, n: np.ndarray):
+    t = np.ascontiguousarray(t, np.float32); d = np.ascontiguousarray(d, np.float32); n = np.ascontiguousarray(n, np.int32)
+    a = np.empty_like(t); b = np.empty_like(t)
+    fp = C.POINTER(C.c_float)
+    lib().emu_add_chain(t.ctypes.data_as(fp), d.ctypes.data_as(fp), n.ctypes.data_as(C.c_void_p), C.c_int(t.size), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
+    return a, b

@@ -78,3 +78,13 @@ extern "C" long emu_tree_from_columns(const int32_t *lo, const int32_t *hi, int 
     if (!vr_native_from_columns(lo, hi, n, (uint8_t)type, t)) return -1;
     return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
 }
+
+/* vr_add_chain (binade jumps) against the literal chain of additions it stands for */
+extern "C" void emu_add_chain(const float *t, const float *d, const int32_t *n, int count, float *jumped, float *literal) {
+    for (int i = 0; i < count; i++) {
+        jumped[i] = vr_add_chain(t[i], d[i], n[i]);
+        volatile float v = t[i];
+        for (int k = 0; k < n[i]; k++) v = v + d[i];
+        literal[i] = v;
+    }
+}

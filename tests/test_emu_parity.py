@@ -101,3 +101,46 @@ def test_axis_walk_device_core(pkg, oracle, name):
         assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
     diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
     assert not (diff[~tie] > 0).any() and (diff <= 1).all()
+
+
+def test_add_chain_binade_jumps():
+    """vr_add_chain evaluates n literal float additions (kernel:559) in closed form per binade: bit-identical
+    to the literal chain for random states, for d exactly half way between two grid points of t (ties-to-even
+    alternation), for d below half an ulp of t (t stops moving) and from t = 0."""
+    rng = np.random.default_rng(1)
+    n_s = 200000
+    t = (rng.random(n_s) * np.exp2(rng.integers(-30, 13, n_s))).astype(np.float32)
+    d = (1.0 / np.maximum(rng.random(n_s), 1e-6)).astype(np.float32)
+    n = rng.integers(0, 3000, n_s).astype(np.int32)
+    q = n_s // 4
+    d[:q] = (np.round(d[:q] * 8) / 8 + np.exp2(-rng.integers(8, 20, q).astype(np.float32))).astype(np.float32)
+    d[q:2 * q] = np.exp2(-rng.integers(0, 30, q).astype(np.float32))
+    t[:1000] = 0
+    a, b = emu_lib.add_chain(t, d, n)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    m = 20000
+    e = rng.integers(1, 12, m)
+    t2 = (np.exp2(e) * (1 + rng.random(m))).astype(np.float32)
+    u = np.exp2(e - 23.0)
+    d2 = (np.floor((1 + rng.random(m) * 3) / u) * u + u / 2).astype(np.float32)
+    a, b = emu_lib.add_chain(t2, d2, rng.integers(8, 2000, m).astype(np.int32))
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+
+
+def test_axis_walk_terrain_256(pkg, oracle):
+    """Per-axis walk with long chains (cells of up to 64^3 voxels, hundreds of crossings per cell) vs the oracle."""
+    S = pkg.scene
+    n = 256
+    vol = S.terrain_map(n, "shell")
+    for cam in (3, 7, 10):
+        pos, direction = S.make_camera(n, S.heightfield(n), cam)
+        scene = S.Scene(n, vol, 480, 270, pos, direction, S.make_lights(n), max_distance=3 * n)
+        table = oracle.make_ray_table(scene.width, scene.height)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, table)
+        rgba, aux = emu_lib.raycast(scene, table, use_svo=2)
+        tie = (ref_aux["flags"] & 4) != 0
+        for f in ("hit", "face", "status", "hit_type", "steps_first", "steps_total"):
+            assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
+        diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
+        assert not (diff[~tie] > 0).any() and (diff <= 1).all()
+        assert ref_aux["steps_total"].max() > 300

@@ -15,7 +15,8 @@ from pathlib import Path
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "libvrcaster.so"
+# VR_CASTER_LIB: another build of the same library (kernel A/B runs on the GPU box); default = the in-tree build
+_LIB_PATH = Path(os.environ.get("VR_CASTER_LIB") or Path(__file__).resolve().parent / "libvrcaster.so")
 _lib = None
 
 # every symbol include/vr_caster.h declares: name -> (restype, argtypes)

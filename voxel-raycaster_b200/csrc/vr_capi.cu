@@ -908,9 +908,11 @@ int vr_octree_load(vr_ctx *c, const char *path) {
     fclose(f);
     if (!ok) return fail(c, "octree_load: %s is not a valid octree file", path);
     /* every child pointer must stay inside the arrays */
-    for (const vr_node &n : t.nodes) {
-        const uint64_t pc = (uint64_t)__builtin_popcountll((uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32));
+    for (vr_node &n : t.nodes) {
+        const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
+        const uint64_t pc = (uint64_t)__builtin_popcountll(m);
         if ((uint64_t)n.child_base + pc > (nn > nt ? nn : nt)) return fail(c, "octree_load: corrupt child pointer in %s", path);
+        n.aux = vr_node_planes(m);           /* derived from the mask: never trusted from the file */
     }
     t.levels = levels;
     t.dim = dim;

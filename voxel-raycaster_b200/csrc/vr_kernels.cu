@@ -5,7 +5,7 @@
  * (reference src/CLCaster.cpp:946-987) and the OpenCL kernel it runs
  * (kernels/ray_caster_kernel.cl:256).  The per-pixel logic lives in vr_trace.h.
  *
- * Pixel -> thread mapping: a CTA of 256 threads covers a 32x8 pixel tile, each warp an 8x4 block
+ * Pixel -> thread mapping: a CTA of 128 threads covers a 32x4 pixel tile, each warp an 8x4 block
  * of it, so that the 32 rays of a warp form a compact bundle (coherent DDA trip counts and octree
  * paths) while ray-table loads (16 B/pixel) and RGBA8 stores (4 B/pixel) still fill whole
  * 128-byte / 32-byte sectors.
@@ -19,10 +19,14 @@
 namespace {
 
 constexpr int kTileW = 32;
-constexpr int kTileH = 8;
+#ifndef VR_TILE_H
+#define VR_TILE_H 4         /* rows of a CTA tile: CTA = 32 x VR_TILE_H pixels, one warp per 8x4 block (4 warps) */
+#endif
+constexpr int kTileH = VR_TILE_H;
 constexpr int kThreads = kTileW * kTileH;
 #ifndef VR_SVO_MIN_CTAS
-#define VR_SVO_MIN_CTAS 3      /* CTAs per SM the register allocation of vr_svo_kernel targets (measured: see DESIGN.md) */
+#define VR_SVO_MIN_CTAS 8      /* CTAs per SM the register allocation of vr_svo_kernel targets: 8 x 4 warps, 64 registers
+                                * (measured against 3 x 8 warps / 80 registers and 7 x 4 / 72: DESIGN.md section 5) */
 #endif
 
 /* thread -> pixel inside the CTA tile: warp w = (w&3, w>>2) of 8x4 blocks, lane = (l&7, l>>3) */

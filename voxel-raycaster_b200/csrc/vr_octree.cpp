@@ -155,7 +155,7 @@ void pyramid_emit(Pyramid &p, int dim, const std::function<uint8_t(int, int, int
             vr_node n;
             n.mask_lo = (uint32_t)m;
             n.mask_hi = (uint32_t)(m >> 32);
-            n.aux = 0;
+            n.aux = vr_node_planes(m);
             if (l == p.levels - 1) {
                 n.child_base = (uint32_t)out.leaf_types.size();
                 for (int ci = 0; ci < 64; ci++)
@@ -385,7 +385,7 @@ bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8
             vr_node v;
             v.mask_lo = (uint32_t)n.mask;
             v.mask_hi = (uint32_t)(n.mask >> 32);
-            v.aux = 0;
+            v.aux = vr_node_planes(n.mask);
             const int pc = __builtin_popcountll(n.mask);
             if (l == L - 1) {
                 v.child_base = (uint32_t)out.solid_voxels;

@@ -22,6 +22,7 @@
 
 #include "vr_types.h"
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDA_ARCH__)
 #define VR_ADD(a, b) __fadd_rn((a), (b))
@@ -37,6 +38,17 @@
 #define VR_DIV(a, b) ((a) / (b))
 #define VR_SQRT(a) sqrtf((a))
 #define VR_POPC64(x) __builtin_popcountll((x))
+#endif
+
+/* profiling hooks of the host emulation (tests/host_emu/prof.cpp); nothing on the device */
+#if defined(VR_PROFILE) && !defined(__CUDA_ARCH__)
+struct vr_prof_rec { int path, n, chain_a, chain_b, chain_c, fix, pops, loads, lookup, hit, replay, adds, jumps; };
+extern thread_local vr_prof_rec vr_prof;
+#define VR_PROF(field, v) (vr_prof.field = (v))
+#define VR_PROF_ADD(field, v) (vr_prof.field += (v))
+#else
+#define VR_PROF(field, v) ((void)0)
+#define VR_PROF_ADD(field, v) ((void)0)
 #endif
 
 struct vf3 { float x, y, z; };
@@ -353,15 +365,15 @@ VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba
  * Stack: node indices per level, provided by the caller (shared memory on the device).
  * Requires a cubic power-of-two map so that cells never straddle the map boundary.
  * ------------------------------------------------------------------------------------------- */
-struct vr_node_regs { unsigned long long mask; uint32_t base; };
+struct vr_node_regs { unsigned long long mask; uint32_t base; uint32_t planes; };
 
 VR_HD vr_node_regs vr_load_node(const vr_frame_params &P, uint32_t idx) {
 #if defined(__CUDA_ARCH__)
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(P.nodes) + idx);          /* one 128-bit load */
-    return {(unsigned long long)v.x | ((unsigned long long)v.y << 32), v.z};
+    return {(unsigned long long)v.x | ((unsigned long long)v.y << 32), v.z, v.w};
 #else
     const vr_node &n = P.nodes[idx];
-    return {(unsigned long long)n.mask_lo | ((unsigned long long)n.mask_hi << 32), n.child_base};
+    return {(unsigned long long)n.mask_lo | ((unsigned long long)n.mask_hi << 32), n.child_base, n.aux};
 #endif
 }
 
@@ -393,8 +405,10 @@ VR_HD float vr_min3(float a, float b, float c) {
 
 #if defined(__CUDA_ARCH__)
 #define VR_FMA_EXACT(a, b, c) __fmaf_rn((a), (b), (c))      /* only used where a*b is exact */
+#define VR_FMA(a, b, c) __fmaf_rn((a), (b), (c))            /* a true fused multiply-add on both sides */
 #else
 #define VR_FMA_EXACT(a, b, c) ((c) + (a) * (b))
+#define VR_FMA(a, b, c) fmaf((a), (b), (c))
 #endif
 
 /* one step; returns kx*ky*kz*rem (zero <=> stop) */
@@ -415,21 +429,21 @@ VR_HD float vr_walk_step(vr_walk_state &w, const vf3 &d) {
 
 /* crossings of one axis needed to leave the cell [origin, origin+size) from `voxel`; clamped to 512
  * (a wider cell is then simply left early and found again by the lookup) */
-VR_HD int vr_exit_count(int step, int voxel, int origin, int size) {
+VR_HD int vr_exit_count(int step, int voxel, int origin, int size, int cap) {
     const int r = step > 0 ? origin + size - voxel : voxel - origin + 1;
-    return r > 512 ? 512 : r;
+    return r > cap ? cap : r;
 }
 
 /* The literal walk of one cell (kernel:558-560 step by step, full face mask): used when the float state
  * is not finite (the packed walk assumes ordered compares) and to recover the face mask of a hit that
  * follows a cell in which a multi-axis (tie) step occurred.  Returns true if the last step left the cell. */
 template <bool AUX>
-VR_HD bool vr_walk_literal(RayState &r, int cs, vi3 co, vr_aux *a) {
+VR_HD bool vr_walk_literal(RayState &r, vi3 co, vi3 ce, vr_aux *a) {
     for (;;) {
         vr_dda_step(r);
         if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
-        const int cx = (r.voxel.x ^ co.x) | (r.voxel.y ^ co.y) | (r.voxel.z ^ co.z);
-        if ((cx >> cs) != 0) return true;
+        if ((unsigned)(r.voxel.x - co.x) >= (unsigned)ce.x || (unsigned)(r.voxel.y - co.y) >= (unsigned)ce.y ||
+            (unsigned)(r.voxel.z - co.z) >= (unsigned)ce.z) return true;
         r.dist++;
         if (!(r.dist < r.max_distance)) return false;
     }
@@ -463,18 +477,78 @@ enum { VR_AXES_FALLBACK = 0, VR_AXES_DONE = 1, VR_AXES_MAXDIST = 2 };
 #define VR_AXES_MIN_COUNT 12     /* rx+ry+rz above which a cell is walked per axis (measured) */
 #endif
 
+VR_HD int vr_f2bits(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(v);
+#else
+    int b; memcpy(&b, &v, 4); return b;
+#endif
+}
+VR_HD float vr_bits2f(int b) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(b);
+#else
+    float v; memcpy(&v, &b, 4); return v;
+#endif
+}
+
+/* t after n additions of d, each rounded to nearest-even like kernel:559 does them one by one -- but in O(number of
+ * binades crossed) instead of O(n).  While t stays inside one binade [2^e, 2^(e+1)) every value is a multiple of
+ * u = ulp = 2^(e-23), so RN(t + d) = t + dr with the SAME dr = "d rounded to the grid u" for every such addition;
+ * j of them are t + j*dr, which one FMA evaluates exactly (the result is a grid point below 2^(e+1)).  Only the
+ * addition that leaves the binade (rounded on the coarser grid) and the case where d falls exactly half way between
+ * two grid points (ties-to-even: the increment then depends on the parity of t) are done literally.
+ * dr is measured, not derived: two literal additions t1 = t+d, t2 = t1+d, dr = t2 - t1 (exact, same binade). */
+#ifndef VR_JUMP_MIN
+#define VR_JUMP_MIN 64           /* chains at least this long use the jumps (one jump costs about 35 issue slots); 0 = never */
+#endif
+#ifndef VR_CHAIN_UNROLL
+#define VR_CHAIN_UNROLL 8
+#endif
 VR_HD float vr_add_chain(float t, float d, int n) {
+    while (VR_JUMP_MIN > 0 && n >= VR_JUMP_MIN) {
+        const float t1 = VR_ADD(t, d);
+        const float t2 = VR_ADD(t1, d);
+        t = t2;
+        n -= 2;
+        VR_PROF_ADD(jumps, 1);
+        const int e1 = vr_f2bits(t1) & 0x7f800000;
+        if ((vr_f2bits(t2) & 0x7f800000) != e1 || e1 < (30 << 23) || e1 >= (250 << 23)) continue;   /* left the binade (or no room for u/2, inf) */
+        const float dr = VR_SUB(t2, t1);
+        if (fabsf(VR_SUB(dr, d)) == vr_bits2f(e1 - (24 << 23))) break;   /* d is half way between grid points: literal */
+        if (dr == 0.0f) return t;                                         /* d < u/2: t no longer moves */
+        const float top = vr_bits2f(e1 + (1 << 23));
+#if defined(__CUDA_ARCH__)
+        const float q = __fdividef(VR_SUB(top, t2), dr);
+#else
+        const float q = VR_SUB(top, t2) / dr;
+#endif
+        int k = (q < 1.0e6f ? (int)q : 1000000) - 2;                      /* t2 + k*dr stays below top (q is off by << 1) */
+        k = k < n ? k : n;
+        if (k > 0) {
+            t = VR_FMA((float)k, dr, t2);
+            n -= k;
+        }
+    }
+    VR_PROF_ADD(adds, n);
+#if VR_CHAIN_UNROLL >= 8
+    for (; n >= 8; n -= 8) t = VR_ADD(VR_ADD(VR_ADD(VR_ADD(VR_ADD(VR_ADD(VR_ADD(VR_ADD(t, d), d), d), d), d), d), d), d);
+#endif
     for (; n >= 4; n -= 4) t = VR_ADD(VR_ADD(VR_ADD(VR_ADD(t, d), d), d), d);
     for (; n > 0; --n) t = VR_ADD(t, d);
     return t;
 }
 
+#ifndef VR_COUNT_MARGIN
+#define VR_COUNT_MARGIN 1
+#endif
 /* crossings of one non-exit axis strictly before T; t ends at the first crossing time >= T */
 VR_HD int vr_count_before(float &t, float d, float inv_d, float T) {
-    int c = (int)(VR_MUL(VR_SUB(T, t), inv_d)) - 2;       /* estimate minus margin: never overshoots */
+    int c = (int)(VR_MUL(VR_SUB(T, t), inv_d)) - VR_COUNT_MARGIN;   /* estimate minus margin: never overshoots (the estimate is off by < 0.5) */
     c = c < 0 ? 0 : c;
     t = vr_add_chain(t, d, c);
-    while (t < T) { t = VR_ADD(t, d); c++; }
+    VR_PROF_ADD(chain_b, c);
+    while (t < T) { t = VR_ADD(t, d); c++; VR_PROF_ADD(fix, 1); }
     return c;
 }
 
@@ -493,6 +567,7 @@ VR_HD int vr_walk_axes(RayState &r, int rx, int ry, int rz, int nmax, int &ax, i
     const int rB = sel == 0 ? ry : (sel == 1 ? rz : rx);
     const int rC = sel == 0 ? rz : (sel == 1 ? rx : ry);
     tA = vr_add_chain(tA, dA, rA - 1);
+    VR_PROF(chain_a, rA - 1);
     const float T = tA;                                                   /* time of the step that leaves the cell */
     tA = VR_ADD(tA, dA);
     int tieB = 0, tieC = 0;
@@ -562,6 +637,48 @@ VR_HD int vr_walk_brick(RayState &r, unsigned long long mask, vi3 co, int &n, in
     return res;
 }
 
+/* The empty box handed to the in-cell walk when the descent meets the empty slot ci of a node (slots of edge 1<<s).
+ * The walk works in any empty box, so the box is grown inside the node as far as the 64-bit mask proves it empty:
+ *   - if the whole 4x4 plane of slots through ci perpendicular to some axis is empty, the box is the run of
+ *     consecutive empty planes around it (heightfield-like scenes: everything above the surface inside the node);
+ *   - else, if the 2x2x2 octant of slots around ci is empty, that octant (the odd levels of the reference's 2^3
+ *     octree, recovered from the 4^3 mask: slots ci&0x2A + {0,1,4,5,16,17,20,21});
+ *   - else the slot itself. */
+#ifndef VR_PLANE_BOXES
+#define VR_PLANE_BOXES 0         /* measured on B200: 12 % fewer lookups at C3 but no faster (2.305 vs 2.301 ms), slower at C2 */
+#endif
+VR_HD void vr_empty_box(unsigned long long m, uint32_t planes, int ci, int s, vi3 v, int N, vi3 &co, vi3 &ce) {
+    if (VR_PLANE_BOXES) {
+        const int cx = ci & 3, cy = (ci >> 2) & 3, cz = ci >> 4;
+        const int axis = ((planes >> (8 + cz)) & 1u) ? 2 : (((planes >> (4 + cy)) & 1u) ? 1 : (((planes >> cx) & 1u) ? 0 : -1));
+        if (axis >= 0) {
+            const uint32_t e = (planes >> (4 * axis)) & 15u;             /* the 4 planes along `axis`; bit c is set */
+            const int c = axis == 2 ? cz : (axis == 1 ? cy : cx);
+#if defined(__CUDA_ARCH__)
+            const int up = __ffs((int)~(e >> (c + 1))) - 1;               /* empty planes right above / below plane c */
+            const int dn = __clz((int)~((e << (31 - c)) << 1));
+#else
+            const int up = __builtin_ffs((int)~(e >> (c + 1))) - 1;
+            const int dn = __builtin_clz(~((e << (31 - c)) << 1));
+#endif
+            const int ns = s + 2;                                        /* the node's own edge is 1 << ns */
+            const int full = 4 << s, o = (c - dn) << s, len = (up + dn + 1) << s;
+            co = {(v.x >> ns) << ns, (v.y >> ns) << ns, (v.z >> ns) << ns};
+            ce = {full, full, full};
+            if (axis == 0) { co.x += o; ce.x = len; }
+            if (axis == 1) { co.y += o; ce.y = len; }
+            if (axis == 2) { co.z += o; ce.z = len; }
+            /* the root may be wider than the map (N not a power of 4): the box must end at the map boundary, where the
+             * walk has to stop for the bounds test */
+            ce = {ce.x < N - co.x ? ce.x : N - co.x, ce.y < N - co.y ? ce.y : N - co.y, ce.z < N - co.z ? ce.z : N - co.z};
+            return;
+        }
+    }
+    const int cs = s + ((((m >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
+    co = {(v.x >> cs) << cs, (v.y >> cs) << cs, (v.z >> cs) << cs};
+    ce = {1 << cs, 1 << cs, 1 << cs};
+}
+
 /* Per-ray traversal state of the SVO variant: everything that lives across cells. */
 template <class Stack>
 struct vr_svo_ray {
@@ -570,8 +687,7 @@ struct vr_svo_ray {
     int s;                    /* its child shift */
     int level;
     vi3 nv;                   /* a voxel inside the current node */
-    int cs;                   /* cached empty cell: edge 1 << cs at origin co */
-    vi3 co;
+    vi3 co, ce;               /* cached empty cell: the box of ce voxels at origin co */
     bool brick;               /* the cached cell is the leaf brick of `node` (4^3 voxels, occupancy = node.mask) */
     bool finite;
     bool first_hit_done;
@@ -596,8 +712,8 @@ VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack
     if (AUX) a->node_fetches = 1;
     /* the first "cell" is the camera voxel itself: the reference steps before it loads (kernel:555-570),
      * so that voxel is never tested */
-    q.cs = 0;
     q.co = q.r.voxel;
+    q.ce = {1, 1, 1};
     q.brick = false;
     q.finite = vr_ray_finite(q.r);
     q.first_hit_done = false;
@@ -621,12 +737,13 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
     const int nmax = r.max_distance - r.dist;
     /* a brick is walked as such unless the ray is about to end (then voxel by voxel, like any 1^3 cell) */
     const bool as_brick = q.brick && q.finite && nmax > 12;
-    const int wcs = q.brick && !as_brick ? 0 : q.cs;
+    const vi3 wce = q.brick && !as_brick ? vi3{1, 1, 1} : q.ce;
     const vi3 wco = q.brick && !as_brick ? r.voxel : q.co;
     if (as_brick) {
         int bit;
         bool tie;
         const int res = vr_walk_brick(r, q.node.mask, q.co, n, bit, tie);
+        VR_PROF(path, 1); VR_PROF(n, n);
         if (AUX && tie) a->flags |= VR_FL_TIE;
         r.dist += n - 1;
         if (res == VR_BRICK_HIT) {
@@ -634,10 +751,12 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             known = true;
         }
     } else if (q.finite) {
-        const int S = 1 << wcs;
-        const int rx = vr_exit_count(r.step.x, r.voxel.x, wco.x, S);
-        const int ry = vr_exit_count(r.step.y, r.voxel.y, wco.y, S);
-        const int rz = vr_exit_count(r.step.z, r.voxel.z, wco.z, S);
+        /* no axis can cross more often than max_distance leaves steps: a ray that ends inside the cell (most shadow
+         * rays end in mid-air, at the light's distance) must not pay for the walk to the far side of a wide cell */
+        const int rcap = nmax < 511 ? nmax + 1 : 512;
+        const int rx = vr_exit_count(r.step.x, r.voxel.x, wco.x, wce.x, rcap);
+        const int ry = vr_exit_count(r.step.y, r.voxel.y, wco.y, wce.y, rcap);
+        const int rz = vr_exit_count(r.step.z, r.voxel.z, wco.z, wce.z, rcap);
         bool exit_tie = false;
         /* short walks (cells of a few voxels next to surfaces) are cheaper step by step: 16 slots per step against
          * ~200 of fixed cost for the per-axis machinery */
@@ -648,6 +767,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             return VR_ST_MAXDIST;
         }
         if (axes == VR_AXES_DONE) {
+            VR_PROF(path, 2); VR_PROF(n, n);
             /* per-axis walk: float state, crossing counts and face mask are exact; see vr_walk_axes */
             r.voxel.x += r.step.x * ax;
             r.voxel.y += r.step.y * ay;
@@ -661,6 +781,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             const float kx = w.kx, ky = w.ky, kz = w.kz;
             ax = rx - (int)kx; ay = ry - (int)ky; az = rz - (int)kz;     /* crossings done per axis */
             n = nmax - (int)w.rem;                                       /* steps done */
+            VR_PROF(path, (WALK == 1 && rx + ry + rz > VR_AXES_MIN_COUNT) ? 4 : 3); VR_PROF(n, n);
             r.voxel.x += r.step.x * ax;
             r.voxel.y += r.step.y * ay;
             r.voxel.z += r.step.z * az;
@@ -672,7 +793,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             if (r.fm == 0) { r.dist += n; return VR_ST_MAXDIST; }        /* max_distance reached inside the cell */
             r.dist += n - 1;
         }
-    } else if (!vr_walk_literal<AUX>(r, wcs, wco, a)) {
+    } else if (!vr_walk_literal<AUX>(r, wco, wce, a)) {
         return VR_ST_MAXDIST;
     }
     /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
@@ -682,10 +803,11 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             return VR_ST_OOB;
         }
         if (AUX) a->lookups++;
+        VR_PROF(lookup, 1);
         /* pop to the lowest ancestor containing the voxel */
         const int nx = (r.voxel.x ^ q.nv.x) | (r.voxel.y ^ q.nv.y) | (r.voxel.z ^ q.nv.z);
         if ((nx >> (q.s + 2)) != 0) {
-            do { q.s += 2; q.level--; } while ((nx >> (q.s + 2)) != 0);
+            do { q.s += 2; q.level--; VR_PROF_ADD(pops, 1); } while ((nx >> (q.s + 2)) != 0);
             q.node = vr_load_node(P, q.stk.get(q.level));
             if (AUX) a->node_fetches++;
         }
@@ -697,16 +819,14 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
                 if (s == 0) {
                     /* an empty voxel of a leaf brick: the whole brick becomes the cell, walked with bit tests */
                     q.brick = true;
-                    q.cs = 2;
+                    q.ce = {4, 4, 4};
                     q.co = {r.voxel.x & ~3, r.voxel.y & ~3, r.voxel.z & ~3};
                     break;
                 }
                 /* if the whole 2x2x2 octant of slots around it is empty the cell is twice as wide -- the odd levels
                  * of the reference's 2^3 octree, recovered from the 4^3 mask (slots ci&0x2A + {0,1,4,5,16,17,20,21}) */
-                const int cs = s + ((((q.node.mask >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
                 q.brick = false;
-                q.cs = cs;
-                q.co = {(r.voxel.x >> cs) << cs, (r.voxel.y >> cs) << cs, (r.voxel.z >> cs) << cs};
+                vr_empty_box(q.node.mask, q.node.planes, ci, s, r.voxel, N, q.co, q.ce);
                 break;
             }
             const uint32_t rank = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
@@ -719,6 +839,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             q.s -= 2;
             q.stk.set(q.level, child);
             q.node = vr_load_node(P, child);
+            VR_PROF_ADD(loads, 1);
             if (AUX) a->node_fetches++;
         }
     }
@@ -731,8 +852,10 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             r.voxel.z -= r.step.z * az;
             r.dist -= n - 1;
             r.t = t0;
-            vr_walk_literal<false>(r, wcs, wco, a);
+            vr_walk_literal<false>(r, wco, wce, a);
+            VR_PROF(replay, 1);
         }
+        VR_PROF(hit, 1);
         const int st = vr_hit_block<AUX>(P, r, voxel_data, a, q.first_hit_done);
         if (st == VR_ST_SKIP_REDIRECT) {
             if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
@@ -743,7 +866,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
          * is the cell (the previous cell may have been a brick whose node is no longer the current one) */
         q.finite = vr_ray_finite(r);
         q.brick = false;
-        q.cs = 0;
+        q.ce = {1, 1, 1};
         q.co = r.voxel;
     }
     r.dist++;

@@ -28,8 +28,20 @@ typedef struct vr_node {
     uint32_t mask_lo;
     uint32_t mask_hi;
     uint32_t child_base;
-    uint32_t aux;          /* reserved (solid-subtree mask table index); 0 */
+    uint32_t aux;          /* vr_node_planes(mask): which of the 4+4+4 axis-perpendicular slot planes are empty */
 } vr_node;
+
+/* aux word of a node: bit k = the 4x4 plane of slots x == k is empty, bit 4+k: y == k, bit 8+k: z == k.
+ * A function of the mask alone, stored so that the traversal gets it with the node's 128-bit load. */
+VR_HD uint32_t vr_node_planes(unsigned long long m) {
+    uint32_t e = 0;
+    for (int k = 0; k < 4; k++) {
+        e |= ((m & (0x1111111111111111ull << k)) == 0ull ? 1u : 0u) << k;
+        e |= ((m & (0x000F000F000F000Full << (4 * k))) == 0ull ? 1u : 0u) << (4 + k);
+        e |= ((m & (0xFFFFull << (16 * k))) == 0ull ? 1u : 0u) << (8 + k);
+    }
+    return e;
+}
 
 /* Per-pixel auxiliary record (32 bytes), layout-identical to the oracle's vro_aux. */
 typedef struct vr_aux {
