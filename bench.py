@@ -39,7 +39,7 @@ def package():
     return importlib.import_module("voxel-raycaster_b200")
 
 
-def bench_scene(config: str = "c3", with_volume: bool = True):
+def bench_scene(config: str = "c3", with_volume: bool = True, lights: int = 1):
     """The named workload.  c3 = BASELINE.json configs[2]: 1024^3 sparse (shell) terrain, 3840x2160,
     one shadow light (light 0 is the only one the reference kernel reads), max_distance 3N."""
     S = package().scene
@@ -49,15 +49,15 @@ def bench_scene(config: str = "c3", with_volume: bool = True):
         n = 4096
         lo, hi = S.terrain_columns(n, "shell")
         pos, direction = S.make_camera(n, hi, BENCH_CAMERA)
-        return S.Scene(n, None, 7680, 4320, pos, direction, S.make_lights(n, 1), max_distance=3 * n, name="c4-shell",
+        return S.Scene(n, None, 7680, 4320, pos, direction, S.make_lights(n, lights), max_distance=3 * n, name="c4-shell",
                        columns=(lo, hi) if with_volume else None)
     if not with_volume:
         # camera / lights / atlas only (ranks > 0 receive the octree by broadcast)
         table = {"c1": (64, 1280, 720), "c2": (256, 1920, 1080), "c3": (1024, 3840, 2160)}
         n, w, h = table[config]
         pos, direction = S.make_camera(n, S.heightfield(n), BENCH_CAMERA)
-        return S.Scene(n, None, w, h, pos, direction, S.make_lights(n, 1), max_distance=3 * n, name=f"{config}-shell")
-    return S.make_scene(config, camera_index=BENCH_CAMERA)
+        return S.Scene(n, None, w, h, pos, direction, S.make_lights(n, lights), max_distance=3 * n, name=f"{config}-shell")
+    return S.make_scene(config, camera_index=BENCH_CAMERA, lights=lights)
 
 
 class ClockSampler:
@@ -124,8 +124,8 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def load_algorithmic_bytes(config: str) -> dict | None:
-    p = ROOT / "profiles" / f"algorithmic_bytes_{config}.json"
+def load_algorithmic_bytes(config: str, lights: int = 1) -> dict | None:
+    p = ROOT / "profiles" / (f"algorithmic_bytes_{config}.json" if lights == 1 else f"algorithmic_bytes_{config}_l{lights}.json")
     return json.loads(p.read_text()) if p.exists() else None
 
 
@@ -136,7 +136,7 @@ def measured_peak_gbs() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_sample(scene, row_stride: int, threads: int = 0) -> tuple[float, int, int]:
+def oracle_sample(scene, row_stride: int, threads: int = 0, lights: int = 1) -> tuple[float, int, int]:
     """Times the CPU restatement of the reference kernel (dense DDA over the char map, kernel:555-570) on
     every row_stride-th row.  Returns (seconds, rays in the sample, host threads)."""
     sys.path.insert(0, str(ROOT / "tests"))
@@ -145,10 +145,13 @@ def oracle_sample(scene, row_stride: int, threads: int = 0) -> tuple[float, int,
     table = O.make_ray_table(scene.width, scene.height)
     O.raycast(scene, table, rows=(0, 8), want_aux=False)                      # warm the library / page in
     t0 = time.perf_counter()
-    _, aux, _ = O.raycast(scene, table, want_aux=True, row_stride=row_stride, threads=threads)
+    _, aux, cnt = O.raycast(scene, table, want_aux=True, row_stride=row_stride, threads=threads, shadow_lights=lights,
+                             want_counters=lights > 1)
     dt = time.perf_counter() - t0
     a = aux[::row_stride]
     rays = int((a["status"] != O.ST_SKIP_PRIMARY).sum() + ((a["flags"] & O.FL_LIT) != 0).sum())
+    if lights > 1:
+        rays = int(cnt["primary_rays"] + cnt["shadow_rays"])
     return dt, rays, threads or O.num_procs()
 
 
@@ -158,11 +161,11 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = bench_scene(args.config)
+    scene = bench_scene(args.config, lights=args.lights)
     stride = args.ref_row_stride
     times, rays = [], 0
     for i in range(args.warmup + args.steps):
-        dt, rays, threads = oracle_sample(scene, stride)
+        dt, rays, threads = oracle_sample(scene, stride, lights=args.lights)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -287,6 +290,8 @@ def main() -> None:
     ap.add_argument("--cpu-row-stride", type=int, default=2, help="oracle sample for cpu_baseline (every Nth row; ~25 core-seconds at c3)")
     ap.add_argument("--ref-row-stride", type=int, default=4, help="oracle sample per step for --impl reference (every Nth row)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lights", type=int, default=1, help="shadow lights: 1 = the reference kernel (light 0 only, the headline); 2 = BASELINE configs[2]'s wording, "
+                    "through the multi-light extension (one shadow ray per light from the same hit)")
     ap.add_argument("--persistent", type=int, default=0, help="1 = persistent-warp octree kernel")
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
@@ -319,7 +324,7 @@ def main() -> None:
         run_views(args, pkg, torch, dist, rank, world, local_rank, dev)
         return
     use_svo = args.mode == "svo"
-    scene = bench_scene(args.config, with_volume=(rank == 0 or not use_svo))
+    scene = bench_scene(args.config, with_volume=(rank == 0 or not use_svo), lights=args.lights)
     c = pkg.CUDACaster()
 
     def must(ok, what):
@@ -330,6 +335,8 @@ def main() -> None:
     must(c.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n), "OCTDIM")
     must(c.add_to_settings_buffer("using_octree", "OCTENABLED", 0 if use_svo else 1), "OCTENABLED")
     must(c.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance), "MAX_DISTANCE")
+    if args.lights > 1:                          # multi-light extension (the reference kernel reads light 0 only)
+        must(c.add_to_settings_buffer("light_count", "LIGHT_COUNT", args.lights), "LIGHT_COUNT")
     stream = torch.cuda.Stream(device=dev)       # a real (non-default) stream shared by torch, NCCL and the caster
     torch.cuda.set_stream(stream)
     must(c.set_stream(stream.cuda_stream), "set_stream")
@@ -395,6 +402,7 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(counts)
     primary, shadow, node_fetches, lookups, steps_total = [int(v) for v in counts.tolist()]
+    shadow *= args.lights                        # one shadow ray per light from every lit hit
     rays = primary + shadow
     must(c.enable_aux(False), "enable_aux off")
     del aux
@@ -485,7 +493,7 @@ def main() -> None:
 
     if rank == 0:
         peak, peak_how = measured_peak_gbs()
-        ab = load_algorithmic_bytes(args.config)
+        ab = load_algorithmic_bytes(args.config, args.lights)
         key = "bytes_svo" if use_svo else "bytes_dense"
         algo_bytes = float(ab[key]) if ab else None
         st = c.stats()
@@ -504,14 +512,14 @@ def main() -> None:
                         "node_bytes_fetched_per_launch": 16.0 * node_fetches / world}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            dt, sample_rays, threads = oracle_sample(scene, args.cpu_row_stride * (8 if args.config == "c4" else 1))
+            dt, sample_rays, threads = oracle_sample(scene, args.cpu_row_stride * (8 if args.config == "c4" else 1), lights=args.lights)
             cpu = {"value": sample_rays / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                    "sample": f"every {args.cpu_row_stride}th row of the frame ({sample_rays} rays, {dt:.1f} s); dense DDA restatement of the OpenCL kernel"}
         out = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
-            "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + 1 shadow light, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
+            "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
                        "mode": args.mode,
                        "walk": ("per-axis in-cell walk: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)" if args.walk == 1 else "merged in-cell walk: bit-identical to the reference restatement on every pixel") if use_svo else "dense DDA",
                        "other_walk_ms_per_frame": other_walk_ms,
@@ -520,6 +528,10 @@ def main() -> None:
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "scene_build_s": round(t_build, 2),
+                       "octree_build": ({"where": "device (vr_build.cu) from the uploaded dense map", "ms": round(float(st.build_ms), 3),
+                                         "map_read_ms": round(float(st.build_masks_ms), 3),
+                                         "map_read_gbs": round(scene.n ** 3 / max(float(st.build_masks_ms), 1e-6) / 1e6, 1)}
+                                        if st.build_ms > 0 else {"where": "host (column builder or broadcast)"}),
                        "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum},
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -139,7 +139,10 @@ int vr_frame_end(vr_ctx *ctx, const uint8_t **rgba);
 int vr_set_bands(vr_ctx *ctx, int band_rows, int stride, int first);
 int vr_local_rows(const vr_ctx *ctx);
 /* Kernel variant knobs: "persistent" (0/1: persistent warps with warp-level pixel refill for the octree
- * kernel), "refill_min" (idle lanes before a warp refills, 1..32), "ctas_per_sm" (persistent grid size). */
+ * kernel), "refill_min" (idle lanes before a warp refills, 1..32), "ctas_per_sm" (persistent grid size),
+ * "walk" (0 merged / 1 per-axis in-cell walk), "l2_persist" (0/1 access-policy window over the octree nodes),
+ * "gpu_build" (1, default: vr_assign_map builds the 64-tree on the device from the uploaded map -- the
+ * replacement of Octree::Generate, ref src/map/Octree.cpp:13-43,171-323; 0: on the host). */
 int vr_set_option(vr_ctx *ctx, const char *name, int64_t value);
 /* Use an externally owned CUDA stream (e.g. the host framework's current stream); NULL restores the own stream. */
 int vr_set_stream(vr_ctx *ctx, void *cuda_stream);
@@ -191,6 +194,8 @@ typedef struct vr_stats {
     int32_t bias[3];               /* last frame's get_oct_vox start bias                    */
     int32_t device;
     float last_kernel_ms;          /* CUDA-event time of the last vr_compute's kernel        */
+    float build_ms;                /* last on-device 64-tree build (assign_map), CUDA events */
+    float build_masks_ms;          /* ... of which the kernel that reads the N^3 map         */
 } vr_stats;
 int vr_get_stats(vr_ctx *ctx, vr_stats *out);
 

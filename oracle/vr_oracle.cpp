@@ -270,12 +270,56 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
     CellTrack cell;
     if (COUNT && count_svo) svo_lookup(s, voxel, cell, k);                /* the camera-voxel descent */
 
-    const f3 L = {s->lights[4], s->lights[5], s->lights[6]};
-    const f4 Lc = {s->lights[0], s->lights[1], s->lights[2], s->lights[3]};
+    /* The reference reads light 0 only (kernel:660-670).  EXTENSION (`shadow_lights` > 1): the
+     * lights are taken one after the other from the same hit point.  Light i adds its view_light term to the
+     * colour accumulated so far and casts its own shadow ray, with the reference's own budget (max_distance =
+     * steps at the hit + distance to that light); a blocked light leaves 0.1 instead of its term in alpha.
+     * With shadow_lights == 1 every statement below is the reference's. */
+    const int n_lights = s->shadow_lights < 1 ? 1 : (s->shadow_lights > s->light_count ? s->light_count : s->shadow_lights);
+    int light_i = 0;
+    f3 L = {s->lights[4], s->lights[5], s->lights[6]};
+    f4 Lc = {s->lights[0], s->lights[1], s->lights[2], s->lights[3]};
+    i3 hit_voxel = {0, 0, 0}, hit_normal = {0, 0, 0}, hit_empty = {0, 0, 0};
+    f3 hit_point = {0, 0, 0};
+    int hit_steps = 0;
+    float alpha_before = 0.0f;
     const int X = s->map_dim[0], Y = s->map_dim[1], Z = s->map_dim[2];
 
+    /* extension: start the shadow ray of the next light from the stored hit; false = pixel skipped (kernel:671) */
+    auto next_light = [&]() -> bool {
+        light_i++;
+        const float *lp = s->lights + 10 * light_i;
+        L = {lp[4], lp[5], lp[6]};
+        Lc = {lp[0], lp[1], lp[2], lp[3]};
+        alpha_before = color.w;
+        color = view_light(color, hit_point - L, Lc, hit_point - cam, hit_normal);
+        distance_traveled = hit_steps + 1;                                /* as after the first redirect (kernel:714) */
+        max_distance = (int)((float)hit_steps + cl_length(to_f3(hit_voxel) - L));
+        ray_dir = cl_normalize(L - hit_point);
+        if (ray_dir.x == 0.0f || ray_dir.y == 0.0f || ray_dir.z == 0.0f) return false;
+        if (COUNT) k.shadow_rays++;
+        voxel = hit_empty;
+        voxel_step = {cl_sign_step(ray_dir.x), cl_sign_step(ray_dir.y), cl_sign_step(ray_dir.z)};
+        delta_t = {fabsf(1.0f / ray_dir.x), fabsf(1.0f / ray_dir.y), fabsf(1.0f / ray_dir.z)};
+        t.x = (delta_t.x * (hit_point.x - floorf(hit_point.x))) * (float)voxel_step.x;
+        t.y = (delta_t.y * (hit_point.y - floorf(hit_point.y))) * (float)voxel_step.y;
+        t.z = (delta_t.z * (hit_point.z - floorf(hit_point.z))) * (float)voxel_step.z;
+        t.x += delta_t.x * ((t.x < 0.0f) ? 1.0f : -0.0f);
+        t.y += delta_t.y * ((t.y < 0.0f) ? 1.0f : -0.0f);
+        t.z += delta_t.z * ((t.z < 0.0f) ? 1.0f : -0.0f);
+        if (COUNT && count_svo) { cell = CellTrack(); svo_lookup(s, voxel, cell, k); }
+        return true;
+    };
+
     uint8_t status = VRO_ST_MAXDIST;
-    while (distance_traveled < max_distance && bounce_count < 2) {        /* kernel:357 */
+    for (;;) {
+        if (!(distance_traveled < max_distance && bounce_count < 2)) {    /* kernel:357 */
+            if (shadow_ray && light_i + 1 < n_lights && bounce_count < 2) {   /* extension: this light is not blocked */
+                if (!next_light()) { finish(VRO_ST_SKIP_REDIRECT, distance_traveled); return; }
+                continue;
+            }
+            break;
+        }
         /* dense branch, kernel:555-570 */
         face_mask.x = (t.x <= cl_min(t.y, t.z)) ? 1 : 0;                  /* kernel:558 */
         face_mask.y = (t.y <= cl_min(t.z, t.x)) ? 1 : 0;
@@ -289,6 +333,10 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
         voxel.z += voxel_step.z * face_mask.z;
 
         if (voxel.x >= X || voxel.y >= Y || voxel.z >= Z || voxel.x < 0 || voxel.y < 0 || voxel.z < 0) { /* :563 */
+            if (shadow_ray && light_i + 1 < n_lights) {                   /* extension: left the map unblocked */
+                if (!next_light()) { finish(VRO_ST_SKIP_REDIRECT, distance_traveled); return; }
+                continue;
+            }
             voxel.x -= voxel_step.x * face_mask.x;
             voxel.y -= voxel_step.y * face_mask.y;
             voxel.z -= voxel_step.z * face_mask.z;
@@ -368,6 +416,12 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
                 voxel_color.z += tex.z / 2.0f;
 
                 f3 hit_pos = to_f3(voxel) + face_position;
+                hit_point = hit_pos;                                      /* extension state (unused with one light) */
+                hit_voxel = voxel;
+                hit_steps = distance_traveled;
+                hit_normal = {face_mask.x * voxel_step.x, face_mask.y * voxel_step.y, face_mask.z * voxel_step.z};
+                hit_empty = {voxel.x - voxel_step.x * face_mask.x, voxel.y - voxel_step.y * face_mask.y,
+                             voxel.z - voxel_step.z * face_mask.z};
                 color = view_light(voxel_color, hit_pos - L, Lc, hit_pos - cam,      /* kernel:658 */
                                    {face_mask.x * voxel_step.x, face_mask.y * voxel_step.y, face_mask.z * voxel_step.z});
                 fog_distance = (float)distance_traveled;                  /* kernel:666 */
@@ -423,7 +477,11 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
                 t.z += delta_t.z * ((t.z < 0.0f) ? 1.0f : -0.0f);
                 bounce_count += 1;                                        /* kernel:704 */
             } else {                                                      /* kernel:707 */
-                color.w = 0.1f;
+                color.w = alpha_before + 0.1f;                            /* one light: 0 + 0.1 = kernel:708 */
+                if (light_i + 1 < n_lights) {                             /* extension */
+                    if (!next_light()) { finish(VRO_ST_SKIP_REDIRECT, distance_traveled); return; }
+                    continue;
+                }
                 status = VRO_ST_SHADOW_HIT;
                 break;
             }

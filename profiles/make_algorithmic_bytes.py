@@ -30,14 +30,16 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c3")
 ap.add_argument("--row-stride", type=int, default=8)
+ap.add_argument("--lights", type=int, default=1)
 args = ap.parse_args()
 
-scene = bench.bench_scene(args.config)
+scene = bench.bench_scene(args.config, lights=args.lights)
 t0 = time.time()
 desc, root = pkg.octree_generate(scene.volume)
 print(f"reference-format octree: {desc.size} descriptors ({desc.nbytes / 1e6:.1f} MB) in {time.time() - t0:.1f} s")
 t0 = time.time()
-_, aux, cnt = O.raycast(scene, octree=(desc, root), want_counters=True, count_svo=True, row_stride=args.row_stride)
+_, aux, cnt = O.raycast(scene, octree=(desc, root), want_counters=True, count_svo=True, row_stride=args.row_stride,
+                        shadow_lights=args.lights)
 print(f"oracle counters over 1/{args.row_stride} of the rows in {time.time() - t0:.1f} s: {cnt}")
 k = scene.height * scene.width / cnt["pixels"]
 P = scene.width * scene.height
@@ -55,6 +57,7 @@ out = {
 out["bytes_svo"] = P * 20 + 8 * out["svo_desc_fetches"] + 4 * out["texel_fetches"]
 out["bytes_dense"] = P * 20 + 1 * out["dda_steps"] + 4 * out["texel_fetches"]
 out["rays"] = out["primary_rays"] + out["shadow_rays"] + out["reflect_rays"]
-path = ROOT / "profiles" / f"algorithmic_bytes_{args.config}.json"
+out["shadow_lights"] = args.lights
+path = ROOT / "profiles" / (f"algorithmic_bytes_{args.config}.json" if args.lights == 1 else f"algorithmic_bytes_{args.config}_l{args.lights}.json")
 path.write_text(json.dumps(out, indent=1) + "\n")
 print(json.dumps(out, indent=1))

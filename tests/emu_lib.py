@@ -24,7 +24,8 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False, max_distance: int | None = None):
+def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False, max_distance: int | None = None,
+            shadow_lights: int = 1):
     w, h = scene.width, scene.height
     vol = np.ascontiguousarray(scene.volume, dtype=np.int8)
     lights = np.ascontiguousarray(scene.lights, dtype=np.float32)
@@ -38,7 +39,7 @@ def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False,
         C.c_int(w), C.c_int(h), ray_table.ctypes.data_as(fp), vol.ctypes.data_as(C.c_void_p), C.c_int(scene.n),
         scene.cam_pos.ctypes.data_as(fp), scene.cam_dir.ctypes.data_as(fp), b, lights.ctypes.data_as(fp),
         atlas.ctypes.data_as(C.c_void_p), C.c_int(atlas.shape[1]), C.c_int(atlas.shape[0]), C.c_int(scene.tile), C.c_int(scene.tile),
-        C.c_int(scene.max_distance if max_distance is None else max_distance), C.c_int(int(use_svo)),
+        C.c_int(scene.max_distance if max_distance is None else max_distance), C.c_int(int(use_svo)), C.c_int(shadow_lights),
         rgba.ctypes.data_as(C.c_void_p), aux.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(f"emu_raycast failed: {rc}")

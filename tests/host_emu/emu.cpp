@@ -20,7 +20,7 @@ struct LocalStack {
 extern "C" int emu_raycast(int width, int height, const float *ray_table, const int8_t *map, int n,
                            const float *cam_pos, const float *cam_dir, const int32_t *bias, const float *lights,
                            const uint8_t *atlas, int atlas_w, int atlas_h, int tile_w, int tile_h, int max_distance,
-                           int use_svo, uint8_t *rgba, vr_aux *aux) {
+                           int use_svo, int shadow_lights, uint8_t *rgba, vr_aux *aux) {
     vr_native_tree tree;
     vr_frame_params P;
     memset(&P, 0, sizeof(P));
@@ -29,8 +29,12 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
     P.ray_table = ray_table;
     P.map = map;
     P.dim[0] = P.dim[1] = P.dim[2] = n;
-    for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = (float)bias[i]; P.light_pos[i] = lights[4 + i]; }
-    for (int i = 0; i < 4; i++) P.light_rgbi[i] = lights[i];
+    for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = (float)bias[i]; }
+    P.light_count = shadow_lights < 1 ? 1 : (shadow_lights > VR_MAX_LIGHTS ? VR_MAX_LIGHTS : shadow_lights);
+    for (int l = 0; l < P.light_count; l++) {
+        for (int i = 0; i < 4; i++) P.light_rgbi[l][i] = lights[10 * l + i];
+        for (int i = 0; i < 3; i++) P.light_pos[l][i] = lights[10 * l + 4 + i];
+    }
     P.trig[0] = sinf(cam_dir[0]); P.trig[1] = cosf(cam_dir[0]); P.trig[2] = sinf(cam_dir[1]); P.trig[3] = cosf(cam_dir[1]);
     P.atlas = atlas; P.atlas_dim[0] = atlas_w; P.atlas_dim[1] = atlas_h;
     P.atlas_scale[0] = atlas_w / tile_w; P.atlas_scale[1] = atlas_h / tile_h;
@@ -46,9 +50,16 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
             uint32_t px;
             vr_aux a;
             bool w;
-            if (use_svo == 2) { LocalStack s; w = vr_trace_svo<true, 1>(P, x, y, &px, &a, s); }
-            else if (use_svo) { LocalStack s; w = vr_trace_svo<true, 0>(P, x, y, &px, &a, s); }
-            else w = vr_trace_dense<true>(P, x, y, &px, &a);
+            LocalStack s;
+            if (P.light_count > 1) {
+                if (use_svo == 2) w = vr_trace_svo<true, 1, true>(P, x, y, &px, &a, s);
+                else if (use_svo) w = vr_trace_svo<true, 0, true>(P, x, y, &px, &a, s);
+                else w = vr_trace_dense<true, true>(P, x, y, &px, &a);
+            } else {
+                if (use_svo == 2) w = vr_trace_svo<true, 1, false>(P, x, y, &px, &a, s);
+                else if (use_svo) w = vr_trace_svo<true, 0, false>(P, x, y, &px, &a, s);
+                else w = vr_trace_dense<true, false>(P, x, y, &px, &a);
+            }
             const size_t i = (size_t)x + (size_t)width * y;
             if (w) memcpy(rgba + 4 * i, &px, 4);
             if (aux) aux[i] = a;

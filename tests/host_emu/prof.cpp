@@ -59,8 +59,9 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
     P.local_rows = height; P.band_rows = 1; P.band_stride = 1; P.band_first = 0;
     P.ray_table = ray_table;
     P.dim[0] = P.dim[1] = P.dim[2] = n;
-    for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = 0.0f; P.light_pos[i] = lights[4 + i]; }
-    for (int i = 0; i < 4; i++) P.light_rgbi[i] = lights[i];
+    for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = 0.0f; P.light_pos[0][i] = lights[4 + i]; }
+    for (int i = 0; i < 4; i++) P.light_rgbi[0][i] = lights[i];
+    P.light_count = 1;
     P.trig[0] = sinf(cam_dir[0]); P.trig[1] = cosf(cam_dir[0]); P.trig[2] = sinf(cam_dir[1]); P.trig[3] = cosf(cam_dir[1]);
     P.atlas = atlas; P.atlas_dim[0] = atlas_w; P.atlas_dim[1] = atlas_h;
     P.atlas_scale[0] = atlas_w / tile_w; P.atlas_scale[1] = atlas_h / tile_h;
@@ -94,7 +95,7 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
                     if (!active[l]) continue;
                     memset(&vr_prof, 0, sizeof(vr_prof));
                     const bool was_shadow = q[l].r.shadow;
-                    const int rc = vr_svo_cell<false, 1>(P, q[l], &a);
+                    const int rc = vr_svo_round<false, 1, false>(P, q[l], &a);
                     if (!was_shadow && q[l].r.shadow) L.rays += 1;
                     const vr_prof_rec &p = vr_prof;
                     const int b = bucket(p.n);

@@ -110,7 +110,8 @@ def trig_of(cam_dir) -> np.ndarray:
 
 def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None,
             rows: tuple[int, int] | None = None, want_aux: bool = True, want_counters: bool = False,
-            count_svo: bool = False, threads: int = 0, max_distance: int | None = None, row_stride: int = 1):
+            count_svo: bool = False, threads: int = 0, max_distance: int | None = None, row_stride: int = 1,
+            shadow_lights: int = 1):
     """Runs the restated reference kernel (dense branch) on a scene.Scene.
     Returns (rgba [H,W,4] prefilled with (255,255,255,100), aux or None, counters dict or None)."""
     w, h = scene.width, scene.height
@@ -147,7 +148,7 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
         s.oct_root_index = root
     s.octdim = scene.n
     s.max_distance = scene.max_distance if max_distance is None else max_distance
-    s.shadow_lights = 1
+    s.shadow_lights = shadow_lights          # 1 = the reference (light 0 only); > 1 = the multi-light extension
     rgba = np.empty((h, w, 4), dtype=np.uint8)
     rgba[...] = (255, 255, 255, 100)
     aux = np.zeros((h, w), dtype=AUX_DTYPE) if want_aux else None

@@ -144,3 +144,40 @@ def test_axis_walk_terrain_256(pkg, oracle):
         diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
         assert not (diff[~tie] > 0).any() and (diff <= 1).all()
         assert ref_aux["steps_total"].max() > 300
+
+
+def _with_lights(pkg, scene, count):
+    """The scene with `count` shadow lights (extension beyond the reference: see vr_next_light / the oracle)."""
+    n = scene.n
+    extra = np.array([[0.3, 0.5, 0.7, 1.0, 0.2 * n, 0.7 * n, 0.9 * n, -1.0, -1.0, -1.5],
+                      [0.5, 0.2, 0.2, 1.0, 0.8 * n, 0.8 * n, 0.6 * n, -1.0, -1.0, -1.5]], np.float32)
+    lights = np.zeros((8, 10), np.float32)
+    lights[0] = scene.lights[0]
+    lights[1:count] = extra[: count - 1]
+    scene.lights = lights
+    return scene
+
+
+@pytest.mark.parametrize("name", ["features", "features-low", "features-mirror", "small"])
+@pytest.mark.parametrize("count", [2, 3])
+def test_multi_light_device_core(pkg, oracle, name, count):
+    """Multi-light extension (LIGHT_COUNT > 1): the device core equals the oracle's restatement of the same
+    extension on all pixels, dense and octree; and with count 1 both are the reference path (other tests)."""
+    scene = _with_lights(pkg, pkg.scene.make_scene(name), count)
+    table = oracle.make_ray_table(scene.width, scene.height)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, counters = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=count, want_counters=True)
+    one_rgba, _, _ = oracle.raycast(scene, table, octree=(desc, root))
+    lit = int(((ref_aux["flags"] & 1) != 0).sum())
+    assert counters["shadow_rays"] >= 1.5 * lit
+    assert lit == 0 or (one_rgba != ref_rgba).any()
+    bias = oracle_bias(oracle, scene, desc, root)
+    for use_svo in (0, 1):
+        rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=count)
+        assert_same_frame(ref_rgba, ref_aux, rgba, aux, f"{name} lights={count} svo={use_svo}")
+    rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=2, shadow_lights=count)
+    tie = (ref_aux["flags"] & 4) != 0
+    for f in ("hit", "face", "status", "hit_type", "steps_first", "steps_total"):
+        assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
+    diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
+    assert not (diff[~tie] > 0).any() and (diff <= 1).all()

@@ -426,3 +426,132 @@ def test_axis_walk_full_size_c3(pkg):
     ties = assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), "axis walk c3")
     assert ties > 0
     c.close()
+
+
+def _device_tree(pkg, volume, gpu_build):
+    """64-tree arrays (nodes as uint32[n, 4], leaf types) of a map, built on the device or on the host."""
+    import torch
+
+    c = pkg.CUDACaster()
+    assert c.init(0)
+    assert c.set_option("gpu_build", 1 if gpu_build else 0)
+    assert c.assign_map(volume), c.last_error()
+    nb, tb, levels, dim = c.native_tree_info()
+    nodes = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
+    types = torch.empty(tb, dtype=torch.uint8, device="cuda:0")
+    assert c.native_tree_copy(nodes.data_ptr(), types.data_ptr())
+    torch.cuda.synchronize()
+    st = c.stats()
+    out = nodes.cpu().numpy().view(np.uint32).reshape(-1, 4), types.cpu().numpy(), levels, dim, st
+    c.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["features", "terrain64", "terrain256-solid", "random32", "empty16", "full8", "dim4", "terrain128-mirrors"])
+def test_gpu_builder_equals_host_builder(pkg, kind):
+    """vr_build.cu (the on-device replacement of Octree::Generate) emits exactly the arrays of the host builder
+    vr_native_from_dense: same nodes in the same breadth-first order, same child pointers, same plane bits, same
+    leaf types -- including maps whose root is wider than the map (edge not a power of 4), the empty map (a root
+    without children), a full map and transparent voxel values (neither 5 nor 6)."""
+    S = pkg.scene
+    rng = np.random.default_rng(5)
+    if kind == "features":
+        vol = S.features_map(32)
+    elif kind == "terrain64":
+        vol = S.terrain_map(64, "shell")
+    elif kind == "terrain256-solid":
+        vol = S.terrain_map(256, "solid")
+    elif kind == "terrain128-mirrors":
+        vol = S.terrain_map(128, "shell", reflect_fraction=0.1)
+    elif kind == "random32":
+        vol = np.zeros((32, 32, 32), np.int8)
+        vol[rng.random(vol.shape) < 0.05] = 5
+        vol[rng.random(vol.shape) < 0.02] = 6
+        vol[rng.random(vol.shape) < 0.05] = 3
+        vol[rng.random(vol.shape) < 0.01] = -7
+    elif kind == "empty16":
+        vol = np.zeros((16, 16, 16), np.int8)
+    elif kind == "full8":
+        vol = np.full((8, 8, 8), 5, np.int8)
+    else:
+        vol = np.zeros((4, 4, 4), np.int8)
+        vol[1, 2, 3] = 6
+        vol[0, 0, 0] = 5
+    g_nodes, g_types, g_levels, g_dim, g_st = _device_tree(pkg, vol, True)
+    h_nodes, h_types, h_levels, h_dim, h_st = _device_tree(pkg, vol, False)
+    assert (g_levels, g_dim) == (h_levels, h_dim)
+    assert g_nodes.shape == h_nodes.shape and np.array_equal(g_nodes, h_nodes)
+    assert np.array_equal(g_types, h_types)
+    assert g_st.solid_voxels == h_st.solid_voxels == int(np.isin(vol, (5, 6)).sum())
+    assert g_st.build_ms > 0 and h_st.build_ms == 0
+
+
+@pytest.mark.gpu
+def test_gpu_builder_full_size_c3(pkg):
+    """1024^3 (1 GiB map): the device-built tree renders the frame the column-built (host) tree renders, and the
+    voxel count is the map's."""
+    import bench
+
+    S = pkg.scene
+    scene = bench.bench_scene("c3")
+    c = make_caster(pkg, scene, True, assign_octree=False, aux=False)       # assign_map -> device build
+    st = c.stats()
+    assert st.build_ms > 0 and st.solid_voxels == int(np.count_nonzero(scene.volume))
+    assert c.set_option("walk", 1) and c.compute()
+    got = c.draw().copy()
+    c.close()
+    lo, hi = S.terrain_columns(scene.n, "shell")
+    scene2 = S.Scene(scene.n, None, scene.width, scene.height, scene.cam_pos, scene.cam_dir, scene.lights,
+                     max_distance=scene.max_distance, columns=(lo, hi))
+    d = make_caster(pkg, scene2, True, assign_octree=False, aux=False)
+    assert d.stats().build_ms == 0 and d.stats().native_nodes == st.native_nodes
+    assert d.set_option("walk", 1) and d.compute()
+    assert np.array_equal(got, d.draw())
+    d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["features", "features-low", "small"])
+@pytest.mark.parametrize("count", [2, 3])
+def test_multi_light_extension(pkg, oracle, name, count):
+    """LIGHT_COUNT > 1 (extension; BASELINE configs[2] says "2 shadow lights", the reference kernel reads light 0
+    only): dense and octree kernels equal the oracle's restatement of the extension on all pixels, and the
+    per-axis walk equals it up to the tie tolerance.  LIGHT_COUNT absent or 1 is the reference path."""
+    from test_emu_parity import _with_lights
+
+    scene = _with_lights(pkg, pkg.scene.make_scene(name), count)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=count)
+    one_rgba, one_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    for use_octree in (False, True):
+        c = pkg.CUDACaster()
+        c.load_scene(scene, use_octree=use_octree, shadow_lights=count)
+        assert c.enable_aux(True) and c.compute(), c.last_error()
+        assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"{name} lights={count} octree={use_octree}")
+        if use_octree:
+            assert c.set_option("walk", 1) and c.compute()
+            assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"{name} lights={count} axis walk")
+            assert c.set_option("walk", 0)
+        # LIGHT_COUNT back to 1: the reference path again (the settings buffer is re-read every frame)
+        assert c.overwrite_setting("light_count", 1) and c.compute()
+        assert_same_frame(one_rgba, one_aux, c.draw(), c.read_aux(), f"{name} lights back to 1")
+        c.close()
+
+
+@pytest.mark.gpu
+def test_multi_light_terrain_256(pkg, oracle):
+    S = pkg.scene
+    n = 256
+    vol = S.terrain_map(n, "shell")
+    pos, direction = S.make_camera(n, S.heightfield(n), 10)
+    scene = S.Scene(n, vol, 960, 540, pos, direction, S.make_lights(n, 2), max_distance=3 * n)
+    ref_rgba, ref_aux, cnt = oracle.raycast(scene, shadow_lights=2, want_counters=True)
+    assert cnt["shadow_rays"] == 2 * int(((ref_aux["flags"] & 1) != 0).sum())
+    c = pkg.CUDACaster()
+    c.load_scene(scene, use_octree=True, assign_octree=False, shadow_lights=2)
+    assert c.enable_aux(True) and c.compute(), c.last_error()
+    assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), "terrain 256, 2 lights")
+    assert c.set_option("walk", 1) and c.compute()
+    assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), "terrain 256, 2 lights, axis walk")
+    c.close()

@@ -28,6 +28,7 @@ class VrStats(C.Structure):
         ("kernel_launches", C.c_uint64), ("frames", C.c_uint64), ("native_nodes", C.c_uint64),
         ("native_bytes", C.c_uint64), ("solid_voxels", C.c_uint64), ("levels", C.c_int32),
         ("used_svo", C.c_int32), ("bias", C.c_int32 * 3), ("device", C.c_int32), ("last_kernel_ms", C.c_float),
+        ("build_ms", C.c_float), ("build_masks_ms", C.c_float),
     ]
 
 
@@ -378,7 +379,7 @@ class CUDACaster:
         return s
 
     # -- convenience: the reference's init order (ref src/Application.cpp:27-88) -----------------
-    def load_scene(self, scene, use_octree: bool, assign_octree: bool = True, device: int = 0) -> None:
+    def load_scene(self, scene, use_octree: bool, assign_octree: bool = True, device: int = 0, shadow_lights: int = 1) -> None:
         def must(ok: bool, what: str) -> None:
             if not ok:
                 raise RuntimeError(f"{what} failed: {self.last_error()}")
@@ -387,6 +388,8 @@ class CUDACaster:
         must(self.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n), "add OCTDIM")
         must(self.add_to_settings_buffer("using_octree", "OCTENABLED", 0 if use_octree else 1), "add OCTENABLED")
         must(self.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance), "add MAX_DISTANCE")
+        if shadow_lights > 1:      # extension: the reference binds light_count but reads light 0 only
+            must(self.add_to_settings_buffer("light_count", "LIGHT_COUNT", shadow_lights), "add LIGHT_COUNT")
         if scene.volume is None:
             must(self.assign_columns(scene.columns[0], scene.columns[1]), "assign_columns")
         else:

@@ -1,0 +1,298 @@
+/*
+ * vr_build.cu -- 64-tree builder on the GPU (sm_100a), from the dense char map already resident in HBM.
+ *
+ * Replaces, for the octree the traversal kernel reads, the reference's CPU builder Octree::Generate /
+ * GenerationRecursion (src/map/Octree.cpp:13-43, 171-323: recursive, visits all N^3 voxels through
+ * get1DIndexedVoxel, O(N^3) on one core, capped at 100 000 descriptors) -- SURVEY 8(f) rank 1.  The host
+ * builder in vr_octree.cpp (vr_native_from_dense) stays as the definition of the layout; this builder emits
+ * exactly the same arrays (tests/test_gpu_parity.py::test_gpu_builder_*).
+ *
+ * Data flow (everything stays in HBM; one small D2H read of the level counts):
+ *   1. vr_brick_masks     N^3 bytes -> one 64-bit occupancy mask per 4^3 brick.  A lane reads 16 x 128 bits (4 bricks
+ *                         x 16 voxel rows), a warp 16 x 512 contiguous bytes, and assembles its 4 masks with
+ *                         byte-SIMD integer ops.  This is the HBM-bound kernel: 1 byte read per voxel.
+ *   2. vr_reduce_masks    level l+1 -> level l: one warp per parent, two ballots over its 64 children.
+ *   3. cub::DeviceScan    per level: exclusive sums of "mask != 0" (node index inside the level) and, on the leaf
+ *                         level, of popcount(mask) (index of the brick's first voxel type).
+ *   4. vr_emit_nodes      one thread per non-empty mask: vr_node {mask, child_base, plane bits} at its BFS slot.
+ *   5. vr_emit_types      one thread per leaf brick: the voxel values of its set bits.
+ * Masks are stored per level under a hierarchical key (6 bits per level: the child slot x | y<<2 | z<<4), so that
+ * ascending key order IS the breadth-first order of the host builder and the children of a node are the 64
+ * consecutive keys key*64 .. key*64+63.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "vr_build.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t solid4(uint32_t w) {
+    /* 4 voxels per word -> 4 bits: value 5 or 6 (kernel:575).  Byte-SIMD in plain integer ops:
+     *   t has a zero byte where the upper six bits of the voxel are 000001 (values 4..7),
+     *   u has bit 0 of a byte set where the two low bits differ (01 or 10: 5 or 6 among 4..7),
+     *   z = exact zero-byte test of t (no carries between bytes), bit 7 of every zero byte. */
+    const uint32_t t = (w & 0xFCFCFCFCu) ^ 0x04040404u;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+    const uint32_t u = (w ^ (w >> 1)) & 0x01010101u;
+    const uint32_t v = (z >> 7) & u;                               /* bits 0, 8, 16, 24 */
+    return ((v * 0x00204081u) >> 21) & 15u;                        /* gathered into one nibble (no colliding partial products) */
+}
+
+__device__ __forceinline__ uint32_t brick_key(uint32_t bx, uint32_t by, uint32_t bz, int digits) {
+    uint32_t key = 0;
+    for (int j = 0; j < digits; j++)
+        key |= (((bx >> (2 * j)) & 3u) | (((by >> (2 * j)) & 3u) << 2) | (((bz >> (2 * j)) & 3u) << 4)) << (6 * j);
+    return key;
+}
+
+/* 1. one lane = 4 bricks adjacent in x (16 voxels = one 128-bit load per voxel row, 16 rows), one warp = 128 bricks:
+ * every load instruction of a warp covers 512 contiguous bytes, 16 independent loads are in flight per lane, and
+ * the 4 masks of a lane are 32 contiguous bytes of the key-ordered output (4 consecutive x slots of one node).
+ * Requires dim >= 16; smaller maps take vr_brick_masks_small. */
+__global__ void __launch_bounds__(128)
+vr_brick_masks(const int8_t *__restrict__ map, int dim, int nb, int nquad, int digits, unsigned long long *__restrict__ leaf) {
+    const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = (unsigned long long)nb * nb * nquad;
+    if (gid >= total) return;
+    const unsigned qx = (unsigned)(gid % (unsigned)nquad);
+    const unsigned row = (unsigned)(gid / (unsigned)nquad);
+    const unsigned by = row % (unsigned)nb, bz = row / (unsigned)nb;
+    const uint4 *rows = reinterpret_cast<const uint4 *>(map);
+    const size_t qdim = (size_t)dim / 16;                      /* 128-bit words per voxel row */
+    uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int z = 0; z < 4; z++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint4 w = __ldg(rows + qx + qdim * ((size_t)(4 * by + y) + (size_t)dim * (size_t)(4 * bz + z)));
+            const int sh = 4 * y + 16 * (z & 1);
+            if (z < 2) {
+                lo[0] |= solid4(w.x) << sh; lo[1] |= solid4(w.y) << sh; lo[2] |= solid4(w.z) << sh; lo[3] |= solid4(w.w) << sh;
+            } else {
+                hi[0] |= solid4(w.x) << sh; hi[1] |= solid4(w.y) << sh; hi[2] |= solid4(w.z) << sh; hi[3] |= solid4(w.w) << sh;
+            }
+        }
+    /* bricks 4*qx .. 4*qx+3 differ in the lowest key digit only: keys k, k+1, k+2, k+3 */
+    uint4 *dst = reinterpret_cast<uint4 *>(leaf + brick_key(4 * qx, by, bz, digits));
+    dst[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
+    dst[1] = make_uint4(lo[2], hi[2], lo[3], hi[3]);
+}
+
+/* maps narrower than 16 voxels: one thread per brick */
+__global__ void vr_brick_masks_small(const int8_t *__restrict__ map, int dim, int nb, int digits, unsigned long long *__restrict__ leaf) {
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (unsigned)(nb * nb * nb)) return;
+    const unsigned bx = gid % (unsigned)nb, by = (gid / (unsigned)nb) % (unsigned)nb, bz = gid / (unsigned)(nb * nb);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(map);
+    const size_t wdim = (size_t)dim / 4;
+    unsigned long long m = 0ull;
+    for (int z = 0; z < 4; z++)
+        for (int y = 0; y < 4; y++)
+            m |= (unsigned long long)solid4(words[bx + wdim * ((size_t)(4 * by + y) + (size_t)dim * (size_t)(4 * bz + z))]) << (4 * y + 16 * z);
+    leaf[brick_key(bx, by, bz, digits)] = m;
+}
+
+/* 2. one warp per parent: bit ci = child ci has any voxel */
+__global__ void __launch_bounds__(128)
+vr_reduce_masks(const unsigned long long *__restrict__ child, unsigned long long *__restrict__ parent, unsigned nparent) {
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= nparent) return;
+    const unsigned long long *c = child + (size_t)warp * 64;
+    const unsigned lo = __ballot_sync(0xffffffffu, c[lane] != 0ull);
+    const unsigned hi = __ballot_sync(0xffffffffu, c[lane + 32] != 0ull);
+    if (lane == 0) parent[warp] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+struct NonZero {
+    __host__ __device__ uint32_t operator()(unsigned long long m) const { return m != 0ull ? 1u : 0u; }
+};
+struct PopCount {
+    __host__ __device__ uint32_t operator()(unsigned long long m) const {
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)__popcll(m);
+#else
+        return (uint32_t)__builtin_popcountll(m);
+#endif
+    }
+};
+
+/* totals[l] = non-empty masks of level l (l >= 1), totals[levels] = solid voxels */
+__global__ void vr_level_totals(const unsigned long long *masks, const uint32_t *prefix, const uint32_t *vox_prefix,
+                                const unsigned long long *level_off, int levels, uint32_t *totals) {
+    const int l = threadIdx.x;
+    if (l > levels) return;
+    if (l == 0) { totals[0] = 1u; return; }
+    if (l < levels) {
+        const unsigned long long last = level_off[l] + (1ull << (6 * l)) - 1;
+        totals[l] = prefix[last] + (masks[last] != 0ull ? 1u : 0u);
+    } else {
+        const unsigned long long first = level_off[levels - 1], last = first + (1ull << (6 * (levels - 1))) - 1;
+        totals[levels] = vox_prefix[last - first] + (uint32_t)__popcll(masks[last]);
+    }
+}
+
+/* 4. nodes of one level */
+__global__ void vr_emit_nodes(const unsigned long long *__restrict__ masks, const uint32_t *__restrict__ prefix,
+                              const uint32_t *__restrict__ child_prefix, unsigned nkeys, uint32_t level_start,
+                              uint32_t child_start, int leaf_level, vr_node *__restrict__ nodes) {
+    const unsigned key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    const unsigned long long m = masks[key];
+    if (m == 0ull && nkeys != 1u) return;                       /* the root exists even when the map is empty */
+    vr_node n;
+    n.mask_lo = (uint32_t)m;
+    n.mask_hi = (uint32_t)(m >> 32);
+    /* inner level: index of the first child node = start of the next level + non-empty masks before key*64;
+     * leaf level: index of the brick's first voxel type */
+    n.child_base = leaf_level ? child_prefix[key] : child_start + child_prefix[(size_t)key * 64];
+    n.aux = vr_node_planes(m);
+    reinterpret_cast<uint4 *>(nodes)[level_start + (nkeys == 1u ? 0u : prefix[key])] = *reinterpret_cast<uint4 *>(&n);
+}
+
+/* 5. voxel values of the set bits of every leaf brick, in ascending bit order */
+__global__ void vr_emit_types(const int8_t *__restrict__ map, int dim, int digits, const unsigned long long *__restrict__ leaf,
+                              const uint32_t *__restrict__ vox_prefix, unsigned nkeys, uint8_t *__restrict__ types) {
+    const unsigned key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    unsigned long long m = leaf[key];
+    if (m == 0ull) return;
+    unsigned bx = 0, by = 0, bz = 0;
+    for (int j = 0; j < digits; j++) {
+        const unsigned d = (key >> (6 * j)) & 63u;
+        bx |= (d & 3u) << (2 * j);
+        by |= ((d >> 2) & 3u) << (2 * j);
+        bz |= (d >> 4) << (2 * j);
+    }
+    uint32_t at = vox_prefix[key];
+    while (m) {
+        const int ci = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const size_t x = 4 * bx + (ci & 3), y = 4 * by + ((ci >> 2) & 3), z = 4 * bz + (ci >> 4);
+        types[at++] = (uint8_t)map[x + (size_t)dim * (y + (size_t)dim * z)];
+    }
+}
+
+#define VRB(call)                                  \
+    do {                                           \
+        const cudaError_t e__ = (call);            \
+        if (e__ != cudaSuccess) { cleanup(); return e__; } \
+    } while (0)
+
+}  // namespace
+
+cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stream, vr_device_tree *out,
+                                 unsigned long long *launches) {
+    if (!d_map || !out || dim < 4 || (dim & (dim - 1))) return cudaErrorInvalidValue;
+    int L = 1;
+    while ((1 << (2 * L)) < dim) L++;
+    if (L > VR_MAX_LEVELS) return cudaErrorInvalidValue;
+    const int nb = dim / 4, nquad = nb / 4, digits = L - 1;
+    unsigned long long off[VR_MAX_LEVELS + 1];
+    off[0] = 0;
+    for (int l = 0; l < L; l++) off[l + 1] = (off[l] + (1ull << (6 * l)) + 3ull) & ~3ull;   /* level l has 64^l keys; 32-byte aligned */
+    const unsigned long long nkeys_all = off[L], nleaf = 1ull << (6 * (L - 1));
+    if (nleaf > (1ull << 31)) return cudaErrorInvalidValue;
+
+    unsigned long long *masks = nullptr, *d_off = nullptr;
+    uint32_t *prefix = nullptr, *vox_prefix = nullptr, *d_totals = nullptr;
+    void *scan_tmp = nullptr;
+    vr_node *nodes = nullptr;
+    uint8_t *types = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(masks); cudaFree(d_off); cudaFree(prefix); cudaFree(vox_prefix); cudaFree(d_totals); cudaFree(scan_tmp);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (e2) cudaEventDestroy(e2);
+    };
+    auto fail_out = [&]() { cudaFree(nodes); cudaFree(types); };
+
+    VRB(cudaMalloc(&masks, nkeys_all * sizeof(unsigned long long)));
+    VRB(cudaMalloc(&prefix, nkeys_all * sizeof(uint32_t)));
+    VRB(cudaMalloc(&vox_prefix, nleaf * sizeof(uint32_t)));
+    VRB(cudaMalloc(&d_totals, (VR_MAX_LEVELS + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&d_off, (VR_MAX_LEVELS + 1) * sizeof(unsigned long long)));
+    VRB(cudaMemcpyAsync(d_off, off, (L + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    size_t tmp_bytes = 0;
+    {
+        auto it = thrust::make_transform_iterator((const unsigned long long *)masks, PopCount());
+        VRB(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, vox_prefix, (int)nleaf, stream));
+    }
+    VRB(cudaMalloc(&scan_tmp, tmp_bytes));
+    VRB(cudaEventCreate(&e0));
+    VRB(cudaEventCreate(&e1));
+    VRB(cudaEventCreate(&e2));
+
+    VRB(cudaEventRecord(e0, stream));
+    if ((1 << (2 * L)) != dim)           /* root wider than the map: the keys outside the map are never written */
+        VRB(cudaMemsetAsync(masks + off[L - 1], 0, nleaf * sizeof(unsigned long long), stream));
+    if (dim >= 16) {
+        const unsigned long long lanes = (unsigned long long)nb * nb * nquad;
+        vr_brick_masks<<<(unsigned)((lanes + 127) / 128), 128, 0, stream>>>(d_map, dim, nb, nquad, digits, masks + off[L - 1]);
+    } else {
+        vr_brick_masks_small<<<(nb * nb * nb + 63) / 64, 64, 0, stream>>>(d_map, dim, nb, digits, masks + off[L - 1]);
+    }
+    if (launches) ++*launches;
+    VRB(cudaEventRecord(e1, stream));
+    for (int l = L - 2; l >= 0; l--) {
+        const unsigned nparent = 1u << (6 * l);
+        vr_reduce_masks<<<(nparent * 32 + 127) / 128, 128, 0, stream>>>(masks + off[l + 1], masks + off[l], nparent);
+        if (launches) ++*launches;
+    }
+    for (int l = 1; l < L; l++) {
+        auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[l]), NonZero());
+        size_t need = tmp_bytes;
+        VRB(cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, prefix + off[l], (int)(1ull << (6 * l)), stream));
+    }
+    {
+        auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[L - 1]), PopCount());
+        size_t need = tmp_bytes;
+        VRB(cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, vox_prefix, (int)nleaf, stream));
+    }
+    vr_level_totals<<<1, 32, 0, stream>>>(masks, prefix, vox_prefix, d_off, L, d_totals);
+    if (launches) ++*launches;
+    uint32_t totals[VR_MAX_LEVELS + 1] = {0};
+    VRB(cudaMemcpyAsync(totals, d_totals, (L + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VRB(cudaStreamSynchronize(stream));                          /* the output sizes are needed on the host */
+
+    uint32_t start[VR_MAX_LEVELS + 1];
+    start[0] = 0;
+    for (int l = 0; l < L; l++) start[l + 1] = start[l] + totals[l];
+    const uint64_t n_nodes = start[L], solid = totals[L], n_types = solid ? solid : 1;
+    {
+        cudaError_t e = cudaMalloc(&nodes, n_nodes * sizeof(vr_node));
+        if (e == cudaSuccess) e = cudaMalloc(&types, n_types);
+        if (e == cudaSuccess && !solid) e = cudaMemsetAsync(types, 0, 1, stream);
+        if (e != cudaSuccess) { fail_out(); cleanup(); return e; }
+    }
+    for (int l = 0; l < L; l++) {
+        const unsigned nk = 1u << (6 * l);
+        const bool leaf = l == L - 1;
+        vr_emit_nodes<<<(nk + 255) / 256, 256, 0, stream>>>(masks + off[l], prefix + off[l], leaf ? vox_prefix : prefix + off[l + 1], nk,
+                                                            start[l], leaf ? 0u : start[l + 1], leaf ? 1 : 0, nodes);
+        if (launches) ++*launches;
+    }
+    if (solid) {
+        vr_emit_types<<<(unsigned)((nleaf + 255) / 256), 256, 0, stream>>>(d_map, dim, digits, masks + off[L - 1], vox_prefix,
+                                                                           (unsigned)nleaf, types);
+        if (launches) ++*launches;
+    }
+    cudaError_t e = cudaEventRecord(e2, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { fail_out(); cleanup(); return e; }
+    cudaEventElapsedTime(&out->masks_ms, e0, e1);
+    cudaEventElapsedTime(&out->total_ms, e0, e2);
+    out->nodes = nodes;
+    out->types = types;
+    out->n_nodes = n_nodes;
+    out->n_types = n_types;
+    out->solid_voxels = solid;
+    out->levels = L;
+    cleanup();
+    return cudaSuccess;
+}

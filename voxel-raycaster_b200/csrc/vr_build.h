@@ -1,0 +1,24 @@
+/* vr_build.h -- GPU 64-tree builder (internal; see vr_build.cu). */
+#ifndef VR_BUILD_H
+#define VR_BUILD_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vr_types.h"
+
+typedef struct vr_device_tree {
+    vr_node *nodes;            /* device, cudaMalloc'ed: ownership passes to the caller */
+    uint8_t *types;
+    uint64_t n_nodes, n_types, solid_voxels;
+    int levels;
+    float masks_ms;            /* CUDA-event time of the HBM-bound brick-mask kernel (reads the N^3 map once) */
+    float total_ms;            /* whole build on the stream, including the host read of the level counts */
+} vr_device_tree;
+
+/* Builds the 64-tree of the dense map d_map[x + dim*(y + dim*z)] (device pointer; dim a power of two >= 4; solid =
+ * value 5 or 6) on `stream`.  Emits exactly the arrays vr_native_from_dense (vr_octree.cpp) produces. */
+cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stream, vr_device_tree *out,
+                                 unsigned long long *launches);
+
+#endif

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/vr_caster.h"
+#include "vr_build.h"
 #include "vr_kernels.h"
 #include "vr_octree.h"
 #include "vr_types.h"
@@ -59,6 +60,8 @@ struct vr_ctx {
     int levels = 0, tree_dim = 0;
     uint64_t n_nodes = 0, n_leaf_types = 0, solid_voxels = 0;
     bool tree_valid = false, tree_from_map = false;
+    bool gpu_build = true;             /* assign_map builds the 64-tree with vr_build.cu (option "gpu_build") */
+    float build_ms = 0.f, build_masks_ms = 0.f;
 
     /* retained host pointers (CL_MEM_USE_HOST_PTR semantics) */
     const float *cam_dir = nullptr, *cam_pos = nullptr;
@@ -243,8 +246,14 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     }
     for (int i = 0; i < 3; i++) P.bias[i] = (float)c->bias[i];
 
-    for (int i = 0; i < 4; i++) P.light_rgbi[i] = c->lights[i];
-    for (int i = 0; i < 3; i++) P.light_pos[i] = c->lights[4 + i];
+    /* the reference binds light_count but reads slot 0 only (host:193, kernel:660-670): LIGHT_COUNT defaults to 1 */
+    P.light_count = 1;
+    if (setting_value(c, "LIGHT_COUNT", &v) && v > 1)
+        P.light_count = (int)(v < c->light_count ? v : c->light_count) < VR_MAX_LIGHTS ? (int)(v < c->light_count ? v : c->light_count) : VR_MAX_LIGHTS;
+    for (int l = 0; l < P.light_count; l++) {
+        for (int i = 0; i < 4; i++) P.light_rgbi[l][i] = c->lights[10 * l + i];
+        for (int i = 0; i < 3; i++) P.light_pos[l][i] = c->lights[10 * l + 4 + i];
+    }
     P.atlas_tex = (unsigned long long)c->atlas_tex;
     P.atlas = c->d_atlas;
     P.atlas_dim[0] = c->atlas_dim[0];
@@ -459,7 +468,24 @@ int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
     VR_CUDA(c, cudaMemcpy(c->d_map, voxels, bytes, cudaMemcpyHostToDevice));
     c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
     /* traversal structure for the octree branch, built from the same voxels (types included) */
-    if (nx == ny && ny == nz && (nx & (nx - 1)) == 0) {
+    if (nx == ny && ny == nz && (nx & (nx - 1)) == 0 && c->gpu_build && nx >= 4) {
+        /* on the device, from the copy just uploaded (vr_build.cu) */
+        vr_device_tree dt;
+        memset(&dt, 0, sizeof(dt));
+        VR_CUDA(c, vr_build_tree_device(c->d_map, nx, c->stream, &dt, &c->launches));
+        free_tree(c);
+        c->d_nodes = dt.nodes;
+        c->d_leaf_types = dt.types;
+        c->levels = dt.levels;
+        c->tree_dim = nx;
+        c->n_nodes = dt.n_nodes;
+        c->n_leaf_types = dt.n_types;
+        c->solid_voxels = dt.solid_voxels;
+        c->tree_valid = true;
+        c->tree_from_map = true;
+        c->build_ms = dt.total_ms;
+        c->build_masks_ms = dt.masks_ms;
+    } else if (nx == ny && ny == nz && (nx & (nx - 1)) == 0) {
         vr_native_tree t;
         if (!vr_native_from_dense(voxels, nx, t)) return fail(c, "assign_map: 64-tree build failed");
         if (!upload_tree(c, t, true)) return 0;
@@ -715,6 +741,7 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     else if (n == "refill_min") c->opt.refill_min = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
     else if (n == "walk") c->opt.walk = value == 1 ? 1 : 0;
+    else if (n == "gpu_build") c->gpu_build = value != 0;        /* 0: assign_map builds the 64-tree on the host */
     else if (n == "l2_persist") {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
         if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");
@@ -934,6 +961,8 @@ int vr_get_stats(vr_ctx *c, vr_stats *out) {
     for (int i = 0; i < 3; i++) out->bias[i] = c->bias[i];
     out->device = c->device;
     out->last_kernel_ms = c->last_kernel_ms;
+    out->build_ms = c->build_ms;
+    out->build_masks_ms = c->build_masks_ms;
     return 1;
 }
 

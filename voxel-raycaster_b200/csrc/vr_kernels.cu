@@ -48,7 +48,9 @@ struct SmemStack {
     __device__ __forceinline__ uint32_t get(int level) const { return base[level * kThreads]; }
 };
 
-template <bool AUX>
+/* MULTI = the multi-light extension (LIGHT_COUNT > 1): a separate instantiation, so that the reference-parity
+ * kernels do not carry its per-ray state */
+template <bool AUX, bool MULTI>
 __global__ void __launch_bounds__(kThreads)
 vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
     int lx, ly;
@@ -61,13 +63,13 @@ vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
     const size_t local = (size_t)x + (size_t)P.width * (size_t)row;
     uint32_t rgba;
     vr_aux a;
-    const bool write = vr_trace_dense<AUX>(P, x, y, &rgba, &a);
+    const bool write = vr_trace_dense<AUX, MULTI>(P, x, y, &rgba, &a);
     if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
 }
 
-template <bool AUX, int WALK>
+template <bool AUX, int WALK, bool MULTI>
 __global__ void __launch_bounds__(kThreads, VR_SVO_MIN_CTAS)
 vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
@@ -82,7 +84,7 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     SmemStack stk{stack + threadIdx.x};
     uint32_t rgba;
     vr_aux a;
-    const bool write = vr_trace_svo<AUX, WALK>(P, x, y, &rgba, &a, stk);
+    const bool write = vr_trace_svo<AUX, WALK, MULTI>(P, x, y, &rgba, &a, stk);
     if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
@@ -141,7 +143,7 @@ vr_svo_persistent_kernel(const __grid_constant__ vr_frame_params P, unsigned int
             if (idle == 0xffffffffu && !more && !__any_sync(0xffffffffu, active)) break;
         }
         if (active) {
-            const int rc = vr_svo_cell<AUX, 0>(P, q, &a);
+            const int rc = vr_svo_round<AUX, 0, false>(P, q, &a);
             if (rc != VR_CELL_CONTINUE) {
                 if (rc != VR_CELL_NO_WRITE) reinterpret_cast<uint32_t *>(P.image)[local] = vr_svo_finish<AUX>(q, rc, &a);
                 if (AUX) {
@@ -166,22 +168,27 @@ cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_au
     if (P.width <= 0 || P.local_rows <= 0) return cudaSuccess;
     const dim3 grid((P.width + kTileW - 1) / kTileW, (P.local_rows + kTileH - 1) / kTileH);
     const dim3 block(kThreads);
-    if (use_svo && opt && opt->persistent) {
+    const bool multi = P.light_count > 1;
+    const bool aux = with_aux != 0;
+    if (use_svo && opt && opt->persistent && !multi) {            /* (the persistent variant has no multi-light build) */
         cudaError_t e = cudaMemsetAsync(opt->counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
         unsigned ctas = (unsigned)(opt->num_sms * opt->ctas_per_sm);
         if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
-        if (with_aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
+        if (aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
         else vr_svo_persistent_kernel<false><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
-    } else if (use_svo && opt && opt->walk == 1) {
-        if (with_aux) vr_svo_kernel<true, 1><<<grid, block, 0, stream>>>(P);
-        else vr_svo_kernel<false, 1><<<grid, block, 0, stream>>>(P);
     } else if (use_svo) {
-        if (with_aux) vr_svo_kernel<true, 0><<<grid, block, 0, stream>>>(P);
-        else vr_svo_kernel<false, 0><<<grid, block, 0, stream>>>(P);
+        const int walk = (opt && opt->walk == 1) ? 1 : 0;
+        void (*k)(vr_frame_params) =
+            walk ? (multi ? (aux ? vr_svo_kernel<true, 1, true> : vr_svo_kernel<false, 1, true>)
+                          : (aux ? vr_svo_kernel<true, 1, false> : vr_svo_kernel<false, 1, false>))
+                 : (multi ? (aux ? vr_svo_kernel<true, 0, true> : vr_svo_kernel<false, 0, true>)
+                          : (aux ? vr_svo_kernel<true, 0, false> : vr_svo_kernel<false, 0, false>));
+        k<<<grid, block, 0, stream>>>(P);
     } else {
-        if (with_aux) vr_dense_kernel<true><<<grid, block, 0, stream>>>(P);
-        else vr_dense_kernel<false><<<grid, block, 0, stream>>>(P);
+        void (*k)(vr_frame_params) = multi ? (aux ? vr_dense_kernel<true, true> : vr_dense_kernel<false, true>)
+                                           : (aux ? vr_dense_kernel<true, false> : vr_dense_kernel<false, false>);
+        k<<<grid, block, 0, stream>>>(P);
     }
     if (launches) ++*launches;
     return cudaGetLastError();

@@ -95,6 +95,11 @@ struct RayState {
     vf4 color;           /* color_accumulator */
     float fog_distance;
     bool shadow;         /* shadow_ray */
+    /* multi-light extension only (dead in the single-light kernels): the hit the shadow rays start from */
+    int light;           /* light whose shadow ray is being traced */
+    vf3 hit_point;
+    vi3 hit_voxel, hit_empty, hit_normal;
+    float alpha_before;  /* colour alpha before the current light was added */
 };
 
 /* kernel:276-337 + 353.  Returns false when the pixel is skipped (kernel:293). */
@@ -135,6 +140,8 @@ VR_HD bool vr_ray_setup(const vr_frame_params &P, int x, int y, RayState &r) {
     r.color = {0.0f, 0.0f, 0.0f, 0.0f};
     r.fog_distance = 0.0f;
     r.shadow = false;
+    r.light = 0;
+    r.alpha_before = 0.0f;
     return true;
 }
 
@@ -179,7 +186,7 @@ VR_HD vf3 vr_atlas_fetch(const vr_frame_params &P, float u, float v, int tile_x,
 }
 
 /* kernel:78-99 */
-VR_HD vf4 vr_view_light(vf3 in_color, vf3 light, const float *rgbi, vf3 view, vi3 mask) {
+VR_HD vf4 vr_view_light(vf3 in_color, float in_w, vf3 light, const float *rgbi, vf3 view, vi3 mask) {
     if (light.x == 0.0f && light.y == 0.0f && light.z == 0.0f) return {0.0f, 0.0f, 0.0f, 0.0f};
     float d = VR_MUL(vr_length(light), 0.01f);
     d = VR_MUL(d, d);
@@ -195,7 +202,7 @@ VR_HD vf4 vr_view_light(vf3 in_color, vf3 light, const float *rgbi, vf3 view, vi
     o.x = VR_ADD(in_color.x, VR_ADD(VR_MUL(diffuse, rgbi[0]), VR_DIV(VR_MUL(specular, rgbi[0]), d)));
     o.y = VR_ADD(in_color.y, VR_ADD(VR_MUL(diffuse, rgbi[1]), VR_DIV(VR_MUL(specular, rgbi[1]), d)));
     o.z = VR_ADD(in_color.z, VR_ADD(VR_MUL(diffuse, rgbi[2]), VR_DIV(VR_MUL(specular, rgbi[2]), d)));
-    o.w = VR_ADD(0.0f, VR_ADD(VR_MUL(diffuse, rgbi[3]), VR_DIV(VR_MUL(specular, rgbi[3]), d)));
+    o.w = VR_ADD(in_w, VR_ADD(VR_MUL(diffuse, rgbi[3]), VR_DIV(VR_MUL(specular, rgbi[3]), d)));
     return o;
 }
 
@@ -217,7 +224,32 @@ VR_HD void vr_restart_dda(RayState &r, vf3 hit_pos, vi3 new_step) {
 
 /* kernel:575-711, entered when the voxel just stepped into holds 5 or 6.
  * Returns -1 to continue the loop (ray was redirected), or the terminal VR_ST_* code. */
-template <bool AUX>
+/* EXTENSION beyond the reference (setting LIGHT_COUNT > 1): the lights are taken one after the other from
+ * the same hit point.  Light i adds its view_light term to the colour accumulated so far and casts its own shadow
+ * ray with the reference's budget (max_distance = steps at the hit + distance to that light); a blocked light leaves
+ * 0.1 instead of its term in alpha.  Restated in the oracle (vr_oracle.cpp: next_light).  Returns false when the pixel
+ * is skipped because the direction to the light has a zero component (kernel:671). */
+VR_HD bool vr_more_lights(const vr_frame_params &P, const RayState &r) { return r.shadow && r.light + 1 < P.light_count; }
+
+VR_HD bool vr_next_light(const vr_frame_params &P, RayState &r) {
+    r.light++;
+    const vf3 L = {P.light_pos[r.light][0], P.light_pos[r.light][1], P.light_pos[r.light][2]};
+    const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
+    r.alpha_before = r.color.w;
+    r.color = vr_view_light({r.color.x, r.color.y, r.color.z}, r.color.w, vr_sub3(r.hit_point, L), P.light_rgbi[r.light],
+                            vr_sub3(r.hit_point, cam), r.hit_normal);
+    const int hit_steps = (int)r.fog_distance;
+    r.dist = hit_steps;
+    r.max_distance = (int)VR_ADD((float)hit_steps, vr_length(vr_sub3(vr_i2f3(r.hit_voxel), L)));
+    r.ray_dir = vr_normalize(vr_sub3(L, r.hit_point));
+    if (vr_any_zero(r.ray_dir)) return false;
+    r.voxel = r.hit_empty;
+    r.fm = 0;                                                    /* vr_restart_dda steps back by step * fm: already done */
+    vr_restart_dda(r, r.hit_point, {vr_sign(r.ray_dir.x), vr_sign(r.ray_dir.y), vr_sign(r.ray_dir.z)});
+    return true;
+}
+
+template <bool AUX, bool MULTI>
 VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr_aux *a, bool &first_hit_done) {
     if (AUX && !first_hit_done) {
         first_hit_done = true;
@@ -261,7 +293,7 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
     if (r.ray_dir.z < 0.0f) tv = VR_ADD(-tv, 1.0f);
 
     const vf3 hit_pos = vr_add3(vr_i2f3(r.voxel), fp);
-    const vf3 L = {P.light_pos[0], P.light_pos[1], P.light_pos[2]};
+    const vf3 L = {P.light_pos[0][0], P.light_pos[0][1], P.light_pos[0][2]};
 
     if (voxel_data == 5 && !r.shadow) {                                  /* kernel:649 */
         r.shadow = true;
@@ -273,7 +305,13 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
         r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_DIV(tex.z, 2.0f));
         const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
         const vi3 nrm = {(r.fm & 1) * r.step.x, ((r.fm >> 1) & 1) * r.step.y, ((r.fm >> 2) & 1) * r.step.z};
-        r.color = vr_view_light(r.voxel_color, vr_sub3(hit_pos, L), P.light_rgbi, vr_sub3(hit_pos, cam), nrm);
+        if (MULTI) {
+            r.hit_point = hit_pos;
+            r.hit_voxel = r.voxel;
+            r.hit_normal = nrm;
+            r.hit_empty = {r.voxel.x - nrm.x, r.voxel.y - nrm.y, r.voxel.z - nrm.z};
+        }
+        r.color = vr_view_light(r.voxel_color, 0.0f, vr_sub3(hit_pos, L), P.light_rgbi[0], vr_sub3(hit_pos, cam), nrm);
         r.fog_distance = (float)r.dist;
         r.max_distance = (int)VR_ADD((float)r.dist, vr_length(vr_sub3(vr_i2f3(r.voxel), L)));   /* kernel:667 */
         r.ray_dir = vr_normalize(vr_sub3(L, hit_pos));
@@ -294,7 +332,8 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
         r.bounce += 1;
         return -1;
     }
-    r.color.w = 0.1f;                                                    /* kernel:708 */
+    r.color.w = MULTI ? VR_ADD(r.alpha_before, 0.1f) : 0.1f;             /* kernel:708 */
+    if (MULTI && vr_more_lights(P, r)) return vr_next_light(P, r) ? -1 : VR_ST_SKIP_REDIRECT;
     return VR_ST_SHADOW_HIT;
 }
 
@@ -318,7 +357,7 @@ VR_HD void vr_aux_init(vr_aux *a, const vr_frame_params &P) {
  * Dense variant: kernel:357 loop with the `else` branch (kernel:555-570).
  * Returns true if the pixel must be written (packed colour in *rgba_out).
  * ------------------------------------------------------------------------------------------- */
-template <bool AUX>
+template <bool AUX, bool MULTI>
 VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a) {
     RayState r;
     if (AUX) vr_aux_init(a, P);
@@ -329,10 +368,24 @@ VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba
     const int X = P.dim[0], Y = P.dim[1], Z = P.dim[2];
     bool first_hit_done = false;
     int status = VR_ST_MAXDIST;
-    while (r.dist < r.max_distance && r.bounce < 2) {
+    for (;;) {
+        if (!(r.dist < r.max_distance && r.bounce < 2)) {
+            /* multi-light extension: this light is not blocked, on to the next one */
+            if (MULTI && r.bounce < 2 && vr_more_lights(P, r)) {
+                if (!vr_next_light(P, r)) { status = VR_ST_SKIP_REDIRECT; break; }
+                r.dist++;
+                continue;
+            }
+            break;
+        }
         vr_dda_step(r);
         if (AUX && (r.fm & (r.fm - 1))) a->flags |= VR_FL_TIE;
         if (r.voxel.x >= X || r.voxel.y >= Y || r.voxel.z >= Z || r.voxel.x < 0 || r.voxel.y < 0 || r.voxel.z < 0) {
+            if (MULTI && vr_more_lights(P, r)) {
+                if (!vr_next_light(P, r)) { status = VR_ST_SKIP_REDIRECT; break; }
+                r.dist++;
+                continue;
+            }
             vr_out_of_bounds(r);
             status = VR_ST_OOB;
             break;
@@ -340,14 +393,14 @@ VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba
         const int voxel_data =
             (int)P.map[(size_t)r.voxel.x + (size_t)X * ((size_t)r.voxel.y + (size_t)Z * (size_t)r.voxel.z)];
         if (voxel_data == 5 || voxel_data == 6) {
-            const int st = vr_hit_block<AUX>(P, r, voxel_data, a, first_hit_done);
-            if (st == VR_ST_SKIP_REDIRECT) {
-                if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
-                return false;
-            }
+            const int st = vr_hit_block<AUX, MULTI>(P, r, voxel_data, a, first_hit_done);
             if (st >= 0) { status = st; break; }
         }
         r.dist++;
+    }
+    if (status == VR_ST_SKIP_REDIRECT) {
+        if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
+        return false;
     }
     if (status == VR_ST_MAXDIST && r.bounce >= 2) status = VR_ST_BOUNCES;
     if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
@@ -694,7 +747,7 @@ struct vr_svo_ray {
     Stack stk;
 };
 
-enum { VR_CELL_CONTINUE = -1, VR_CELL_NO_WRITE = -2 };   /* otherwise: terminal VR_ST_* status */
+enum { VR_CELL_CONTINUE = -1, VR_CELL_NO_WRITE = -2, VR_CELL_NEXT_LIGHT = -3 };   /* otherwise: terminal VR_ST_* status */
 
 /* kernel:276-354 for one pixel.  Returns false when the pixel is skipped (kernel:293). */
 template <bool AUX, class Stack>
@@ -723,7 +776,7 @@ VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack
 /* One iteration of the cell loop: walk the cached cell, then look the new voxel up.
  * Returns VR_CELL_CONTINUE, VR_CELL_NO_WRITE (pixel skipped after a redirect, kernel:671/694) or the
  * terminal status. */
-template <bool AUX, int WALK, class Stack>
+template <bool AUX, int WALK, bool MULTI, class Stack>
 VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
     RayState &r = q.r;
     if (!(r.dist < r.max_distance && r.bounce < 2)) return r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST;
@@ -799,6 +852,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
     /* ---- (2) the last step left the cell: bounds test, octree lookup, hit handling */
     if (!known) {
         if ((unsigned)r.voxel.x >= (unsigned)N || (unsigned)r.voxel.y >= (unsigned)N || (unsigned)r.voxel.z >= (unsigned)N) {
+            if (MULTI && vr_more_lights(P, r)) return VR_CELL_NEXT_LIGHT;   /* left the map unblocked: next light */
             vr_out_of_bounds(r);
             return VR_ST_OOB;
         }
@@ -856,7 +910,7 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
             VR_PROF(replay, 1);
         }
         VR_PROF(hit, 1);
-        const int st = vr_hit_block<AUX>(P, r, voxel_data, a, q.first_hit_done);
+        const int st = vr_hit_block<AUX, MULTI>(P, r, voxel_data, a, q.first_hit_done);
         if (st == VR_ST_SKIP_REDIRECT) {
             if (AUX) { a->status = (uint8_t)st; a->steps_total = (uint32_t)r.dist; }
             return VR_CELL_NO_WRITE;
@@ -880,14 +934,34 @@ VR_HD uint32_t vr_svo_finish(vr_svo_ray<Stack> &q, int status, vr_aux *a) {
     return vr_epilogue(q.r);
 }
 
+/* One vr_svo_cell plus the multi-light extension's turn-over: a shadow ray that ends unblocked (max_distance or
+ * out of the map) hands over to the next light, restarting from the stored hit. */
+template <bool AUX, int WALK, bool MULTI, class Stack>
+VR_HD int vr_svo_round(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
+    int rc = vr_svo_cell<AUX, WALK, MULTI>(P, q, a);
+    if (MULTI && (rc == VR_CELL_NEXT_LIGHT || (rc == VR_ST_MAXDIST && q.r.bounce < 2 && vr_more_lights(P, q.r)))) {
+        if (!vr_next_light(P, q.r)) {
+            if (AUX) { a->status = (uint8_t)VR_ST_SKIP_REDIRECT; a->steps_total = (uint32_t)q.r.dist; }
+            return VR_CELL_NO_WRITE;
+        }
+        q.r.dist++;
+        q.finite = vr_ray_finite(q.r);
+        q.brick = false;
+        q.ce = {1, 1, 1};
+        q.co = q.r.voxel;
+        rc = VR_CELL_CONTINUE;
+    }
+    return rc;
+}
+
 /* whole pixel, static pixel->thread mapping */
-template <bool AUX, int WALK, class Stack>
+template <bool AUX, int WALK, bool MULTI, class Stack>
 VR_HD bool vr_trace_svo(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
     vr_svo_ray<Stack> q;
     q.stk = stk;
     if (!vr_svo_begin<AUX>(P, x, y, q, a)) return false;
     int rc;
-    while ((rc = vr_svo_cell<AUX, WALK>(P, q, a)) == VR_CELL_CONTINUE) {}
+    while ((rc = vr_svo_round<AUX, WALK, MULTI>(P, q, a)) == VR_CELL_CONTINUE) {}
     if (rc == VR_CELL_NO_WRITE) return false;
     *rgba_out = vr_svo_finish<AUX>(q, rc, a);
     return true;

@@ -62,6 +62,7 @@ enum {
 };
 enum { VR_FL_LIT = 1, VR_FL_REFLECTED = 2, VR_FL_TIE = 4, VR_FL_ATLAS_CLAMP = 8, VR_FL_FRAC0 = 16 };
 
+#define VR_MAX_LIGHTS 8          /* LightController's fixed slot count (ref src/LightController.cpp:3-11)  */
 #define VR_MAX_LEVELS 8          /* 64-tree levels: dimension up to 4^8 = 65536 */
 
 typedef struct vr_frame_params {
@@ -82,9 +83,11 @@ typedef struct vr_frame_params {
     float cam_pos[3];
     float trig[4];
     float bias[3];                 /* get_oct_vox start bias (kernel:353), host evaluated     */
-    /* light 0 (arg 6): rgbi + position                                                       */
-    float light_rgbi[4];
-    float light_pos[3];
+    /* lights (arg 6): rgbi + position per slot.  The reference reads slot 0 only (kernel:660-670);
+     * light_count > 1 (setting LIGHT_COUNT) enables the multi-light extension, see vr_next_light      */
+    float light_rgbi[VR_MAX_LIGHTS][4];
+    float light_pos[VR_MAX_LIGHTS][3];
+    int32_t light_count;
     /* atlas (args 9-11) */
     unsigned long long atlas_tex;  /* cudaTextureObject_t                                     */
     const uint8_t *atlas;          /* same texels, linear RGBA8 (host emulation + fallback)   */
