@@ -212,6 +212,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     must(c.assign_lights(lights), "assign_lights")
     must(c.create_texture_atlas(S.synthetic_atlas(), (16, 16)), "atlas")
     must(c.validate(), "validate")
+    must(c.set_option("walk", args.walk), "walk")
     frames = torch.empty((len(mine), H, W, 4), dtype=torch.uint8, device=dev)
     # rays per batch from one untimed aux pass per view
     must(c.enable_aux(True), "aux")
@@ -269,6 +270,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
             "gpu_launches": int(launches),
             "config": {"workload": "c5: 64 random cameras x 1920x1080, 1024^3 shell terrain SVO, primary + 1 shadow light (BASELINE configs[4], not the headline)",
                        "parallelism": f"views{world}: view v on rank v % {world}", "views": views, "rays_per_batch": rays,
+                       "walk": "per-axis" if args.walk == 1 else "merged",
                        "ms_per_view": ms / (views / world) if world else None},
             "roofline": None, "cpu_baseline": None,
             "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
