@@ -307,6 +307,8 @@ def main() -> None:
         run_reference(args)
         return
 
+    # stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO prints to stdout) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
