@@ -299,6 +299,8 @@ def main() -> None:
     ap.add_argument("--ctas-per-sm", type=int, default=3)
     ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
     ap.add_argument("--walk", type=int, default=1, help="in-cell walk of the octree kernel: 1 = per-axis (default here; exact except the step count of exact-tie rays), 0 = merged (bit-identical on every pixel; the library default)")
+    ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
+                    help="N > 1 end-to-end leg: 'shared' = every rank copies its bands into a shared pinned host frame; 'root' = rank 0 copies the gathered frame")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
@@ -473,6 +475,8 @@ def main() -> None:
     # call, the frame is copied back to pinned host memory inside the timed region (double buffered at N = 1)
     barrier()
     t0 = time.perf_counter()
+    t_done = None
+    e2e_how = "frame_begin/frame_end, double buffered D2H on a second stream" if world == 1 else "rank 0 copies every gathered frame D2H"
     if world == 1:
         c.set_bands(BAND_ROWS, 1, 0)
         must(c.frame_begin(), "frame_begin")
@@ -481,6 +485,24 @@ def main() -> None:
             host = c.frame_end()
         host = c.frame_end()
         checksum = int(host[::64, ::64].astype(np.int64).sum())
+    elif args.host_frame == "shared":
+        # N > 1, HOST result: the frame lives in POSIX shared memory, page-locked by every rank; each rank copies its
+        # own bands device -> host into frame order over its own PCIe link (no gather on the device in this path)
+        shared = pkg.tiles.SharedHostFrame(layout, dist, rank, count=2)
+        shared.register(c)
+        pipe.set_shared_host(shared, c)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pipe.step()
+        pipe.drain()
+        torch.cuda.synchronize()
+        barrier()
+        t_done = time.perf_counter()
+        e2e_how = "every rank copies its bands D2H into a shared page-locked host frame (POSIX shm): all PCIe links in parallel, no device-side gather"
+        checksum = int(shared.frame((args.steps - 1) % 2)[::64, ::64].astype(np.int64).sum()) if rank == 0 else 0
+        pipe.set_shared_host(None, None)
+        shared.close()
     else:
         pipe.host_frame = host_frame                  # rank 0 copies every gathered frame to pinned host memory
         for i in range(args.steps):
@@ -489,7 +511,7 @@ def main() -> None:
         torch.cuda.synchronize()
         checksum = int(host_frame[::64, ::64].sum().item()) if rank == 0 else 0
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_s = torch.tensor([(t_done if t_done is not None else time.perf_counter()) - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
@@ -540,7 +562,7 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 5 * 4 + 10 * 4 + 64 * 8,
-                    "d2h_bytes_per_step": W * H * 4},
+                    "d2h_bytes_per_step": W * H * 4, "how": e2e_how},
             "clocks": clocks.summary(),
         }
         print(json.dumps(out))

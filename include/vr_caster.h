@@ -177,6 +177,11 @@ int vr_ipc_get_handle(vr_ctx *ctx, void *device_ptr, void *handle64);
 int vr_ipc_open_handle(vr_ctx *ctx, const void *handle64, void **device_ptr);
 int vr_ipc_close_handle(vr_ctx *ctx, void *device_ptr);
 int vr_push_bands(vr_ctx *ctx, const void *slab, void *frame, void *cuda_stream);
+/* Page-locks host memory the caller owns (e.g. a frame in a POSIX shared-memory segment mapped by every rank) so
+ * that vr_push_bands can take it as `frame`: each rank then copies its own bands device->host over its own PCIe
+ * link, straight into frame order -- the end-to-end path with a HOST result needs no gather on the device. */
+int vr_host_register(vr_ctx *ctx, void *host_ptr, size_t bytes);
+int vr_host_unregister(vr_ctx *ctx, void *host_ptr);
 
 /* Octree::Load (declared, never defined in the reference: include/map/Octree.h:38) and its counterpart: the
  * traversal octree of this context to / from a file ("VR64" header + node array + leaf types). */

@@ -555,3 +555,32 @@ def test_multi_light_terrain_256(pkg, oracle):
     assert c.set_option("walk", 1) and c.compute()
     assert_same_except_ties(ref_rgba, ref_aux, c.draw(), c.read_aux(), "terrain 256, 2 lights, axis walk")
     c.close()
+
+
+@pytest.mark.gpu
+def test_push_bands_into_registered_host_frame(pkg, oracle):
+    """vr_host_register + vr_push_bands with a host target: two band sets (as two ranks would hold them) copied
+    device -> host straight into frame order reproduce the single-context frame."""
+    import torch
+
+    tiles = pkg.tiles
+    scene = pkg.scene.make_scene("features")
+    full = make_caster(pkg, scene, True, aux=False)
+    assert full.compute()
+    want = full.draw().copy()
+    full.close()
+    H, W = scene.height, scene.width
+    lay = tiles.BandLayout(H, W, 8, 2)
+    shared = tiles.SharedHostFrame(lay, None, 0, count=1)
+    casters = [make_caster(pkg, scene, True, aux=False) for _ in range(2)]
+    shared.register(casters[0])
+    for rank, c in enumerate(casters):
+        assert c.set_bands(8, 2, rank)
+        slab = torch.zeros((lay.slab_rows, W, 4), dtype=torch.uint8, device="cuda:0")
+        assert c.compute_into(slab.data_ptr()), c.last_error()
+        assert c.push_bands(slab.data_ptr(), shared.ptr(0)), c.last_error()
+        torch.cuda.synchronize()
+    assert np.array_equal(shared.frame(0), want)
+    shared.close()                       # unregisters through casters[0]
+    for c in casters:
+        c.close()

@@ -91,6 +91,8 @@ SYMBOLS = {
     "vr_ipc_open_handle": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "vr_ipc_close_handle": (_i, [_vp, _vp]),
     "vr_push_bands": (_i, [_vp, _vp, _vp, _vp]),
+    "vr_host_register": (_i, [_vp, _vp, C.c_size_t]),
+    "vr_host_unregister": (_i, [_vp, _vp]),
     "vr_octree_save": (_i, [_vp, C.c_char_p]),
     "vr_octree_load": (_i, [_vp, C.c_char_p]),
     "vr_get_stats": (_i, [_vp, C.POINTER(VrStats)]),
@@ -366,6 +368,13 @@ class CUDACaster:
 
     def push_bands(self, slab_ptr: int, frame_ptr: int, cuda_stream: int | None = None) -> bool:
         return bool(self._lib.vr_push_bands(self._ctx, _vp(slab_ptr), _vp(frame_ptr), _vp(cuda_stream or 0)))
+
+    def host_register(self, host_ptr: int, nbytes: int) -> bool:
+        """page-lock caller-owned host memory (e.g. a shared-memory frame) so push_bands can target it"""
+        return bool(self._lib.vr_host_register(self._ctx, _vp(host_ptr), nbytes))
+
+    def host_unregister(self, host_ptr: int) -> bool:
+        return bool(self._lib.vr_host_unregister(self._ctx, _vp(host_ptr)))
 
     def octree_save(self, path: str) -> bool:
         return bool(self._lib.vr_octree_save(self._ctx, str(path).encode()))

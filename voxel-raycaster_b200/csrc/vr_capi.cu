@@ -893,6 +893,20 @@ int vr_push_bands(vr_ctx *c, const void *slab, void *frame, void *cuda_stream) {
     return 1;
 }
 
+int vr_host_register(vr_ctx *c, void *host_ptr, size_t bytes) {
+    if (!c || !host_ptr || !bytes) return 0;
+    cudaSetDevice(c->device);
+    VR_CUDA(c, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return 1;
+}
+
+int vr_host_unregister(vr_ctx *c, void *host_ptr) {
+    if (!c || !host_ptr) return 0;
+    cudaSetDevice(c->device);
+    VR_CUDA(c, cudaHostUnregister(host_ptr));
+    return 1;
+}
+
 /* On-disk octree: "VR64" | u32 version | i32 dim | i32 levels | u64 nodes | u64 types | vr_node[] | u8[] */
 int vr_octree_save(vr_ctx *c, const char *path) {
     if (!c || !path) return 0;

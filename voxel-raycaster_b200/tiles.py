@@ -55,6 +55,64 @@ def gather_frame(layout: BandLayout, slab, gathered, frame, dist=None, rank: int
     return frame
 
 
+class SharedHostFrame:
+    """`count` frames [max_bands*world*band_rows, W, 4] uint8 in one POSIX shared-memory file mapped by every rank
+    of the node.  With the mapping page-locked (CUDACaster.host_register) each rank copies its own bands device ->
+    host into frame order (CUDACaster.push_bands with the mapping as target): the frame reaches host memory over all
+    PCIe links at once and no rank ever holds the whole frame on its GPU."""
+
+    def __init__(self, layout: BandLayout, dist=None, rank: int = 0, count: int = 2, directory: str = "/dev/shm"):
+        import mmap
+        import os
+
+        import numpy as np
+
+        self.layout, self.rank, self.count = layout, rank, count
+        self.rows = layout.max_bands * layout.world * layout.band_rows
+        self.frame_bytes = self.rows * layout.width * 4
+        names = [None]
+        if rank == 0:
+            names[0] = os.path.join(directory, f"vr_frame_{os.getpid()}_{id(self) & 0xffff:x}")
+            with open(names[0], "wb") as f:
+                f.truncate(self.frame_bytes * count)
+        if dist is not None and layout.world > 1:
+            dist.broadcast_object_list(names, src=0)
+        self.path = names[0]
+        self._fd = os.open(self.path, os.O_RDWR)
+        self._map = mmap.mmap(self._fd, self.frame_bytes * count)
+        self.array = np.frombuffer(self._map, dtype=np.uint8).reshape(count, self.rows, layout.width, 4)
+        self.registered_by = None
+        if dist is not None and layout.world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)              # every rank holds its mapping; the name is no longer needed
+
+    def ptr(self, i: int) -> int:
+        return self.array[i].ctypes.data
+
+    def register(self, caster) -> None:
+        if not caster.host_register(self.array.ctypes.data, self.frame_bytes * self.count):
+            raise RuntimeError(caster.last_error())
+        self.registered_by = caster
+
+    def frame(self, i: int):
+        """frame i in frame order, height rows"""
+        return self.array[i, : self.layout.height]
+
+    def close(self) -> None:
+        import os
+
+        if self.registered_by is not None:
+            self.registered_by.host_unregister(self.array.ctypes.data)
+            self.registered_by = None
+        self.array = None
+        try:
+            self._map.close()
+        except BufferError:
+            pass
+        os.close(self._fd)
+
+
 class _RawCuda:
     """uint8 device memory owned elsewhere, exposed to torch via the CUDA array interface"""
 
@@ -76,6 +134,7 @@ class FramePipeline:
 
         self.torch, self.layout, self.dist, self.rank, self.render, self.host_frame = torch, layout, dist, rank, render, host_frame
         self.caster = caster
+        self.shared_host = None       # set_shared_host(): every rank copies its bands straight to the host frame
         W = layout.width
         self.slabs = [torch.zeros((layout.slab_rows, W, 4), dtype=torch.uint8, device=device) for _ in range(2)]
         self.gathered = torch.empty((layout.world * layout.slab_rows, W, 4), dtype=torch.uint8, device=device)
@@ -113,7 +172,11 @@ class FramePipeline:
         self.rendered[i].record(cur)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.rendered[i])
-            if self.caster is not None:
+            if self.shared_host is not None:
+                # end-to-end path with a HOST result: this rank's bands -> frame order in shared pinned memory
+                if not self.shared_caster.push_bands(self.slabs[i].data_ptr(), self.shared_host.ptr(i % self.shared_host.count), self.comm.cuda_stream):
+                    raise RuntimeError(self.shared_caster.last_error())
+            elif self.caster is not None:
                 if not self.caster.push_bands(self.slabs[i].data_ptr(), self.frame_ptrs[i], self.comm.cuda_stream):
                     raise RuntimeError(self.caster.last_error())
                 self.dist.all_reduce(self.token)          # completes on the root only after every push has landed
@@ -125,6 +188,9 @@ class FramePipeline:
                 self.host_frame.copy_(self.frame[: self.layout.height], non_blocking=True)
             self.collected[i].record(self.comm)
         self.k += 1
+
+    def set_shared_host(self, shared_host, caster) -> None:
+        self.shared_host, self.shared_caster = shared_host, caster
 
     def drain(self) -> None:
         """make the current stream wait for every gather issued so far"""
