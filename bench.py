@@ -29,7 +29,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 METRIC = "Mrays/s (primary + shadow rays), 1024^3 SVO @ 3840x2160 + shadows"
-BAND_ROWS = 8
+BAND_ROWS = int(os.environ.get("VR_BAND_ROWS", "8"))   # rows per interleaved band (multiple of the 4-row CTA tile)
 BENCH_CAMERA = 9            # make_camera(index): terrain + sky + shadowed pixels
 
 
@@ -299,9 +299,11 @@ def main() -> None:
     ap.add_argument("--ctas-per-sm", type=int, default=3)
     ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
     ap.add_argument("--walk", type=int, default=1, help="in-cell walk of the octree kernel: 1 = per-axis (default here; exact except the step count of exact-tie rays), 0 = merged (bit-identical on every pixel; the library default)")
+    ap.add_argument("--overlap-frames", type=int, default=1, help="N > 1: 1 = consecutive frames are launched on two alternating streams (the next frame's "
+                    "first CTAs fill the tail of the current one); the kernel events then overlap, so roofline.kernel_ms is the step time")
     ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
                     help="N > 1 end-to-end leg: 'shared' = every rank copies its bands into a shared pinned host frame; 'root' = rank 0 copies the gathered frame")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "direct"],
                     help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -420,8 +422,17 @@ def main() -> None:
 
     # ---- device-resident timing: K steps bracketed by barrier + synchronize, CUDA events on the launch stream.
     # N > 1: the gather of frame k overlaps the rendering of frame k+1 (tiles.FramePipeline, double buffered).
+    direct = world > 1 and args.gather == "direct"
+    if direct:
+        # 2-D tile interleave, rendered in place into the root's frame over NVLink: no slab, no gather
+        must(c.set_bands(BAND_ROWS, 1, 0) and c.set_tiles(world, rank), "set_tiles")
     pipe = pkg.tiles.FramePipeline(layout, dev, dist, rank, lambda ptr: must(c.compute_into(ptr), "compute_into"),
-                                   caster=c if args.gather == "p2p" else None) if world > 1 else None
+                                   caster=c if args.gather in ("p2p", "direct") else None, direct=direct) if world > 1 else None
+    overlap = pipe is not None and args.overlap_frames == 1
+    if overlap:
+        # consecutive frames on two streams: the first CTAs of frame k+1 fill the SMs the tail of frame k leaves idle
+        stream_b = torch.cuda.Stream(device=dev)
+        pipe.alternate_streams([stream, stream_b], lambda s: must(c.set_stream(s.cuda_stream), "set_stream"))
     for _ in range(args.warmup):
         pipe.step() if pipe else render_step()
     if pipe:
@@ -435,9 +446,10 @@ def main() -> None:
         for i in range(args.steps):
             if pipe:
                 def timed_render(ptr, i=i):               # events hug the kernel, not the wait for a free slab
-                    kev[i][0].record(stream)
+                    ks = pipe.render_streams[pipe.k & 1] if pipe.render_streams is not None else stream
+                    kev[i][0].record(ks)
                     must(c.compute_into(ptr), "compute_into")
-                    kev[i][1].record(stream)
+                    kev[i][1].record(ks)
                 pipe.render = timed_render
                 pipe.step()
             else:
@@ -450,11 +462,25 @@ def main() -> None:
         ev1.record(stream)
         barrier()
     launches = c.stats().kernel_launches - launches0
+    device_checksum = None
+    if overlap:
+        pipe.render_streams = None
+        must(c.set_stream(stream.cuda_stream), "set_stream")
+    if pipe is not None and rank == 0:
+        torch.cuda.synchronize()
+        device_checksum = int(pipe.frame[: scene.height][::64, ::64].sum().item())     # the frame assembled on the root GPU
+    if direct:
+        pipe.direct = False                          # the legs below (other walk, end to end) use row bands again
+        pipe.slabs = [torch.zeros((layout.slab_rows, scene.width, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+        pipe.nbuf = 2
+        must(c.set_tiles(1, 0) and c.set_bands(BAND_ROWS, world, rank), "set_bands")
     t_ms = torch.tensor([ev0.elapsed_time(ev1), float(np.mean([a.elapsed_time(b) for a, b in kev]))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms = [float(v) for v in t_ms.tolist()]
     ms_per_step = total_ms / args.steps
+    if overlap:
+        kernel_ms = ms_per_step      # launches of consecutive frames overlap: effective duration per launch
     value = rays / (ms_per_step / 1e3) / 1e6
 
     # the other in-cell walk, for the record (a few untimed-region frames, kernel only)
@@ -549,7 +575,7 @@ def main() -> None:
                        "mode": args.mode,
                        "walk": ("per-axis in-cell walk: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)" if args.walk == 1 else "merged in-cell walk: bit-identical to the reference restatement on every pixel") if use_svo else "dense DDA",
                        "other_walk_ms_per_frame": other_walk_ms,
-                       "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1" if world > 1 else "1 GPU",
+                       "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
@@ -558,7 +584,7 @@ def main() -> None:
                                          "map_read_ms": round(float(st.build_masks_ms), 3),
                                          "map_read_gbs": round(scene.n ** 3 / max(float(st.build_masks_ms), 1e-6) / 1e6, 1)}
                                         if st.build_ms > 0 else {"where": "host (column builder or broadcast)"}),
-                       "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum},
+                       "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum, "device_frame_checksum": device_checksum},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 5 * 4 + 10 * 4 + 64 * 8,

@@ -138,6 +138,13 @@ int vr_frame_end(vr_ctx *ctx, const uint8_t **rgba);
  * (band = band_rows consecutive rows) into a compact slab.  (1,1,0) = whole frame. */
 int vr_set_bands(vr_ctx *ctx, int band_rows, int stride, int first);
 int vr_local_rows(const vr_ctx *ctx);
+/* Multi-GPU 2-D tile interleave, the alternative to row bands: this context renders the 32x4-pixel CTA tiles (tx, ty)
+ * with (tx + ty) % world == rank IN PLACE into the full-size frame passed to vr_compute_into -- its own memory or
+ * another GPU's frame mapped with vr_ipc_open_handle, in which case the kernel's RGBA stores travel over NVLink and
+ * the frame is assembled by the render kernels themselves (no slab, no gather).  A thin expensive screen feature
+ * (the horizon) is spread over all ranks instead of landing on the one or two ranks that own its rows.
+ * (1, 0) = off. */
+int vr_set_tiles(vr_ctx *ctx, int world, int rank);
 /* Kernel variant knobs: "persistent" (0/1: persistent warps with warp-level pixel refill for the octree
  * kernel), "refill_min" (idle lanes before a warp refills, 1..32), "ctas_per_sm" (persistent grid size),
  * "walk" (0 merged / 1 per-axis in-cell walk), "l2_persist" (0/1 access-policy window over the octree nodes),

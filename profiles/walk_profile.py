@@ -58,6 +58,7 @@ hist = take(NP * NH).reshape(NP, NH); hist_steps = take(NP * NH).reshape(NP, NH)
 lookups, pops, loads, hits, replays, chain, fix, rounds, lane_rounds, rays, adds, jumps = take(12)
 model_warp, model_lane = take(2)
 comp = take(8)
+grp_rounds, grp_adds, grp_model, grp_rays = take(8), take(8), take(8), take(8)
 names = ["none", "brick", "axes", "merged", "merged after axes fallback"]
 print(f"{config} stride {stride}: rays {rays:.0f} (x{stride} = {rays * stride / 1e6:.2f} M), lane-rounds/ray {lane_rounds / rays:.2f}, "
       f"SIMT round efficiency {lane_rounds / (32 * rounds):.3f}")
@@ -72,3 +73,5 @@ for p in range(NP):
 print(f"model: warp slots/frame {model_warp * stride / 1e9:.3f} G (ncu smsp__inst_executed), lane slots {model_lane * stride / 1e9:.2f} G, "
       f"thread/inst {model_lane / model_warp:.1f}")
 print("  warp-slot share: " + ", ".join(f"{nm} {100 * v / model_warp:.1f}%" for nm, v in zip(["brick", "axes", "merged", "lookup", "hit", "loop"], comp)))
+print("by tile row mod 8 (4 screen rows each): warp rounds " + " ".join(f"{v / grp_rounds.mean():.3f}" for v in grp_rounds)
+      + " | chain work " + " ".join(f"{v / grp_adds.mean():.3f}" for v in grp_adds) + " | model " + " ".join(f"{v / grp_model.mean():.3f}" for v in grp_model))

@@ -30,6 +30,7 @@ struct Totals {
     double lookups, pops, loads, hits, replays, chain, fix, rounds, lane_rounds, rays, adds, jumps;
     double model_warp, model_lane;       /* modelled warp issue slots (SIMT: max per path) and lane slots (sum) */
     double comp_warp[8];
+    double grp_rounds[8], grp_adds[8], grp_model[8], grp_rays[8];   /* by (tile row mod 8): screen-row periodicity of the cost */
 };
 
 static int bucket(int n) { int b = 0; while ((1 << b) < n && b < NH - 1) b++; return b; }
@@ -103,6 +104,7 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
                     L.lookups += p.lookup; L.pops += p.pops; L.loads += p.loads; L.hits += p.hit; L.replays += p.replay;
                     L.chain += p.chain_a + p.chain_b; L.fix += p.fix; L.adds += p.adds; L.jumps += p.jumps;
                     L.lane_rounds += 1;
+                    L.grp_adds[by & 7] += p.adds + p.fix + 35 * p.jumps;
                     const Cost c = cost_of(p, model);
                     L.model_lane += c.brick + c.axes + c.merged + c.lookup + c.hit + model[11];
                     mx.brick = fmaxf(mx.brick, c.brick); mx.axes = fmaxf(mx.axes, c.axes); mx.merged = fmaxf(mx.merged, c.merged);
@@ -110,6 +112,8 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
                     if (rc != VR_CELL_CONTINUE) { active[l] = false; nact--; }
                 }
                 L.rounds += 1;
+                L.grp_rounds[by & 7] += 1;
+                L.grp_model[by & 7] += mx.brick + mx.axes + mx.merged + mx.lookup + mx.hit + model[11];
                 L.model_warp += mx.brick + mx.axes + mx.merged + mx.lookup + mx.hit + model[11];
                 L.comp_warp[0] += mx.brick; L.comp_warp[1] += mx.axes; L.comp_warp[2] += mx.merged; L.comp_warp[3] += mx.lookup;
                 L.comp_warp[4] += mx.hit; L.comp_warp[5] += model[11];

@@ -584,3 +584,32 @@ def test_push_bands_into_registered_host_frame(pkg, oracle):
     shared.close()                       # unregisters through casters[0]
     for c in casters:
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_interleave_renders_in_place(pkg, oracle, world):
+    """vr_set_tiles: the tile sets of `world` ranks, rendered one after the other IN PLACE into one full-size frame
+    (what the ranks of a multi-GPU run do into the root's frame over NVLink), give the single-context frame --
+    dense and octree kernels, frame sizes that are not multiples of the tile or of world."""
+    import torch
+
+    scene = pkg.scene.make_scene("features")           # 200 x 120: 6.25 tiles wide
+    for use_octree in (False, True):
+        full = make_caster(pkg, scene, use_octree, aux=False)
+        assert full.compute()
+        want = full.draw().copy()
+        frame = torch.tensor([255, 255, 255, 100], dtype=torch.uint8, device="cuda:0").repeat(scene.height, scene.width, 1).contiguous()
+        covered = torch.zeros((scene.height, scene.width, 4), dtype=torch.uint8, device="cuda:0")
+        for rank in range(world):
+            assert full.set_tiles(world, rank)
+            assert full.compute_into(frame.data_ptr()), full.last_error()
+            one = torch.zeros_like(covered)
+            assert full.compute_into(one.data_ptr())
+            torch.cuda.synchronize()
+            assert not ((one != 0) & (covered != 0)).any()          # tile sets are disjoint
+            covered |= one
+        assert np.array_equal(frame.cpu().numpy(), want)
+        assert full.set_bands(8, 2, 1) and not full.compute_into(frame.data_ptr())      # bands + tiles: refused
+        assert "mutually exclusive" in full.last_error()
+        full.close()

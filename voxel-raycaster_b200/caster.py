@@ -76,6 +76,7 @@ SYMBOLS = {
     "vr_frame_end": (_i, [_vp, C.POINTER(_u8p)]),
     "vr_set_bands": (_i, [_vp, _i, _i, _i]),
     "vr_local_rows": (_i, [_vp]),
+    "vr_set_tiles": (_i, [_vp, _i, _i]),
     "vr_set_option": (_i, [_vp, C.c_char_p, C.c_int64]),
     "vr_set_stream": (_i, [_vp, _vp]),
     "vr_enable_aux": (_i, [_vp, _i]),
@@ -301,6 +302,10 @@ class CUDACaster:
     # -- extensions -----------------------------------------------------------------------------
     def set_bands(self, band_rows: int, stride: int, first: int) -> bool:
         return bool(self._lib.vr_set_bands(self._ctx, band_rows, stride, first))
+
+    def set_tiles(self, world: int, rank: int) -> bool:
+        """2-D tile interleave: render tiles (tx + ty) % world == rank in place into a full-size frame"""
+        return bool(self._lib.vr_set_tiles(self._ctx, world, rank))
 
     def set_option(self, name: str, value: int) -> bool:
         return bool(self._lib.vr_set_option(self._ctx, name.encode(), int(value)))

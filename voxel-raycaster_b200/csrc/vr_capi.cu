@@ -46,6 +46,7 @@ struct vr_ctx {
     vr_aux *d_aux = nullptr;
     bool aux_on = false;
     int band_rows = 1, band_stride = 1, band_first = 0;
+    int tile_world = 1, tile_rank = 0;
 
     /* dense map */
     int8_t *d_map = nullptr;
@@ -221,6 +222,10 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     P.band_stride = c->band_stride;
     P.band_first = c->band_first;
     P.local_rows = local_rows_padded(c);
+    P.tile_world = c->tile_world;
+    P.tile_rank = c->tile_rank;
+    if (c->tile_world > 1 && (c->band_stride != 1 || c->band_first != 0))
+        return fail(c, "compute: tile interleave (vr_set_tiles) and row bands (vr_set_bands) are mutually exclusive");
     P.ray_table = c->d_ray_table;
     P.image = image;
     P.aux = c->aux_on ? c->d_aux : nullptr;
@@ -731,6 +736,14 @@ int vr_set_bands(vr_ctx *c, int band_rows, int stride, int first) {
     c->band_rows = band_rows;
     c->band_stride = stride;
     c->band_first = first;
+    return 1;
+}
+
+int vr_set_tiles(vr_ctx *c, int world, int rank) {
+    if (!c) return 0;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, "set_tiles: bad arguments");
+    c->tile_world = world;
+    c->tile_rank = rank;
     return 1;
 }
 

@@ -42,6 +42,31 @@ __device__ __forceinline__ int frame_row(const vr_frame_params &P, int ly) {
     return (lb * P.band_stride + P.band_first) * P.band_rows + (ly - lb * P.band_rows);
 }
 
+/* CTA -> pixel of this thread.  Returns false when the thread has no pixel.  Band mode (default): the grid covers the
+ * rank's compact slab, `local` addresses the slab, y is the frame row.  Tile mode (P.tile_world > 1): the grid covers
+ * ceil(tiles_x / world) x tiles_y CTAs, CTA (k, ty) is tile tx = ((rank - ty) mod world) + k * world of tile row ty, and
+ * `local` addresses the full frame: the pixel is written where it belongs, possibly in a peer GPU's memory. */
+__device__ __forceinline__ bool cta_pixel(const vr_frame_params &P, int &x, int &y, size_t &local) {
+    int lx, ly;
+    tile_xy(threadIdx.x, lx, ly);
+    if (P.tile_world > 1) {
+        int first = (P.tile_rank - (int)blockIdx.y) % P.tile_world;
+        first += first < 0 ? P.tile_world : 0;
+        x = (first + (int)blockIdx.x * P.tile_world) * kTileW + lx;
+        y = (int)blockIdx.y * kTileH + ly;
+        if (x >= P.width || y >= P.height) return false;
+        local = (size_t)x + (size_t)P.width * (size_t)y;
+        return true;
+    }
+    x = blockIdx.x * kTileW + lx;
+    const int row = blockIdx.y * kTileH + ly;
+    if (x >= P.width || row >= P.local_rows) return false;
+    y = frame_row(P, row);
+    if (y >= P.height) return false;
+    local = (size_t)x + (size_t)P.width * (size_t)row;
+    return true;
+}
+
 struct SmemStack {
     uint32_t *base;   /* &stack[0][tid]; level stride = kThreads */
     __device__ __forceinline__ void set(int level, uint32_t v) { base[level * kThreads] = v; }
@@ -53,14 +78,9 @@ struct SmemStack {
 template <bool AUX, bool MULTI>
 __global__ void __launch_bounds__(kThreads)
 vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
-    int lx, ly;
-    tile_xy(threadIdx.x, lx, ly);
-    const int x = blockIdx.x * kTileW + lx;
-    const int row = blockIdx.y * kTileH + ly;
-    if (x >= P.width || row >= P.local_rows) return;
-    const int y = frame_row(P, row);
-    if (y >= P.height) return;
-    const size_t local = (size_t)x + (size_t)P.width * (size_t)row;
+    int x, y;
+    size_t local;
+    if (!cta_pixel(P, x, y, local)) return;
     uint32_t rgba;
     vr_aux a;
     const bool write = vr_trace_dense<AUX, MULTI>(P, x, y, &rgba, &a);
@@ -73,14 +93,9 @@ template <bool AUX, int WALK, bool MULTI>
 __global__ void __launch_bounds__(kThreads, VR_SVO_MIN_CTAS)
 vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
-    int lx, ly;
-    tile_xy(threadIdx.x, lx, ly);
-    const int x = blockIdx.x * kTileW + lx;
-    const int row = blockIdx.y * kTileH + ly;
-    if (x >= P.width || row >= P.local_rows) return;
-    const int y = frame_row(P, row);
-    if (y >= P.height) return;
-    const size_t local = (size_t)x + (size_t)P.width * (size_t)row;
+    int x, y;
+    size_t local;
+    if (!cta_pixel(P, x, y, local)) return;
     SmemStack stk{stack + threadIdx.x};
     uint32_t rgba;
     vr_aux a;
@@ -166,11 +181,13 @@ __global__ void vr_fill_kernel(uint32_t *dst, size_t n, uint32_t value) {
 cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_aux, cudaStream_t stream,
                               unsigned long long *launches, const vr_launch_options *opt) {
     if (P.width <= 0 || P.local_rows <= 0) return cudaSuccess;
-    const dim3 grid((P.width + kTileW - 1) / kTileW, (P.local_rows + kTileH - 1) / kTileH);
+    const int tiles_x = (P.width + kTileW - 1) / kTileW;
+    const dim3 grid(P.tile_world > 1 ? (tiles_x + P.tile_world - 1) / P.tile_world : tiles_x,
+                    ((P.tile_world > 1 ? P.height : P.local_rows) + kTileH - 1) / kTileH);
     const dim3 block(kThreads);
     const bool multi = P.light_count > 1;
     const bool aux = with_aux != 0;
-    if (use_svo && opt && opt->persistent && !multi) {            /* (the persistent variant has no multi-light build) */
+    if (use_svo && opt && opt->persistent && !multi && P.tile_world <= 1) {   /* (no multi-light / tile-interleave build) */
         cudaError_t e = cudaMemsetAsync(opt->counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
         unsigned ctas = (unsigned)(opt->num_sms * opt->ctas_per_sm);

@@ -73,6 +73,10 @@ typedef struct vr_frame_params {
      * rows into a compact slab: local row ly -> frame row
      * ((ly / band_rows) * band_stride + band_first) * band_rows + ly % band_rows. */
     int32_t local_rows, band_rows, band_stride, band_first;
+    /* multi-GPU 2-D tile interleave (vr_set_tiles): with tile_world > 1 the launch renders, IN PLACE in a full-size
+     * frame (local memory or a peer GPU's frame mapped over NVLink), the CTA tiles (tx, ty) with
+     * (tx + ty) % tile_world == tile_rank; bands are then off */
+    int32_t tile_world, tile_rank;
     const float *ray_table;        /* float4 per pixel (kernel arg 3)                        */
     uint8_t *image;                /* RGBA8, row pitch width*4; local slab when banded       */
     vr_aux *aux;                   /* optional                                               */

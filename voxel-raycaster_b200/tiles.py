@@ -126,48 +126,80 @@ class FramePipeline:
     other slab.  `render(ptr)` must enqueue the rendering of this rank's bands into device memory at `ptr`
     on the CURRENT torch stream (CUDACaster.compute_into after set_stream)."""
 
-    def __init__(self, layout: BandLayout, device, dist, rank: int, render, host_frame=None, caster=None):
+    def __init__(self, layout: BandLayout, device, dist, rank: int, render, host_frame=None, caster=None, direct=False):
         """caster != None selects the copy-engine gather: every rank pushes its slab into the root's frame buffer
         through a CUDA-IPC mapping (CUDACaster.push_bands), followed by a one-element all_reduce as the "frame
-        complete" signal; otherwise the slabs go through NCCL all_gather + one un-interleave copy."""
+        complete" signal; otherwise the slabs go through NCCL all_gather + one un-interleave copy.
+        direct=True (needs caster, and the caster in tile mode: CUDACaster.set_tiles): there are no slabs at all --
+        `render(ptr)` is handed the root's frame itself (local on the root, IPC-mapped elsewhere) and the render
+        kernels store their pixels in place over NVLink; three frame buffers, so that a rank may start frame k+3
+        as soon as frame k+1 is complete everywhere (no per-frame bubble)."""
         import torch
 
         self.torch, self.layout, self.dist, self.rank, self.render, self.host_frame = torch, layout, dist, rank, render, host_frame
         self.caster = caster
+        self.direct = bool(direct and caster is not None)
         self.shared_host = None       # set_shared_host(): every rank copies its bands straight to the host frame
+        self.nbuf = 3 if self.direct else 2
         W = layout.width
-        self.slabs = [torch.zeros((layout.slab_rows, W, 4), dtype=torch.uint8, device=device) for _ in range(2)]
-        self.gathered = torch.empty((layout.world * layout.slab_rows, W, 4), dtype=torch.uint8, device=device)
-        self.frame = torch.empty((layout.max_bands * layout.world * layout.band_rows, W, 4), dtype=torch.uint8, device=device) if rank == 0 else None
+        self.slabs = [] if self.direct else [torch.zeros((layout.slab_rows, W, 4), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.gathered = torch.empty((layout.world * layout.slab_rows, W, 4), dtype=torch.uint8, device=device) if caster is None else None
+        self.frame = torch.empty((layout.max_bands * layout.world * layout.band_rows, W, 4), dtype=torch.uint8, device=device) if (rank == 0 and caster is None) else None
         self.comm = torch.cuda.Stream(device=device)
         self.token = torch.zeros(1, dtype=torch.int32, device=device)
         self.frames = None
         if caster is not None:
-            # two frame buffers on the root, mapped into every other rank
+            # frame buffers on the root, mapped into every other rank
+            shape = (layout.max_bands * layout.world * layout.band_rows, W, 4)
+            nbytes = shape[0] * shape[1] * shape[2]
             if rank == 0:
                 # cudaMalloc'ed by the caster (torch's caching allocator memory is not reliably IPC-exportable),
                 # wrapped as torch tensors through __cuda_array_interface__
-                shape = tuple(self.frame.shape)
-                nbytes = self.frame.numel()
-                self.frame_ptrs = [caster.device_alloc(nbytes) for _ in range(2)]
+                self.frame_ptrs = [caster.device_alloc(nbytes) for _ in range(self.nbuf)]
                 self.frames = [torch.as_tensor(_RawCuda(p, shape), device=device) for p in self.frame_ptrs]
                 self.frame = self.frames[0]
                 handles = [caster.ipc_get_handle(p) for p in self.frame_ptrs]
             else:
-                handles = [None, None]
+                handles = [None] * self.nbuf
             dist.broadcast_object_list(handles, src=0)
             if rank != 0:
                 self.frame_ptrs = [caster.ipc_open_handle(h) for h in handles]
-        self.rendered = [torch.cuda.Event() for _ in range(2)]
-        self.collected = [torch.cuda.Event() for _ in range(2)]
+        self.rendered = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.collected = [torch.cuda.Event() for _ in range(self.nbuf)]
         self.k = 0
+        # alternate_streams(): consecutive frames are rendered on two streams, so that the first CTAs of frame k+1
+        # fill the SMs the tail of frame k leaves idle (a 1/8-frame kernel is only ~7 waves of CTAs)
+        self.render_streams = None
+        self.use_stream = None
+
+    def alternate_streams(self, streams, use_stream) -> None:
+        """streams: two torch streams; use_stream(s): make the renderer launch on s (CUDACaster.set_stream)"""
+        self.render_streams, self.use_stream = streams, use_stream
 
     def step(self) -> None:
         torch = self.torch
-        i = self.k & 1
+        i = self.k % self.nbuf
         cur = torch.cuda.current_stream()
+        if self.render_streams is not None:
+            cur = self.render_streams[self.k & 1]
+            self.use_stream(cur)
         if self.k >= 2:
-            cur.wait_event(self.collected[i])            # slab i has left for the gather of frame k-2
+            # buffer i was last used by step k - nbuf; every rank (and the root's consumer) is past it once the
+            # collection of step k - 2 has completed here
+            cur.wait_event(self.collected[(self.k - 2) % self.nbuf])
+        if self.direct:
+            self.render(self.frame_ptrs[i])               # pixels go straight into the root's frame (NVLink stores)
+            self.rendered[i].record(cur)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.rendered[i])
+                self.dist.all_reduce(self.token)          # completes on the root only after every kernel has finished
+                if self.rank == 0:
+                    self.frame = self.frames[i]
+                    if self.host_frame is not None:
+                        self.host_frame.copy_(self.frame[: self.layout.height], non_blocking=True)
+                self.collected[i].record(self.comm)
+            self.k += 1
+            return
         self.render(self.slabs[i].data_ptr())
         self.rendered[i].record(cur)
         with torch.cuda.stream(self.comm):
@@ -195,3 +227,6 @@ class FramePipeline:
     def drain(self) -> None:
         """make the current stream wait for every gather issued so far"""
         self.torch.cuda.current_stream().wait_stream(self.comm)
+        if self.render_streams is not None:
+            for s in self.render_streams:
+                self.torch.cuda.current_stream().wait_stream(s)
