@@ -303,8 +303,9 @@ def main() -> None:
                     "first CTAs fill the tail of the current one); the kernel events then overlap, so roofline.kernel_ms is the step time")
     ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
                     help="N > 1 end-to-end leg: 'shared' = every rank copies its bands into a shared pinned host frame; 'root' = rank 0 copies the gathered frame")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "direct"],
-                    help="N > 1 frame assembly: copy-engine push into the root's frame (CUDA IPC) + 1-element all_reduce, or NCCL all_gather")
+    ap.add_argument("--gather", default="direct", choices=["direct", "p2p", "nccl"],
+                    help="N > 1 frame assembly on the root GPU: 'direct' = 2-D tile interleave, the render kernels store their pixels in place into the "
+                    "root's frame over NVLink (CUDA IPC); 'p2p' = row bands + copy-engine push into the root's frame; 'nccl' = row bands + all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
