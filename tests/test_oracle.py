@@ -168,8 +168,13 @@ def test_golden_fixture(pkg, oracle):
     for f in files:
         z = np.load(f)
         scene = pkg.scene.make_scene(str(z["scene"]))
+        lights = int(z["lights"]) if "lights" in z.files else 1
+        if lights > 1:
+            from test_emu_parity import _with_lights
+
+            scene = _with_lights(pkg, scene, lights)
         desc, root = pkg.octree_generate(scene.volume)
-        rgba, aux, _ = oracle.raycast(scene, octree=(desc, root))
+        rgba, aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=lights)
         assert np.array_equal(rgba, z["rgba"]), f.name
         for k in ("hit", "face", "status", "flags", "steps_first", "steps_total"):
             assert np.array_equal(aux[k], z[k]), (f.name, k)
