@@ -281,7 +281,11 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
     int use_svo = 0;
     if (!build_params(c, P, image, &use_svo)) return 0;
     if (timed) VR_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
-    VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &c->opt));
+    /* the per-axis walk sizes its add chains from a closed-form estimate whose error grows with ulp(t) (vr_count_before:
+     * < 0.2 crossings up to 4096^3, where it is tested); beyond 16384^3 the merged walk is used whatever the option says */
+    vr_launch_options opt = c->opt;
+    if (P.dim[0] > 16384) opt.walk = 0;
+    VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &opt));
     if (timed) {
         VR_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
         c->timing_pending = true;
