@@ -9,12 +9,19 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  Nothing under voxel-raycaster_b200/ links, imports or executes it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden images or known-answer vectors for this
- * path and cannot be compiled here (no OpenCL runtime, SFML or GL in the
- * image), so this restatement cannot be checked against reference-owned fixtures.  What pins it:
- *   - the derived known answers listed in tests/test_oracle.py (HEAD 16^3 octree: 585 descriptors,
- *     root index 99415; hand-computed rays in tiny maps; Octree::Validate's occupancy property),
- *   - line-against-line review with the kernel (every function cites the kernel lines it follows).
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN CODE, EXECUTED.  The reference ships no tests, golden images or
+ * known-answer vectors for this path and no OpenCL runtime, SFML or GL exists in the image,
+ * but its sources can be compiled for the CPU from where they lie (`make -C oracle ref` -> oracle/_ref/*.so):
+ *   - kernels/ray_caster_kernel.cl by g++ through ref_shim/cl_shim.h (OpenCL C vector types, operators and built-ins
+ *     in C++; the only edit, by sed on the fly, is the vector-literal syntax `(typeN)(` -> `typeN(`), verbatim and with
+ *     kernel:326's max_distance read from a variable;
+ *   - src/map/Octree.cpp + include/util.hpp with stand-ins for the three SFML headers they include.
+ * tests/test_reference_kernel.py requires this restatement to reproduce that code bit for bit: every RGBA8 pixel and
+ * the written/skipped mask on 14 scene/camera combinations (HEAD, shadows, reflections, biased camera, 64^3 and 256^3
+ * terrain, transparent values), all 100 000 entries of Octree::Generate's buffer and its root index, util.hpp's
+ * Normalize.  Not pinned by the reference: the OpenCL built-ins below (an OpenCL runtime supplies them; cl_shim.h and
+ * this file define them identically) and CLCaster::create_viewport's loop (OpenCL/GL translation unit: restated, its
+ * Normalize call pinned).  Further pins: the derived known answers in tests/test_oracle.py and tests/golden/.
  *
  * OpenCL built-ins whose results are implementation-defined in the reference (it is built with
  * -cl-fast-relaxed-math, src/CLCaster.cpp:771) are pinned here to IEEE-754 binary32:

@@ -613,3 +613,23 @@ def test_tile_interleave_renders_in_place(pkg, oracle, world):
         assert full.set_bands(8, 2, 1) and not full.compute_into(frame.data_ptr())      # bands + tiles: refused
         assert "mutually exclusive" in full.last_error()
         full.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["head", "features", "features-low", "features-high", "features-mirror", "small"])
+def test_cuda_equals_reference_kernel_source(pkg, name):
+    """Directly against the reference's own kernel source compiled for the CPU (oracle/_ref/libref_kernel_md.so, see
+    tests/test_reference_kernel.py), not through the oracle: RGBA8 of the dense kernel and of the octree kernel (merged
+    walk) on all pixels, including which pixels are left unwritten."""
+    import ref_kernel_lib as R
+
+    if not R.available(True):
+        pytest.skip("oracle/_ref/libref_kernel_md.so not built (needs /root/reference at build time)")
+    scene = pkg.scene.make_scene(name)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, _ = R.raycast(scene, octree=(desc, root), lifted=True)
+    for use_octree in (False, True):
+        c = make_caster(pkg, scene, use_octree, aux=False)
+        assert c.compute(), c.last_error()
+        assert np.array_equal(c.draw(), ref_rgba), f"{name} use_octree={use_octree}"
+        c.close()
