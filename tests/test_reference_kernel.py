@@ -138,3 +138,23 @@ def test_ray_table_uses_reference_normalize(oracle):
             want = R.normalize(v)
             got = table[y + h // 2, x + w // 2, :3] if table.ndim == 3 else table.reshape(h, w, 4)[y + h // 2, x + w // 2, :3]
             assert np.array_equal(want.view(np.uint32), np.asarray(got, np.float32).view(np.uint32)), (x, y)
+
+
+@needs_kernel
+@needs_octree
+@pytest.mark.parametrize("name", ["head", "features", "tiny"])
+def test_reference_octree_branch_never_registers_a_hit(pkg, name):
+    """Why the reference's octree branch (OCTENABLED == 0, kernel:359-550, "not working") is REPLACED rather than
+    ported: executed as written, on the reference's own octree buffer, it never assigns voxel_data (kernel:549 is
+    commented out), so no pixel is textured or lit -- every pixel is an opaque flat grey (1 - steps/8, kernel:372-377)
+    whatever the scene.  The caster instead renders, with OCTENABLED == 0, what the dense branch renders."""
+    scene = pkg.scene.make_scene(name)
+    ref = R.RefOctree(scene.volume)
+    rgba, written = R.raycast(scene, octree=(ref.descriptors, ref.root_index), lifted=False, octenabled=0)
+    ref.close()
+    assert written.all()
+    assert (rgba[..., 3] == 255).all()
+    assert (rgba[..., 0] == rgba[..., 1]).all() and (rgba[..., 1] == rgba[..., 2]).all()
+    assert len(np.unique(rgba[..., 0])) <= 8
+    dense, _ = R.raycast(scene, octree=(ref.descriptors, ref.root_index), lifted=False, octenabled=1)
+    assert not np.array_equal(dense, rgba)
