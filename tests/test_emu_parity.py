@@ -181,3 +181,58 @@ def test_multi_light_device_core(pkg, oracle, name, count):
         assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
     diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
     assert not (diff[~tie] > 0).any() and (diff <= 1).all()
+
+
+def random_scene(pkg, rng):
+    """One random scene of the differential fuzz tests (also used on the GPU): 8^3..64^3 maps of random density with
+    mirrors and transparent values, cameras at random / integer / half-integer coordinates and outside the map, random
+    and axis-aligned view directions, 1-3 random lights, max_distance 5 / 20 / 3N.  Returns (scene, light count)."""
+    S = pkg.scene
+    n = int(rng.choice([8, 16, 32, 64]))
+    vol = np.zeros((n, n, n), np.int8)
+    dens = rng.choice([0.002, 0.01, 0.05, 0.2, 0.6])
+    vol[rng.random((n, n, n)) < dens] = 5
+    vol[rng.random((n, n, n)) < dens * 0.3] = 6
+    vol[rng.random((n, n, n)) < 0.02] = int(rng.integers(-5, 9))
+    mode = int(rng.integers(0, 5))
+    pos = (rng.random(3) * n).astype(np.float32)
+    if mode == 1:
+        pos = np.floor(pos).astype(np.float32)
+    if mode == 2:
+        pos = (np.floor(pos) + 0.5).astype(np.float32)
+    if mode == 3:
+        pos = (rng.random(3) * n * 1.5 - 0.25 * n).astype(np.float32)
+    pos = np.clip(pos, -3, n + 3).astype(np.float32)
+    d = np.array([rng.random() * np.pi, rng.random() * 2 * np.pi], np.float32)
+    if mode == 4:
+        d = np.array([rng.choice([0, np.pi / 2, np.pi, 1.57]), rng.choice([0, np.pi / 2, np.pi, 3 * np.pi / 2])], np.float32)
+    nl = int(rng.choice([1, 1, 2, 3]))
+    lights = np.zeros((8, 10), np.float32)
+    for l in range(nl):
+        lights[l] = [rng.random(), rng.random(), rng.random(), rng.random() * 2, *(rng.random(3) * n * 1.2 - 0.1 * n), -1, -1, -1.5]
+    return S.Scene(n, vol, 48, 32, pos, d, lights, max_distance=int(rng.choice([20, 3 * n, 5]))), nl
+
+
+def assert_walk_matches(ref_rgba, ref_aux, rgba, aux, per_axis, what):
+    """all pixels identical; for the per-axis walk the oracle-flagged tie pixels get the north-star tolerance"""
+    tie = ((ref_aux["flags"] & 4) != 0) if per_axis else np.zeros(ref_aux["flags"].shape, bool)
+    for f in ("hit", "face", "status", "hit_type", "steps_first", "steps_total"):
+        assert not (np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie).any(), (what, f)
+    diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(-1)
+    assert not (diff[~tie] > 0).any() and (diff <= 1).all(), what
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_device_core_random_scenes(pkg, oracle, seed):
+    """Differential fuzzing of the device core (host build) against the oracle: 30 random scenes per seed, dense /
+    octree merged walk / per-axis walk, 1-3 lights.  (600 such scenes x 3 walks were run when this was introduced.)"""
+    rng = np.random.default_rng(seed)
+    for it in range(30):
+        scene, nl = random_scene(pkg, rng)
+        table = oracle.make_ray_table(scene.width, scene.height)
+        desc, root = pkg.octree_generate(scene.volume)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl)
+        bias = oracle_bias(oracle, scene, desc, root)
+        for use_svo in (0, 1, 2):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_walk_matches(ref_rgba, ref_aux, rgba, aux, use_svo == 2, f"seed {seed} scene {it} svo {use_svo}")

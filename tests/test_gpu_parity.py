@@ -633,3 +633,25 @@ def test_cuda_equals_reference_kernel_source(pkg, name):
         assert c.compute(), c.last_error()
         assert np.array_equal(c.draw(), ref_rgba), f"{name} use_octree={use_octree}"
         c.close()
+
+
+@pytest.mark.gpu
+def test_cuda_random_scenes(pkg, oracle):
+    """Differential fuzzing on the GPU (kept last in this file): 24 random scenes (see test_emu_parity.random_scene),
+    dense kernel / octree kernel with the merged walk / with the per-axis walk, 1-3 lights, against the oracle."""
+    from test_emu_parity import assert_walk_matches, random_scene
+
+    rng = np.random.default_rng(2)
+    for it in range(24):
+        scene, nl = random_scene(pkg, rng)
+        desc, root = pkg.octree_generate(scene.volume)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=nl)
+        for use_octree in (False, True):
+            c = pkg.CUDACaster()
+            c.load_scene(scene, use_octree=use_octree, shadow_lights=nl)
+            assert c.enable_aux(True) and c.compute(), c.last_error()
+            assert_walk_matches(ref_rgba, ref_aux, c.draw(), c.read_aux(), False, f"scene {it} octree={use_octree}")
+            if use_octree:
+                assert c.set_option("walk", 1) and c.compute()
+                assert_walk_matches(ref_rgba, ref_aux, c.draw(), c.read_aux(), True, f"scene {it} per-axis walk")
+            c.close()
