@@ -178,3 +178,41 @@ def test_golden_fixture(pkg, oracle):
         assert np.array_equal(rgba, z["rgba"]), f.name
         for k in ("hit", "face", "status", "flags", "steps_first", "steps_total"):
             assert np.array_equal(aux[k], z[k]), (f.name, k)
+
+
+def _golden_ref_scene(pkg, name):
+    S = pkg.scene
+    if name == "terrain64-cam3":
+        n = 64
+        vol = S.terrain_map(n, "shell", reflect_fraction=0.05)
+        pos, direction = S.make_camera(n, S.heightfield(n), 3)
+        return S.Scene(n, vol, 256, 144, pos, direction, S.make_lights(n), max_distance=3 * n)
+    return S.make_scene(name)
+
+
+def test_reference_generated_golden_vectors(pkg, oracle):
+    """tests/golden/ref/*.npz were written by the REFERENCE'S OWN kernel and Octree::Generate executed on the CPU
+    (tests/golden/make_golden_ref.py over oracle/_ref, see tests/test_reference_kernel.py): the oracle must reproduce
+    every pixel, the written mask, the root index and every used descriptor -- a pin that needs nothing but git."""
+    import pathlib
+
+    g = pathlib.Path(__file__).parent / "golden" / "ref"
+    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
+    assert len(frames) >= 16
+    for f in frames:
+        z = np.load(f)
+        scene = _golden_ref_scene(pkg, str(z["scene"]))
+        buf, root, _ = oracle.octree_generate(scene.volume, 100000)
+        rgba, aux, _ = oracle.raycast(scene, octree=(buf, root), max_distance=int(z["max_distance"]))
+        assert np.array_equal(rgba, z["rgba"]), f.name
+        skipped = (aux["status"] == 0) | (aux["status"] == 4)
+        assert np.array_equal(z["written"], ~skipped), f.name
+    trees = sorted(g.glob("*-octree.npz"))
+    assert len(trees) >= 3
+    for f in trees:
+        z = np.load(f)
+        scene = _golden_ref_scene(pkg, str(z["scene"]))
+        buf, root, _ = oracle.octree_generate(scene.volume, 100000)
+        first = int(z["first_used"])
+        assert root == int(z["root_index"]) and not buf[:first].any(), f.name
+        assert np.array_equal(buf[first:], z["descriptors"]), f.name
