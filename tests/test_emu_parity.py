@@ -236,3 +236,26 @@ def test_device_core_random_scenes(pkg, oracle, seed):
         for use_svo in (0, 1, 2):
             rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
             assert_walk_matches(ref_rgba, ref_aux, rgba, aux, use_svo == 2, f"seed {seed} scene {it} svo {use_svo}")
+
+
+def test_device_core_equals_reference_generated_golden_vectors(pkg, oracle):
+    """The device core (host build), dense and octree, against the committed outputs of the reference's own kernel
+    (tests/golden/ref): every pixel, and unwritten pixels keep create_viewport's initial fill."""
+    import pathlib
+
+    from test_oracle import _golden_ref_scene
+
+    g = pathlib.Path(__file__).parent / "golden" / "ref"
+    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
+    assert len(frames) >= 16
+    for f in frames:
+        z = np.load(f)
+        scene = _golden_ref_scene(pkg, str(z["scene"]))
+        scene.max_distance = int(z["max_distance"])
+        desc, root = pkg.octree_generate(scene.volume)
+        table = oracle.make_ray_table(scene.width, scene.height)
+        bias = oracle_bias(oracle, scene, desc, root)
+        for use_svo in (0, 1):
+            rgba, _ = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo)
+            assert np.array_equal(rgba, z["rgba"]), (f.name, use_svo)
+            assert (rgba[~z["written"]] == np.array([255, 255, 255, 100], np.uint8)).all()
