@@ -155,52 +155,73 @@ def oracle_sample(scene, row_stride: int, threads: int = 0, lights: int = 1) -> 
     return dt, rays, threads or O.num_procs()
 
 
+class CpuReference:
+    """The reference's CPU implementation of the path on every row_stride-th row of the frame, all host threads.
+    kind "reference": the reference's OWN kernel source (kernels/ray_caster_kernel.cl) compiled for the CPU by g++ through
+    oracle/ref_shim/cl_shim.h (oracle/_ref, built where /root/reference exists; tests/test_reference_kernel.py) -- the
+    `md` build (max_distance lifted to the workload's) for maps up to 256^3, the `wide` build (additionally the kernel's
+    8-entry private stacks widened to 32, kernel:119-124) beyond.  kind "port": the oracle's restatement, when that
+    library is absent, the scene has no dense map (4096^3) or more than one light is requested (extension)."""
+
+    def __init__(self, scene, row_stride: int, lights: int = 1) -> None:
+        self.scene, self.stride, self.lights = scene, row_stride, lights
+        self.kind, self.lib = "port", None
+        self.note = "reference OpenCL kernel restated in C++ (oracle/, no OpenCL runtime in the image)"
+        self.dt0, self.rays, self.threads = oracle_sample(scene, row_stride, lights=lights)      # also the ray count of the sample
+        if lights == 1 and scene.volume is not None:
+            try:
+                sys.path.insert(0, str(ROOT / "tests"))
+                import ref_kernel_lib as R
+
+                build = True if scene.n <= 256 else "wide"
+                if R.available(build):
+                    R.lib(build)                                      # loads (or raises) here, not inside the timed call
+                    octree = package().octree_generate(scene.volume)
+                    self.lib, self.build, self.kind, self.octree = R, build, "reference", octree
+                    self.note = ("kernels/ray_caster_kernel.cl itself, compiled for the CPU by g++ through oracle/ref_shim/cl_shim.h (OpenMP over rows); "
+                                 "max_distance lifted to the workload's" + ("" if build is True else ", private stacks widened 8 -> 32 entries"))
+            except Exception as e:                                    # a missing / unloadable library must not cost the bench line
+                sys.stderr.write(f"bench.py: reference kernel library unusable ({e}); timing the port instead\n")
+                self.lib, self.kind = None, "port"
+
+    def run(self) -> float:
+        """seconds for one pass over the sample"""
+        if self.lib is not None:
+            try:
+                t0 = time.perf_counter()
+                self.lib.raycast(self.scene, octree=self.octree, lifted=self.build, row_stride=self.stride)
+                return time.perf_counter() - t0
+            except Exception as e:
+                sys.stderr.write(f"bench.py: reference kernel run failed ({e}); timing the port instead\n")
+                self.lib, self.kind = None, "port"
+                self.note = "reference OpenCL kernel restated in C++ (oracle/, no OpenCL runtime in the image)"
+        return oracle_sample(self.scene, self.stride, lights=self.lights)[0]
+
+
 def run_reference(args) -> None:
-    """--impl reference: the reference's own CPU implementation of the path.  The OpenCL kernel cannot run in
-    this image (no OpenCL runtime), so this is its C++ restatement (oracle/, kind "port") on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (see CpuReference) on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     scene = bench_scene(args.config, lights=args.lights)
     stride = args.ref_row_stride
-    times, rays = [], 0
-    kind, note = "port", "reference OpenCL kernel restated in C++ (no OpenCL runtime in the image); ms_per_step is for the sample"
-    ref_kernel = None
-    if scene.n <= 256 and args.lights == 1 and scene.volume is not None:
-        # maps the reference kernel can represent (8-entry octree stacks, kernel:119-124): time the REFERENCE'S OWN kernel
-        # source, compiled for the CPU through oracle/ref_shim (oracle/_ref/libref_kernel_md.so), instead of the port
-        sys.path.insert(0, str(ROOT / "tests"))
-        import ref_kernel_lib as R
-
-        if R.available(True):
-            ref_kernel = R
-            kind = "reference"
-            note = ("kernels/ray_caster_kernel.cl itself, compiled for the CPU by g++ through oracle/ref_shim/cl_shim.h (OpenMP over rows), "
-                    "max_distance lifted to the workload's; ms_per_step is for the sample")
-    elif scene.n > 256:
-        note += "; the reference kernel itself cannot represent this map (8-entry octree stacks, kernel:119-124)"
+    cpu = CpuReference(scene, stride, args.lights)
+    times = []
     for i in range(args.warmup + args.steps):
-        if ref_kernel is not None:
-            if i == 0:
-                _, rays, threads = oracle_sample(scene, stride, lights=args.lights)       # ray count of the sample (untimed)
-                desc, root = package().octree_generate(scene.volume)
-            t0 = time.perf_counter()
-            ref_kernel.raycast(scene, octree=(desc, root), lifted=True, row_stride=stride)
-            dt = time.perf_counter() - t0
-        else:
-            dt, rays, threads = oracle_sample(scene, stride, lights=args.lights)
+        dt = cpu.run()
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
+    rays, threads = cpu.rays, cpu.threads
     value = rays / (ms / 1e3) / 1e6
     sample = f"every {stride}th row of the {scene.width}x{scene.height} frame ({rays} rays per step)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain, {scene.width}x{scene.height}, 1 shadow light, dense DDA on CPU",
-                   "note": note},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
+        "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain, {scene.width}x{scene.height}, {args.lights} shadow light{'s' if args.lights > 1 else ''}, dense DDA on CPU",
+                   "note": cpu.note + "; ms_per_step is for the sample"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -588,9 +609,13 @@ def main() -> None:
                         "node_bytes_fetched_per_launch": 16.0 * node_fetches / world}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            dt, sample_rays, threads = oracle_sample(scene, args.cpu_row_stride * (8 if args.config == "c4" else 1), lights=args.lights)
-            cpu = {"value": sample_rays / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                   "sample": f"every {args.cpu_row_stride}th row of the frame ({sample_rays} rays, {dt:.1f} s); dense DDA restatement of the OpenCL kernel"}
+            cpu_stride = args.cpu_row_stride * (8 if args.config == "c4" else 1)
+            ref = CpuReference(scene, cpu_stride, args.lights)
+            dt = min(ref.run(), ref.run()) if ref.lib is not None else ref.dt0
+            if ref.lib is None and ref.kind == "port":
+                dt = min(dt, ref.dt0)
+            cpu = {"value": ref.rays / dt / 1e6, "unit": "Mrays/s", "cores": ref.threads, "kind": ref.kind,
+                   "sample": f"every {cpu_stride}th row of the frame ({ref.rays} rays, {dt:.1f} s); {ref.note}"}
         out = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

@@ -13,12 +13,12 @@
  * known-answer vectors for this path and no OpenCL runtime, SFML or GL exists in the image,
  * but its sources can be compiled for the CPU from where they lie (`make -C oracle ref` -> oracle/_ref/*.so):
  *   - kernels/ray_caster_kernel.cl by g++ through ref_shim/cl_shim.h (OpenCL C vector types, operators and built-ins
- *     in C++; the only edit, by sed on the fly, is the vector-literal syntax `(typeN)(` -> `typeN(`), verbatim and with
- *     kernel:326's max_distance read from a variable;
+ *     in C++; the only edit, by sed on the fly, is the vector-literal syntax `(typeN)(` -> `typeN(`), verbatim, with
+ *     kernel:326's max_distance read from a variable, and with the three 8-entry private stacks widened to 32;
  *   - src/map/Octree.cpp + include/util.hpp with stand-ins for the three SFML headers they include.
  * tests/test_reference_kernel.py requires this restatement to reproduce that code bit for bit: every RGBA8 pixel and
- * the written/skipped mask on 14 scene/camera combinations (HEAD, shadows, reflections, biased camera, 64^3 and 256^3
- * terrain, transparent values), all 100 000 entries of Octree::Generate's buffer and its root index, util.hpp's
+ * the written/skipped mask on 16 scene/camera combinations (HEAD, shadows, reflections, biased camera, 64^3..512^3
+ * terrain, transparent values, the 1024^3 bench frame on sampled rows) and 80 random scenes, all 100 000 entries of Octree::Generate's buffer and its root index, util.hpp's
  * Normalize.  Not pinned by the reference: the OpenCL built-ins below (an OpenCL runtime supplies them; cl_shim.h and
  * this file define them identically) and CLCaster::create_viewport's loop (OpenCL/GL translation unit: restated, its
  * Normalize call pinned).  Further pins: the derived known answers in tests/test_oracle.py and tests/golden/.

@@ -15,12 +15,18 @@ REF_DIR = Path(__file__).resolve().parent.parent / "oracle" / "_ref"
 _libs: dict[str, C.CDLL] = {}
 
 
-def available(lifted: bool = False) -> bool:
-    return (REF_DIR / ("libref_kernel_md.so" if lifted else "libref_kernel.so")).exists()
+def _name(lifted) -> str:
+    """lifted: False = the kernel verbatim; True = max_distance lifted; "wide" = max_distance lifted and the three
+    private stacks widened from 8 to 32 entries (maps deeper than 256^3)"""
+    return {False: "libref_kernel.so", True: "libref_kernel_md.so", "wide": "libref_kernel_wide.so"}[lifted]
 
 
-def lib(lifted: bool) -> C.CDLL:
-    name = "libref_kernel_md.so" if lifted else "libref_kernel.so"
+def available(lifted=False) -> bool:
+    return (REF_DIR / _name(lifted)).exists()
+
+
+def lib(lifted) -> C.CDLL:
+    name = _name(lifted)
     if name not in _libs:
         _libs[name] = C.CDLL(str(REF_DIR / name))
         _libs[name].ref_raycast.restype = C.c_int
@@ -28,8 +34,8 @@ def lib(lifted: bool) -> C.CDLL:
     return _libs[name]
 
 
-def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None, lifted: bool = False,
-            octenabled: int = 1, row_stride: int = 1):
+def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None, lifted=False,
+            octenabled: int = 1, row_stride: int = 1, rows: tuple[int, int] | None = None):
     """One frame through the reference kernel.  lifted=False: the kernel verbatim (max_distance 20, kernel:326);
     lifted=True: max_distance = scene.max_distance.  Returns (rgba prefilled with (255,255,255,100) like host:280-286,
     written mask).  `octree` = (descriptors, root index) in the reference layout; without it a one-entry buffer with an
@@ -38,7 +44,7 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
     if ray_table is None:
         ray_table = O.make_ray_table(w, h)
     ray_table = np.ascontiguousarray(ray_table, np.float32)
-    vol = np.ascontiguousarray(scene.volume, np.int8)
+    vol = scene.volume if (scene.volume.dtype == np.int8 and scene.volume.flags.c_contiguous) else np.ascontiguousarray(scene.volume, np.int8)
     dims = (C.c_int * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
     lights = np.ascontiguousarray(scene.lights, np.float32).copy()
     atlas = np.ascontiguousarray(scene.atlas, np.uint8).copy()
@@ -67,7 +73,7 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
                        rgba.ctypes.data_as(C.c_void_p), written.ctypes.data_as(C.c_void_p), atlas.ctypes.data_as(C.c_void_p),
                        C.c_int(atlas.shape[1]), C.c_int(atlas.shape[0]), C.c_int(scene.tile), C.c_int(scene.tile),
                        desc.ctypes.data_as(C.c_void_p), lookup.ctypes.data_as(C.c_void_p), attach.ctypes.data_as(C.c_void_p),
-                       settings.ctypes.data_as(C.c_void_p), C.c_int(0), C.c_int(h), C.c_int(row_stride))
+                       settings.ctypes.data_as(C.c_void_p), C.c_int(rows[0] if rows else 0), C.c_int(rows[1] if rows else h), C.c_int(row_stride))
     if rc != 0:
         raise RuntimeError(f"ref_raycast failed: {rc}")
     return rgba, written.astype(bool)

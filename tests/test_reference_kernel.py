@@ -197,3 +197,45 @@ def test_oracle_equals_reference_kernel_random_scenes(pkg, oracle, seed):
         o_rgba, o_aux, _ = oracle.raycast(scene, octree=(desc, root))
         r_rgba, written = R.raycast(scene, octree=(desc, root), lifted=True)
         _same(o_rgba, o_aux, r_rgba, written, f"seed {seed} scene {it} (n {n}, mode {mode})")
+
+
+needs_wide = pytest.mark.skipif(not R.available("wide"), reason="oracle/_ref/libref_kernel_wide.so not built")
+
+
+@needs_wide
+def test_oracle_equals_widened_reference_kernel_512(pkg, oracle):
+    """Beyond 256^3 the reference kernel's 8-entry private stacks overflow (kernel:119-124); the `wide` build widens
+    exactly those three arrays to 32 entries (sed, oracle/Makefile) and lifts max_distance.  512^3 terrain (octree
+    depth 9), 480x270, max_distance 1536: all pixels identical."""
+    S = pkg.scene
+    n = 512
+    vol = S.terrain_map(n, "shell")
+    pos, direction = S.make_camera(n, S.heightfield(n), 9)
+    scene = S.Scene(n, vol, 480, 270, pos, direction, S.make_lights(n), max_distance=3 * n)
+    desc, root = pkg.octree_generate(vol)
+    o_rgba, o_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    r_rgba, written = R.raycast(scene, octree=(desc, root), lifted="wide")
+    _same(o_rgba, o_aux, r_rgba, written, "terrain512 wide")
+    assert o_aux["steps_total"].max() > 300
+    # the widened build is the same kernel where the stacks suffice
+    small = S.make_scene("features")
+    d2, r2 = pkg.octree_generate(small.volume)
+    a, wa = R.raycast(small, octree=(d2, r2), lifted="wide")
+    b, wb = R.raycast(small, octree=(d2, r2), lifted=True)
+    assert np.array_equal(a, b) and np.array_equal(wa, wb)
+
+
+@needs_wide
+def test_oracle_equals_widened_reference_kernel_full_size_c3(pkg, oracle):
+    """BASELINE's headline workload itself (1024^3 shell terrain, 3840x2160, max_distance 3072, the bench camera):
+    every 32nd row = 261 120 pixels, rays of up to 2 300 steps, oracle == the reference's own (widened) kernel."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    desc, root = pkg.octree_generate(scene.volume)
+    stride = 32
+    o_rgba, o_aux, _ = oracle.raycast(scene, octree=(desc, root), row_stride=stride)
+    r_rgba, written = R.raycast(scene, octree=(desc, root), lifted="wide", row_stride=stride)
+    rows = slice(0, scene.height, stride)
+    _same(o_rgba[rows], o_aux[rows], r_rgba[rows], written[rows], "c3 sampled rows")
+    assert o_aux["steps_total"][rows].max() > 2000 and ((o_aux["flags"][rows] & 1) != 0).mean() > 0.5
