@@ -616,6 +616,32 @@ def test_tile_interleave_renders_in_place(pkg, oracle, world):
 
 
 @pytest.mark.gpu
+def test_cuda_equals_reference_generated_golden_vectors(pkg):
+    """The committed outputs of the reference's own kernel (tests/golden/ref, written by make_golden_ref.py from
+    oracle/_ref): RGBA8 and the written mask of the dense and octree CUDA kernels, max_distance 20 (verbatim kernel)
+    and the scene's (lifted build)."""
+    import pathlib
+
+    from test_oracle import _golden_ref_scene
+
+    g = pathlib.Path(__file__).parent / "golden" / "ref"
+    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
+    assert len(frames) >= 16
+    for f in frames:
+        z = np.load(f)
+        scene = _golden_ref_scene(pkg, str(z["scene"]))
+        scene.max_distance = int(z["max_distance"])
+        for use_octree in (False, True):
+            c = make_caster(pkg, scene, use_octree, aux=False)
+            assert c.compute(), c.last_error()
+            got = c.draw()
+            assert np.array_equal(got, z["rgba"]), f"{f.name} use_octree={use_octree}"
+            # unwritten pixels keep the initial fill (255,255,255,100) of create_viewport (host:280-286)
+            assert (got[~z["written"]] == np.array([255, 255, 255, 100], np.uint8)).all()
+            c.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["head", "features", "features-low", "features-high", "features-mirror", "small"])
 def test_cuda_equals_reference_kernel_source(pkg, name):
     """Directly against the reference's own kernel source compiled for the CPU (oracle/_ref/libref_kernel_md.so, see
@@ -654,30 +680,4 @@ def test_cuda_random_scenes(pkg, oracle):
             if use_octree:
                 assert c.set_option("walk", 1) and c.compute()
                 assert_walk_matches(ref_rgba, ref_aux, c.draw(), c.read_aux(), True, f"scene {it} per-axis walk")
-            c.close()
-
-
-@pytest.mark.gpu
-def test_cuda_equals_reference_generated_golden_vectors(pkg):
-    """The committed outputs of the reference's own kernel (tests/golden/ref, written by make_golden_ref.py from
-    oracle/_ref): RGBA8 and the written mask of the dense and octree CUDA kernels, max_distance 20 (verbatim kernel)
-    and the scene's (lifted build)."""
-    import pathlib
-
-    from test_oracle import _golden_ref_scene
-
-    g = pathlib.Path(__file__).parent / "golden" / "ref"
-    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
-    assert len(frames) >= 16
-    for f in frames:
-        z = np.load(f)
-        scene = _golden_ref_scene(pkg, str(z["scene"]))
-        scene.max_distance = int(z["max_distance"])
-        for use_octree in (False, True):
-            c = make_caster(pkg, scene, use_octree, aux=False)
-            assert c.compute(), c.last_error()
-            got = c.draw()
-            assert np.array_equal(got, z["rgba"]), f"{f.name} use_octree={use_octree}"
-            # unwritten pixels keep the initial fill (255,255,255,100) of create_viewport (host:280-286)
-            assert (got[~z["written"]] == np.array([255, 255, 255, 100], np.uint8)).all()
             c.close()
