@@ -59,6 +59,7 @@ lookups, pops, loads, hits, replays, chain, fix, rounds, lane_rounds, rays, adds
 model_warp, model_lane = take(2)
 comp = take(8)
 grp_rounds, grp_adds, grp_model, grp_rays = take(8), take(8), take(8), take(8)
+mixed_rounds, alt_warp, alt_small, alt_axes = take(4)
 names = ["none", "brick", "axes", "merged", "merged after axes fallback"]
 print(f"{config} stride {stride}: rays {rays:.0f} (x{stride} = {rays * stride / 1e6:.2f} M), lane-rounds/ray {lane_rounds / rays:.2f}, "
       f"SIMT round efficiency {lane_rounds / (32 * rounds):.3f}")
@@ -75,3 +76,6 @@ print(f"model: warp slots/frame {model_warp * stride / 1e9:.3f} G (ncu smsp__ins
 print("  warp-slot share: " + ", ".join(f"{nm} {100 * v / model_warp:.1f}%" for nm, v in zip(["brick", "axes", "merged", "lookup", "hit", "loop"], comp)))
 print("by tile row mod 8 (4 screen rows each): warp rounds " + " ".join(f"{v / grp_rounds.mean():.3f}" for v in grp_rounds)
       + " | chain work " + " ".join(f"{v / grp_adds.mean():.3f}" for v in grp_adds) + " | model " + " ".join(f"{v / grp_model.mean():.3f}" for v in grp_model))
+print(f"rounds with both a per-axis walk and a small-cell walk in the warp: {100 * mixed_rounds / rounds:.1f} % of {rounds * stride / 1e6:.2f} M warp rounds")
+print(f"phase-batched schedule (small-cell lanes iterate until none is left, then one per-axis cell): model {alt_warp * stride / 1e9:.3f} G warp slots "
+      f"vs {model_warp * stride / 1e9:.3f} G now ({100 * alt_warp / model_warp:.1f} %), iterations small {alt_small * stride / 1e6:.2f} M + axes {alt_axes * stride / 1e6:.2f} M")

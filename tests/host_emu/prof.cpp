@@ -31,6 +31,7 @@ struct Totals {
     double model_warp, model_lane;       /* modelled warp issue slots (SIMT: max per path) and lane slots (sum) */
     double comp_warp[8];
     double grp_rounds[8], grp_adds[8], grp_model[8], grp_rays[8];   /* by (tile row mod 8): screen-row periodicity of the cost */
+    double mixed_rounds, alt_warp, alt_iters_small, alt_iters_axes;  /* phase-batched schedule (see emu_profile) */
 };
 
 static int bucket(int n) { int b = 0; while ((1 << b) < n && b < NH - 1) b++; return b; }
@@ -90,6 +91,8 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
                 nact += active[l];
                 L.rays += active[l];
             }
+            std::vector<Cost> ev[32];           /* per lane: the cost record of every vr_svo_cell call, in order */
+            std::vector<int> evpath[32];
             while (nact) {
                 Cost mx = {0, 0, 0, 0, 0};
                 for (int l = 0; l < 32; l++) {
@@ -106,17 +109,44 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
                     L.lane_rounds += 1;
                     L.grp_adds[by & 7] += p.adds + p.fix + 35 * p.jumps;
                     const Cost c = cost_of(p, model);
+                    ev[l].push_back(c);
+                    evpath[l].push_back(p.path);
                     L.model_lane += c.brick + c.axes + c.merged + c.lookup + c.hit + model[11];
                     mx.brick = fmaxf(mx.brick, c.brick); mx.axes = fmaxf(mx.axes, c.axes); mx.merged = fmaxf(mx.merged, c.merged);
                     mx.lookup = fmaxf(mx.lookup, c.lookup); mx.hit = fmaxf(mx.hit, c.hit);
                     if (rc != VR_CELL_CONTINUE) { active[l] = false; nact--; }
                 }
                 L.rounds += 1;
+                if (mx.axes > 0 && (mx.brick > 0 || mx.merged > 0)) L.mixed_rounds += 1;
                 L.grp_rounds[by & 7] += 1;
                 L.grp_model[by & 7] += mx.brick + mx.axes + mx.merged + mx.lookup + mx.hit + model[11];
                 L.model_warp += mx.brick + mx.axes + mx.merged + mx.lookup + mx.hit + model[11];
                 L.comp_warp[0] += mx.brick; L.comp_warp[1] += mx.axes; L.comp_warp[2] += mx.merged; L.comp_warp[3] += mx.lookup;
                 L.comp_warp[4] += mx.hit; L.comp_warp[5] += model[11];
+            }
+            /* alternative schedule: lanes whose next cell is small (brick / merged walk) iterate together until none is
+             * left in a small cell, then the lanes whose next cell takes the per-axis walk do one cell together, ... */
+            size_t at[32] = {0};
+            for (;;) {
+                bool any_small = false, any_axes = false;
+                for (int l = 0; l < 32; l++) {
+                    if (at[l] >= ev[l].size()) continue;
+                    const int pth = evpath[l][at[l]];
+                    if (pth == P_AXES || pth == P_MERGED_FB) any_axes = true; else any_small = true;
+                }
+                if (!any_small && !any_axes) break;
+                Cost mx = {0, 0, 0, 0, 0};
+                for (int l = 0; l < 32; l++) {
+                    if (at[l] >= ev[l].size()) continue;
+                    const int pth = evpath[l][at[l]];
+                    const bool is_axes = (pth == P_AXES || pth == P_MERGED_FB);
+                    if (any_small ? is_axes : !is_axes) continue;
+                    const Cost &c = ev[l][at[l]++];
+                    mx.brick = fmaxf(mx.brick, c.brick); mx.axes = fmaxf(mx.axes, c.axes); mx.merged = fmaxf(mx.merged, c.merged);
+                    mx.lookup = fmaxf(mx.lookup, c.lookup); mx.hit = fmaxf(mx.hit, c.hit);
+                }
+                L.alt_warp += mx.brick + mx.axes + mx.merged + mx.lookup + mx.hit + model[11];
+                if (any_small) L.alt_iters_small += 1; else L.alt_iters_axes += 1;
             }
         }
 #pragma omp critical
