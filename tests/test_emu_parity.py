@@ -106,7 +106,7 @@ def test_axis_walk_device_core(pkg, oracle, name):
 def test_add_chain_binade_jumps():
     """vr_add_chain evaluates n literal float additions (kernel:559) in closed form per binade: bit-identical
     to the literal chain for random states, for d exactly half way between two grid points of t (ties-to-even
-    alternation), for d below half an ulp of t (t stops moving) and from t = 0."""
+    alternation), for d below half an ulp of t (t stops moving), from t = 0 and from negative t."""
     rng = np.random.default_rng(1)
     n_s = 200000
     t = (rng.random(n_s) * np.exp2(rng.integers(-30, 13, n_s))).astype(np.float32)
@@ -124,6 +124,11 @@ def test_add_chain_binade_jumps():
     u = np.exp2(e - 23.0)
     d2 = (np.floor((1 + rng.random(m) * 3) / u) * u + u / 2).astype(np.float32)
     a, b = emu_lib.add_chain(t2, d2, rng.integers(8, 2000, m).astype(np.int32))
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    # negative start (the get_oct_vox bias of a camera in a collapsed empty cell, kernel:353): |t| shrinks first
+    t3 = (-rng.random(m) * np.exp2(rng.integers(-3, 10, m))).astype(np.float32)
+    d3 = (1.0 / np.maximum(rng.random(m), 1e-3)).astype(np.float32)
+    a, b = emu_lib.add_chain(t3, d3, rng.integers(0, 1500, m).astype(np.int32))
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
 
 
@@ -259,3 +264,38 @@ def test_device_core_equals_reference_generated_golden_vectors(pkg, oracle):
             rgba, _ = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo)
             assert np.array_equal(rgba, z["rgba"]), (f.name, use_svo)
             assert (rgba[~z["written"]] == np.array([255, 255, 255, 100], np.uint8)).all()
+
+
+def test_device_core_random_sparse_maps(pkg, oracle):
+    """Differential fuzzing where the octree cells are huge: 128^3 maps with 0.02-0.5 % random voxels (and sometimes a
+    ground slab), cameras anywhere -- most sit in a collapsed empty cell, so the get_oct_vox bias makes intersection_t
+    start NEGATIVE and the per-axis walk runs chains of hundreds of additions through zero (a case the binade jumps
+    once got wrong).  Octree kernel core, merged and per-axis walk, 1-2 lights, against the oracle."""
+    S = pkg.scene
+    rng = np.random.default_rng(1)
+    n = 128
+    biased = 0
+    for it in range(12):
+        vol = np.zeros((n, n, n), np.int8)
+        dens = rng.choice([0.0002, 0.001, 0.005])
+        vol[rng.random((n, n, n)) < dens] = 5
+        vol[rng.random((n, n, n)) < dens * 0.2] = 6
+        if rng.random() < 0.5:
+            vol[: n // 8] = 5
+        pos = (rng.random(3) * n).astype(np.float32)
+        pos[2] = max(pos[2], n // 8 + 1.3)
+        d = np.array([rng.random() * np.pi, rng.random() * 2 * np.pi], np.float32)
+        nl = int(rng.choice([1, 2]))
+        lights = np.zeros((8, 10), np.float32)
+        for l in range(nl):
+            lights[l] = [rng.random(), rng.random(), rng.random(), 1.0, *(rng.random(3) * n), -1, -1, -1.5]
+        scene = S.Scene(n, vol, 96, 64, pos, d, lights, max_distance=3 * n)
+        table = oracle.make_ray_table(96, 64)
+        desc, root = pkg.octree_generate(vol)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl)
+        bias = oracle_bias(oracle, scene, desc, root)
+        biased += any(b != 0 for b in bias)
+        for use_svo in (1, 2):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_walk_matches(ref_rgba, ref_aux, rgba, aux, use_svo == 2, f"sparse scene {it} svo {use_svo}")
+    assert biased >= 6

@@ -551,7 +551,8 @@ VR_HD float vr_bits2f(int b) {
  * j of them are t + j*dr, which one FMA evaluates exactly (the result is a grid point below 2^(e+1)).  Only the
  * addition that leaves the binade (rounded on the coarser grid) and the case where d falls exactly half way between
  * two grid points (ties-to-even: the increment then depends on the parity of t) are done literally.
- * dr is measured, not derived: two literal additions t1 = t+d, t2 = t1+d, dr = t2 - t1 (exact, same binade). */
+ * dr is measured, not derived: two literal additions t1 = t+d, t2 = t1+d, dr = t2 - t1 (exact, same binade).
+ * All of this holds for t > 0 and d > 0 (t grows); negative t is walked literally until it turns positive. */
 #ifndef VR_JUMP_MIN
 #define VR_JUMP_MIN 64           /* chains at least this long use the jumps (one jump costs about 35 issue slots); 0 = never */
 #endif
@@ -565,8 +566,10 @@ VR_HD float vr_add_chain(float t, float d, int n) {
         t = t2;
         n -= 2;
         VR_PROF_ADD(jumps, 1);
-        const int e1 = vr_f2bits(t1) & 0x7f800000;
-        if ((vr_f2bits(t2) & 0x7f800000) != e1 || e1 < (30 << 23) || e1 >= (250 << 23)) continue;   /* left the binade (or no room for u/2, inf) */
+        const int e1 = vr_f2bits(t1) & (int)0xff800000;      /* sign + exponent: negative for t1 < 0 */
+        /* literal while t is negative (the get_oct_vox start bias, kernel:353, can make it so: |t| then SHRINKS towards
+         * finer grids), when the two additions left the binade, and where u/2 or 2^(e+1) would not be normal numbers */
+        if ((vr_f2bits(t2) & 0x7f800000) != e1 || e1 < (30 << 23) || e1 >= (250 << 23)) continue;
         const float dr = VR_SUB(t2, t1);
         if (fabsf(VR_SUB(dr, d)) == vr_bits2f(e1 - (24 << 23))) break;   /* d is half way between grid points: literal */
         if (dr == 0.0f) return t;                                         /* d < u/2: t no longer moves */
