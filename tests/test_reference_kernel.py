@@ -239,3 +239,23 @@ def test_oracle_equals_widened_reference_kernel_full_size_c3(pkg, oracle):
     rows = slice(0, scene.height, stride)
     _same(o_rgba[rows], o_aux[rows], r_rgba[rows], written[rows], "c3 sampled rows")
     assert o_aux["steps_total"][rows].max() > 2000 and ((o_aux["flags"][rows] & 1) != 0).mean() > 0.5
+
+
+@needs_octree
+def test_octree_generators_on_random_volumes(pkg, oracle):
+    """Random 8^3..32^3 volumes of random density: the oracle's restated generator reproduces Octree::Generate's whole
+    buffer; the product's generator (different layout) and the reference's answer every point query alike."""
+    rng = np.random.default_rng(4)
+    for it in range(12):
+        n = int(rng.choice([8, 16, 32]))
+        vol = (rng.random((n, n, n)) < rng.choice([0.002, 0.05, 0.3, 0.9])).astype(np.int8) * int(rng.choice([5, 6, 3]))
+        ref = R.RefOctree(vol)
+        buf, root, used = oracle.octree_generate(vol, 100000)
+        assert root == ref.root_index and np.array_equal(buf, ref.descriptors), it
+        mine, my_root = pkg.octree_generate(vol)
+        for x, y, z in rng.integers(0, n, size=(200, 3)):
+            a = oracle.get_oct_vox(buf, root, n, (x, y, z))
+            b = oracle.get_oct_vox(mine, my_root, n, (x, y, z))
+            assert a[:3] == b[:3], (it, x, y, z)
+            assert bool(ref.get_voxel(int(x), int(y), int(z))[0]) == bool(a[0]) == bool(vol[z, y, x])
+        ref.close()
