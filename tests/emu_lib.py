@@ -76,3 +76,8 @@ def add_chain(t: np.ndarray, d: np.ndarray, n: np.ndarray):
     fp = C.POINTER(C.c_float)
     lib().emu_add_chain(t.ctypes.data_as(fp), d.ctypes.data_as(fp), n.ctypes.data_as(C.c_void_p), C.c_int(t.size), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
     return a, b
+
+
+def tree_from_ref(desc: np.ndarray, root: int, dim: int):
+    d = np.ascontiguousarray(desc, dtype=np.uint64)
+    return _tree(lib().emu_tree_from_ref, d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size), C.c_uint64(root), C.c_int(dim))

@@ -99,3 +99,11 @@ extern "C" void emu_add_chain(const float *t, const float *d, const int32_t *n, 
         literal[i] = v;
     }
 }
+
+/* importer of reference-format descriptor buffers (what vr_assign_octree alone leads to): occupancy only, type 5 */
+extern "C" long emu_tree_from_ref(const uint64_t *desc, uint64_t len, uint64_t root, int dim, void *nodes, long cap_nodes, uint8_t *types,
+                                  long cap_types, long *ntypes, int *levels) {
+    vr_native_tree t;
+    if (!vr_native_from_ref(desc, len, root, dim, nullptr, t)) return -1;
+    return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
+}

@@ -299,3 +299,19 @@ def test_device_core_random_sparse_maps(pkg, oracle):
             rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
             assert_walk_matches(ref_rgba, ref_aux, rgba, aux, use_svo == 2, f"sparse scene {it} svo {use_svo}")
     assert biased >= 6
+
+
+def test_reference_octree_importer_random_volumes(pkg):
+    """vr_native_from_ref (what `assign_octree` without `assign_map` leads to): the 64-tree imported from a reference-
+    format descriptor buffer equals the one built from the dense map (all solids typed 5) -- random volumes, including
+    one whose buffer needs far pointers (> 32k descriptors, kernel:222-225) and a root wider than the map (32^3)."""
+    rng = np.random.default_rng(9)
+    for n, dens in ((8, 0.3), (16, 0.05), (32, 0.02), (32, 0.6), (64, 0.01), (128, 0.02)):
+        vol = (rng.random((n, n, n)) < dens).astype(np.int8) * 5
+        desc, root = pkg.octree_generate(vol)
+        if n == 128:
+            assert desc.size > 0x8000
+        a = emu_lib.tree_from_dense(vol)
+        b = emu_lib.tree_from_ref(desc, root, n)
+        assert a[2] == b[2] and a[0].shape == b[0].shape
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (n, dens)
