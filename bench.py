@@ -31,6 +31,14 @@ ROOT = Path(__file__).resolve().parent
 METRIC = "Mrays/s (primary + shadow rays), 1024^3 SVO @ 3840x2160 + shadows"
 BAND_ROWS = int(os.environ.get("VR_BAND_ROWS", "8"))   # rows per interleaved band (multiple of the 4-row CTA tile)
 BENCH_CAMERA = 9            # make_camera(index): terrain + sky + shadowed pixels
+WALK_NAMES = {0: "merged", 1: "per-axis", 2: "closed-form"}
+WALK_NOTES = {
+    0: "merged in-cell walk, literal additions: bit-identical to the reference restatement on every pixel",
+    1: "per-axis in-cell walk, literal additions: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)",
+    2: "closed-form crossing times t(k) = fma(k, delta_t, t0) (SURVEY Appendix E): identical to the oracle's restatement of that form except distance_traveled on exact-tie "
+       "rays; against the reference walk RGBA8 within +-1 on 99.98 % of the pixels and first hit / face identical outside the degenerate (voxel-edge) rays "
+       "(tests/test_gpu_canonical.py, DESIGN.md section 2)",
+}
 
 
 def package():
@@ -314,7 +322,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
             "gpu_launches": int(launches),
             "config": {"workload": "c5: 64 random cameras x 1920x1080, 1024^3 shell terrain SVO, primary + 1 shadow light (BASELINE configs[4], not the headline)",
                        "parallelism": f"views{world}: view v on rank v % {world}", "views": views, "rays_per_batch": rays,
-                       "walk": "per-axis" if args.walk == 1 else "merged",
+                       "walk": WALK_NAMES[args.walk],
                        "ms_per_view": ms / (views / world) if world else None},
             "roofline": None, "cpu_baseline": None,
             "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
@@ -342,7 +350,10 @@ def main() -> None:
     ap.add_argument("--refill-min", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
     ap.add_argument("--l2-persist", type=int, default=0, help="1 = cudaAccessPolicyWindow over the octree nodes")
-    ap.add_argument("--walk", type=int, default=1, help="in-cell walk of the octree kernel: 1 = per-axis (default here; exact except the step count of exact-tie rays), 0 = merged (bit-identical on every pixel; the library default)")
+    ap.add_argument("--walk", type=int, default=2, choices=[0, 1, 2],
+                    help="in-cell walk of the octree kernel: 2 = closed-form crossing times (default: within BASELINE.json's tolerance of the reference walk, "
+                    "see DESIGN.md section 2), 1 = literal additions walked per axis (exact except the step count of exact-tie rays), "
+                    "0 = literal additions, merged walk (bit-identical to the reference on every pixel)")
     ap.add_argument("--overlap-frames", type=int, default=1, help="N > 1: 1 = consecutive frames are launched on two alternating streams (the next frame's "
                     "first CTAs fill the tail of the current one); the kernel events then overlap, so roofline.kernel_ms is the step time")
     ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
@@ -528,18 +539,22 @@ def main() -> None:
         kernel_ms = ms_per_step      # launches of consecutive frames overlap: effective duration per launch
     value = rays / (ms_per_step / 1e3) / 1e6
 
-    # the other in-cell walk, for the record (a few untimed-region frames, kernel only)
+    # the other in-cell walks, for the record (a few frames outside the timed region, kernel only)
     other_walk_ms = None
     if use_svo and world == 1:
-        must(c.set_option("walk", 1 - args.walk), "walk")
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(3 + 10):
-            if i == 3:
-                o0.record(stream)
-            must(c.compute_into(slab.data_ptr()), "compute_into")
-        o1.record(stream)
-        torch.cuda.synchronize()
-        other_walk_ms = o0.elapsed_time(o1) / 10
+        other_walk_ms = {}
+        for w in (0, 1, 2):
+            if w == args.walk:
+                continue
+            must(c.set_option("walk", w), "walk")
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(3 + 10):
+                if i == 3:
+                    o0.record(stream)
+                must(c.compute_into(slab.data_ptr()), "compute_into")
+            o1.record(stream)
+            torch.cuda.synchronize()
+            other_walk_ms[WALK_NAMES[w]] = o0.elapsed_time(o1) / 10
         must(c.set_option("walk", args.walk), "walk")
 
     # ---- end to end through the public API with HOST buffers: camera/lights are read from host memory at every
@@ -622,7 +637,7 @@ def main() -> None:
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
                        "mode": args.mode,
-                       "walk": ("per-axis in-cell walk: identical to the reference restatement except distance_traveled on exact-tie rays (degenerate, ~0.9 % of pixels, RGBA +-1)" if args.walk == 1 else "merged in-cell walk: bit-identical to the reference restatement on every pixel") if use_svo else "dense DDA",
+                       "walk": WALK_NOTES[args.walk] if use_svo else "dense DDA",
                        "other_walk_ms_per_frame": other_walk_ms,
                        "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",

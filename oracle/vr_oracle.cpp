@@ -267,6 +267,25 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
      * caller evaluates it once and passes ((sub_oct_pos - voxel) * resolution) / 2 as `bias`. */
     t.x += (float)bias.x; t.y += (float)bias.y; t.z += (float)bias.z;
 
+    /* PARITY-CHAIN LINK "Oracle-B" (SURVEY Appendix E), not part of the reference: the crossing times of an axis in
+     * closed form, t(k) = fma(k, delta_t, t0) with k the crossings made since the ray (re)started and t0 the value
+     * intersection_t had then.  With s->canonical_t != 0 the walk below USES them instead of the accumulated sums of
+     * kernel:559 (what the octree kernel's walk = 2 computes); with canonical_t == 0 (the reference) they are only
+     * evaluated next to the real ones to flag VRO_FL_NEAR: some step of this ray would have been taken along other
+     * axes under the closed form, i.e. two crossing times are closer than the rounding the additions accumulate --
+     * the ray passes within float noise of a voxel edge (BASELINE.json: "degenerate" rays). */
+    const bool canon = s->canonical_t != 0;
+    f3 t0 = t, tc = t;
+    float kx = 0.0f, ky = 0.0f, kz = 0.0f;
+    auto restart_canon = [&]() { t0 = t; tc = t; kx = ky = kz = 0.0f; };
+    auto blocked_at = [&](const i3 &v) -> bool {      /* set (5 / 6) or outside the map */
+        if (v.x < 0 || v.y < 0 || v.z < 0 || v.x >= s->map_dim[0] || v.y >= s->map_dim[1] || v.z >= s->map_dim[2]) return true;
+        int d;
+        if (s->map) d = (int)s->map[(size_t)v.x + (size_t)s->map_dim[0] * ((size_t)v.y + (size_t)s->map_dim[2] * (size_t)v.z)];
+        else { const size_t c = (size_t)v.x + (size_t)s->map_dim[0] * (size_t)v.y; d = (v.z >= s->col_lo[c] && v.z <= s->col_hi[c]) ? 5 : 0; }
+        return d == 5 || d == 6;
+    };
+
     CellTrack cell;
     if (COUNT && count_svo) svo_lookup(s, voxel, cell, k);                /* the camera-voxel descent */
 
@@ -307,6 +326,7 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
         t.x += delta_t.x * ((t.x < 0.0f) ? 1.0f : -0.0f);
         t.y += delta_t.y * ((t.y < 0.0f) ? 1.0f : -0.0f);
         t.z += delta_t.z * ((t.z < 0.0f) ? 1.0f : -0.0f);
+        restart_canon();
         if (COUNT && count_svo) { cell = CellTrack(); svo_lookup(s, voxel, cell, k); }
         return true;
     };
@@ -325,9 +345,24 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
         face_mask.y = (t.y <= cl_min(t.z, t.x)) ? 1 : 0;
         face_mask.z = (t.z <= cl_min(t.x, t.y)) ? 1 : 0;
         if (face_mask.x + face_mask.y + face_mask.z > 1) a.flags |= VRO_FL_TIE;
+        if (!canon) {
+            const int cx = (tc.x <= cl_min(tc.y, tc.z)) ? 1 : 0, cy = (tc.y <= cl_min(tc.z, tc.x)) ? 1 : 0,
+                      cz = (tc.z <= cl_min(tc.x, tc.y)) ? 1 : 0;
+            if (cx != face_mask.x || cy != face_mask.y || cz != face_mask.z) {
+                /* the two evaluation orders step differently here.  That is only visible if one of the two voxels
+                 * entered is set or outside the map; between empty voxels the two paths meet again a step later */
+                const i3 va = {voxel.x + voxel_step.x * face_mask.x, voxel.y + voxel_step.y * face_mask.y, voxel.z + voxel_step.z * face_mask.z};
+                const i3 vb = {voxel.x + voxel_step.x * cx, voxel.y + voxel_step.y * cy, voxel.z + voxel_step.z * cz};
+                a.flags |= (blocked_at(va) || blocked_at(vb)) ? VRO_FL_NEAR : VRO_FL_NEAR_AIR;
+            }
+        }
         t.x += delta_t.x * (float)face_mask.x;                            /* kernel:559 */
         t.y += delta_t.y * (float)face_mask.y;
         t.z += delta_t.z * (float)face_mask.z;
+        if (face_mask.x) { kx += 1.0f; tc.x = fmaf(kx, delta_t.x, t0.x); }
+        if (face_mask.y) { ky += 1.0f; tc.y = fmaf(ky, delta_t.y, t0.y); }
+        if (face_mask.z) { kz += 1.0f; tc.z = fmaf(kz, delta_t.z, t0.z); }
+        if (canon) t = tc;
         voxel.x += voxel_step.x * face_mask.x;                            /* kernel:560 */
         voxel.y += voxel_step.y * face_mask.y;
         voxel.z += voxel_step.z * face_mask.z;
@@ -444,6 +479,7 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
                 t.x += delta_t.x * ((t.x < 0.0f) ? 1.0f : -0.0f);         /* kernel:679 */
                 t.y += delta_t.y * ((t.y < 0.0f) ? 1.0f : -0.0f);
                 t.z += delta_t.z * ((t.z < 0.0f) ? 1.0f : -0.0f);
+                restart_canon();
             } else if (voxel_data == 6 && !shadow_ray) {                  /* kernel:682 */
                 a.flags |= VRO_FL_REFLECTED;
                 bool clamped = false;
@@ -475,6 +511,7 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
                 t.x += delta_t.x * ((t.x < 0.0f) ? 1.0f : -0.0f);         /* kernel:702 */
                 t.y += delta_t.y * ((t.y < 0.0f) ? 1.0f : -0.0f);
                 t.z += delta_t.z * ((t.z < 0.0f) ? 1.0f : -0.0f);
+                restart_canon();
                 bounce_count += 1;                                        /* kernel:704 */
             } else {                                                      /* kernel:707 */
                 color.w = alpha_before + 0.1f;                            /* one light: 0 + 0.1 = kernel:708 */

@@ -75,6 +75,10 @@ typedef struct vro_scene {
      * only the `map[...]` load of kernel:569 is answered by the column table. */
     const int32_t *col_lo;
     const int32_t *col_hi;
+    /* 0 = the reference (kernel:559: intersection_t accumulates one rounded addition per step).  1 = "Oracle-B" of the
+     * parity chain: crossing times in closed form, t(k) = fma(k, delta_t, t0) -- the arithmetic of
+     * the octree kernel's walk = 2.  Not part of the reference; see vr_oracle.cpp. */
+    int32_t canonical_t;
 } vro_scene;
 
 /* Per-pixel auxiliary record, 32 bytes.  The reference kernel only writes RGBA8; these expose
@@ -103,7 +107,12 @@ enum {
     VRO_FL_REFLECTED = 2,      /* at least one type-6 reflection                                     */
     VRO_FL_TIE       = 4,      /* some DDA step moved along more than one axis (exact t tie)         */
     VRO_FL_ATLAS_CLAMP = 8,    /* atlas texel coordinate fell outside the image and was clamped      */
-    VRO_FL_FRAC0     = 16      /* a camera position component is an exact integer                    */
+    VRO_FL_FRAC0     = 16,     /* a camera position component is an exact integer                    */
+    VRO_FL_NEAR      = 32,     /* (canonical_t == 0 only) some step would be taken along other axes under closed-form
+                                * crossing times -- two crossing times closer than the accumulated rounding: the ray
+                                * passes a voxel edge within float noise -- AND one of the two voxels entered is set or
+                                * outside the map, so the difference can show (BASELINE.json: "degenerate" ray)       */
+    VRO_FL_NEAR_AIR  = 64      /* same, between empty voxels: the two paths meet again one step later (statistics)   */
 };
 
 /* Whole-frame counters (SURVEY 8d byte model). */

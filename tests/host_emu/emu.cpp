@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../voxel-raycaster_b200/csrc/vr_trace.h"
+#include "../../voxel-raycaster_b200/csrc/vr_canon.h"
 #include "../../voxel-raycaster_b200/csrc/vr_octree.h"
 
 struct LocalStack {
@@ -52,11 +53,13 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
             bool w;
             LocalStack s;
             if (P.light_count > 1) {
-                if (use_svo == 2) w = vr_trace_svo<true, 1, true>(P, x, y, &px, &a, s);
+                if (use_svo == 3) w = vr_trace_svo_canon<true, true>(P, x, y, &px, &a, s);
+                else if (use_svo == 2) w = vr_trace_svo<true, 1, true>(P, x, y, &px, &a, s);
                 else if (use_svo) w = vr_trace_svo<true, 0, true>(P, x, y, &px, &a, s);
                 else w = vr_trace_dense<true, true>(P, x, y, &px, &a);
             } else {
-                if (use_svo == 2) w = vr_trace_svo<true, 1, false>(P, x, y, &px, &a, s);
+                if (use_svo == 3) w = vr_trace_svo_canon<true, false>(P, x, y, &px, &a, s);
+                else if (use_svo == 2) w = vr_trace_svo<true, 1, false>(P, x, y, &px, &a, s);
                 else if (use_svo) w = vr_trace_svo<true, 0, false>(P, x, y, &px, &a, s);
                 else w = vr_trace_dense<true, false>(P, x, y, &px, &a);
             }

@@ -16,7 +16,7 @@ ORACLE_DIR = ROOT / "oracle"
 _lib = None
 
 ST_SKIP_PRIMARY, ST_OOB, ST_MAXDIST, ST_SHADOW_HIT, ST_SKIP_REDIRECT, ST_BOUNCES = range(6)
-FL_LIT, FL_REFLECTED, FL_TIE, FL_ATLAS_CLAMP, FL_FRAC0 = 1, 2, 4, 8, 16
+FL_LIT, FL_REFLECTED, FL_TIE, FL_ATLAS_CLAMP, FL_FRAC0, FL_NEAR, FL_NEAR_AIR = 1, 2, 4, 8, 16, 32, 64
 
 AUX_DTYPE = np.dtype([
     ("hit", "<i4", (3,)), ("face", "u1"), ("status", "u1"), ("flags", "u1"), ("hit_type", "u1"),
@@ -36,6 +36,7 @@ class VroScene(C.Structure):
         ("octdim", C.c_int64), ("oct_root_index", C.c_int64),
         ("max_distance", C.c_int32), ("shadow_lights", C.c_int32),
         ("col_lo", C.POINTER(C.c_int32)), ("col_hi", C.POINTER(C.c_int32)),
+        ("canonical_t", C.c_int32),
     ]
 
 
@@ -111,7 +112,7 @@ def trig_of(cam_dir) -> np.ndarray:
 def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None,
             rows: tuple[int, int] | None = None, want_aux: bool = True, want_counters: bool = False,
             count_svo: bool = False, threads: int = 0, max_distance: int | None = None, row_stride: int = 1,
-            shadow_lights: int = 1):
+            shadow_lights: int = 1, canonical_t: bool = False, keep_near: bool = False):
     """Runs the restated reference kernel (dense branch) on a scene.Scene.
     Returns (rgba [H,W,4] prefilled with (255,255,255,100), aux or None, counters dict or None)."""
     w, h = scene.width, scene.height
@@ -149,6 +150,7 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
     s.octdim = scene.n
     s.max_distance = scene.max_distance if max_distance is None else max_distance
     s.shadow_lights = shadow_lights          # 1 = the reference (light 0 only); > 1 = the multi-light extension
+    s.canonical_t = 1 if canonical_t else 0  # False = the reference; True = "Oracle-B" (closed-form crossing times)
     rgba = np.empty((h, w, 4), dtype=np.uint8)
     rgba[...] = (255, 255, 255, 100)
     aux = np.zeros((h, w), dtype=AUX_DTYPE) if want_aux else None
@@ -159,6 +161,8 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
                            C.byref(counters) if counters is not None else None, int(count_svo), threads)
     if rc != 0:
         raise RuntimeError(f"vro_raycast failed: {rc}")
+    if aux is not None and not keep_near:
+        aux["flags"] &= np.uint8(~(FL_NEAR | FL_NEAR_AIR) & 0xFF)   # the near-tie classifier is only of interest to the walk = 2 tests
     return rgba, aux, (counters.as_dict() if counters is not None else None)
 
 

@@ -1,0 +1,180 @@
+"""GPU parity tests of the octree kernel's closed-form walk (option walk = 2, voxel-raycaster_b200/csrc/vr_canon.h).
+
+Parity chain, each link asserted here through the C ABI:
+  (B) CUDA walk = 2  ==  "Oracle-B" = the oracle with closed-form crossing times (oracle_lib.raycast(canonical_t=True)):
+      RGBA8 and every integer aux field identical on every pixel whose ray makes no exact multi-axis (tie) step; on
+      the tie pixels (flag VRO_FL_TIE of Oracle-B) the same first hit and RGBA8 within +-1 (a tie between two crossings
+      strictly inside an empty octree cell is not observed: distance_traveled is then one larger per such tie).
+  (A) CUDA walk = 2  vs  the reference walk (Oracle-A, pinned to the reference's own kernel source in
+      test_reference_kernel.py), BASELINE.json's bar, asserted at the headline size with the numbers printed:
+      first-hit voxel, face and type bit-exact on every non-degenerate ray -- degenerate = VRO_FL_TIE (exact tie) or
+      VRO_FL_NEAR (a step that the two evaluation orders take along different axes next to a set voxel or the map
+      boundary: the ray passes a voxel edge within float noise) -- and RGBA8 max abs diff <= 1 on >= 99.9 % of pixels.
+"""
+import numpy as np
+import pytest
+
+from test_gpu_parity import SMALL, make_caster
+
+pytestmark = pytest.mark.gpu
+
+HIT_FIELDS = ("hit", "face", "hit_type")
+INT_FIELDS = ("hit", "face", "status", "hit_type", "steps_first", "steps_total")
+
+
+def assert_equals_oracle_b(ref_rgba, ref_aux, rgba, aux, what):
+    tie = (ref_aux["flags"] & 4) != 0
+    for f in INT_FIELDS:
+        bad = np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1) & ~tie
+        assert not bad.any(), f"{what}: {f} differs on {int(bad.sum())} non-tie pixels, first (y,x)={np.argwhere(bad)[0]}"
+    bad = ((ref_aux["flags"] & 0xFB) != (aux["flags"] & 0xFB)) & ~tie
+    assert not bad.any(), f"{what}: flags differ on non-tie pixels"
+    diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(axis=-1)
+    assert not (diff[~tie] > 0).any(), f"{what}: RGBA differs on {int((diff[~tie] > 0).sum())} non-tie pixels"
+    assert (diff <= 1).all(), f"{what}: a tie pixel beyond +-1 (max {int(diff.max())})"
+    for f in HIT_FIELDS:
+        assert np.array_equal(ref_aux[f], aux[f]), f"{what}: first hit ({f}) differs on a tie pixel"
+    return int(tie.sum())
+
+
+def north_star_statistic(ref_rgba, ref_aux, rgba, aux):
+    """(share of pixels with RGBA max-abs-diff > 1, first-hit mismatches outside the degenerate flags, degenerate share)"""
+    deg = (ref_aux["flags"] & (4 | 32)) != 0
+    diff = np.abs(ref_rgba.astype(np.int16) - rgba.astype(np.int16)).max(axis=-1)
+    hit_bad = np.zeros(deg.shape, bool)
+    for f in HIT_FIELDS:
+        hit_bad |= np.any(np.atleast_3d(ref_aux[f] != aux[f]), axis=-1)
+    return float((diff > 1).mean()), int((hit_bad & ~deg).sum()), int(hit_bad.sum()), float(deg.mean())
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_canonical_walk_small(pkg, oracle, name):
+    scene = pkg.scene.make_scene(name)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), canonical_t=True)
+    c = make_caster(pkg, scene, True)
+    assert c.set_option("walk", 2) and c.compute(), c.last_error()
+    assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 {name}")
+    c.close()
+
+
+def test_canonical_walk_terrain(pkg, oracle):
+    """64^3 with 5 % mirrors at 1280x720 and 256^3 at 1080p (BASELINE configs[0] / [1] sizes), one and two lights."""
+    S = pkg.scene
+    for n, w, h, cam, lights in ((64, 1280, 720, 3, 1), (256, 1920, 1080, 4, 1), (256, 960, 540, 2, 2)):
+        vol = S.terrain_map(n, "shell", reflect_fraction=0.05 if n == 64 else 0.0)
+        pos, direction = S.make_camera(n, S.heightfield(n), cam)
+        scene = S.Scene(n, vol, w, h, pos, direction, S.make_lights(n, lights), max_distance=3 * n)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, shadow_lights=lights, canonical_t=True)
+        c = pkg.CUDACaster()
+        c.load_scene(scene, use_octree=True, assign_octree=False, shadow_lights=lights)
+        assert c.enable_aux(True) and c.set_option("walk", 2) and c.compute(), c.last_error()
+        ties = assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 terrain {n} lights {lights}")
+        print(f"terrain {n}: {ties} tie pixels")
+        c.close()
+
+
+def test_canonical_walk_full_size_c3(pkg, oracle):
+    """The headline frame (1024^3, 3840x2160, bench camera), every 24th row: == Oracle-B, and BASELINE.json's bar
+    against the reference walk with the statistic printed."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    c = make_caster(pkg, scene, True, assign_octree=False)
+    assert c.set_option("walk", 2) and c.compute(), c.last_error()
+    rgba, aux = c.draw(), c.read_aux()
+    assert c.compute() and np.array_equal(c.draw(), rgba)                 # deterministic
+    c.close()
+    k = 24
+    b_rgba, b_aux, _ = oracle.raycast(scene, row_stride=k, canonical_t=True)
+    ties = assert_equals_oracle_b(b_rgba[::k], b_aux[::k], rgba[::k], aux[::k], "walk 2 c3 rows vs Oracle-B")
+    a_rgba, a_aux, _ = oracle.raycast(scene, row_stride=k, keep_near=True)
+    gt1, hit_out, hit_all, deg = north_star_statistic(a_rgba[::k], a_aux[::k], rgba[::k], aux[::k])
+    print(f"c3 walk 2 vs reference walk on {rgba[::k].shape[0] * rgba.shape[1]} pixels: RGBA diff > 1 on {100 * gt1:.4f} % "
+          f"(bar: <= 0.1 %), first-hit mismatches {hit_all} of which outside the degenerate flags {hit_out} (bar: 0), "
+          f"degenerate rays {100 * deg:.3f} %, tie pixels vs Oracle-B {ties}")
+    assert gt1 <= 1e-3 and hit_out == 0 and deg < 0.02
+
+
+def test_per_axis_walk_full_size_c3_vs_oracle(pkg, oracle):
+    """walk = 1 (literal additions, per-axis chains) against the ORACLE itself at the headline size, every 24th row
+    (the round-1 suite compared it with walk = 0 on the GPU only): identical outside the exact-tie pixels; on those the
+    same first hit and RGBA8 within +-1.  Prints BASELINE.json's statistic."""
+    import bench
+
+    scene = bench.bench_scene("c3")
+    c = make_caster(pkg, scene, True, assign_octree=False)
+    assert c.set_option("walk", 1) and c.compute(), c.last_error()
+    rgba, aux = c.draw(), c.read_aux()
+    c.close()
+    k = 24
+    a_rgba, a_aux, _ = oracle.raycast(scene, row_stride=k)
+    ties = assert_equals_oracle_b(a_rgba[::k], a_aux[::k], rgba[::k], aux[::k], "walk 1 c3 rows vs oracle")
+    gt1, hit_out, hit_all, deg = north_star_statistic(a_rgba[::k], a_aux[::k], rgba[::k], aux[::k])
+    print(f"c3 walk 1 vs reference walk: RGBA diff > 1 on {100 * gt1:.4f} %, first-hit mismatches {hit_all}, tie pixels {ties}")
+    assert gt1 == 0.0 and hit_all == 0 and ties > 0
+
+
+def test_canonical_walk_random_scenes(pkg, oracle):
+    """Differential fuzzing: 40 random scenes (maps 8^3..64^3, cameras inside / on integer coordinates / outside the
+    map, axis-aligned directions, 1-3 lights, max_distance 5 / 20 / 3N) against Oracle-B."""
+    from test_emu_parity import random_scene
+
+    rng = np.random.default_rng(5)
+    for it in range(40):
+        scene, nl = random_scene(pkg, rng)
+        desc, root = pkg.octree_generate(scene.volume)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+        c = pkg.CUDACaster()
+        c.load_scene(scene, use_octree=True, shadow_lights=nl)
+        assert c.enable_aux(True) and c.set_option("walk", 2) and c.compute(), c.last_error()
+        assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 random scene {it}")
+        c.close()
+
+
+def sparse_scene(pkg, rng, n):
+    """a sparse n^3 map (0.02-0.5 % random voxels, sometimes a ground slab) and a camera anywhere in it: most cameras sit
+    in a collapsed empty octree cell, so the get_oct_vox bias (kernel:353) makes intersection_t start negative and the
+    walks cross cells hundreds of voxels wide"""
+    S = pkg.scene
+    vol = np.zeros((n, n, n), np.int8)
+    dens = rng.choice([0.0002, 0.001, 0.005])
+    vol[rng.random((n, n, n)) < dens] = 5
+    vol[rng.random((n, n, n)) < dens * 0.2] = 6
+    if rng.random() < 0.5:
+        vol[: n // 8] = 5
+    pos = (rng.random(3) * n).astype(np.float32)
+    pos[2] = max(pos[2], n // 8 + 1.3)
+    d = np.array([rng.random() * np.pi, rng.random() * 2 * np.pi], np.float32)
+    nl = int(rng.choice([1, 2]))
+    lights = np.zeros((8, 10), np.float32)
+    for l in range(nl):
+        lights[l] = [rng.random(), rng.random(), rng.random(), 1.0, *(rng.random(3) * n), -1, -1, -1.5]
+    return S.Scene(n, vol, 192, 128, pos, d, lights, max_distance=3 * n), nl
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_sparse_maps_all_walks(pkg, oracle, n):
+    """GPU fuzz on sparse 128^3 / 256^3 maps with cameras in collapsed empty cells (negative intersection_t, add chains
+    beyond VR_JUMP_MIN = 64: the case the binade jumps of walk = 1 once got wrong, found on the CPU only in round 1):
+    walk 0 == oracle on all pixels, walk 1 == oracle except ties, walk 2 == Oracle-B except ties."""
+    from conftest import assert_same_frame, oracle_bias
+
+    rng = np.random.default_rng(100 + n)
+    biased = 0
+    for it in range(6 if n == 128 else 3):
+        scene, nl = sparse_scene(pkg, rng, n)
+        desc, root = pkg.octree_generate(scene.volume)
+        biased += any(b != 0 for b in oracle_bias(oracle, scene, desc, root))
+        a_rgba, a_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=nl)
+        b_rgba, b_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+        c = pkg.CUDACaster()
+        c.load_scene(scene, use_octree=True, shadow_lights=nl)
+        assert c.enable_aux(True) and c.set_option("walk", 0) and c.compute(), c.last_error()
+        assert_same_frame(a_rgba, a_aux, c.draw(), c.read_aux(), f"sparse {n} scene {it} walk 0")
+        assert c.set_option("walk", 1) and c.compute()
+        assert_equals_oracle_b(a_rgba, a_aux, c.draw(), c.read_aux(), f"sparse {n} scene {it} walk 1")
+        assert c.set_option("walk", 2) and c.compute()
+        assert_equals_oracle_b(b_rgba, b_aux, c.draw(), c.read_aux(), f"sparse {n} scene {it} walk 2")
+        c.close()
+    assert biased >= 2

@@ -284,7 +284,7 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
     /* the per-axis walk sizes its add chains from a closed-form estimate whose error grows with ulp(t) (vr_count_before:
      * < 0.2 crossings up to 4096^3, where it is tested); beyond 16384^3 the merged walk is used whatever the option says */
     vr_launch_options opt = c->opt;
-    if (P.dim[0] > 16384) opt.walk = 0;
+    if (P.dim[0] > 16384 && opt.walk == 1) opt.walk = 0;
     VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &opt));
     if (timed) {
         VR_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
@@ -757,7 +757,7 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     if (n == "persistent") c->opt.persistent = value != 0;
     else if (n == "refill_min") c->opt.refill_min = value < 1 ? 1 : (value > 32 ? 32 : (int)value);
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
-    else if (n == "walk") c->opt.walk = value == 1 ? 1 : 0;
+    else if (n == "walk") c->opt.walk = (value == 1 || value == 2) ? (int)value : 0;
     else if (n == "gpu_build") c->gpu_build = value != 0;        /* 0: assign_map builds the 64-tree on the host */
     else if (n == "l2_persist") {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */

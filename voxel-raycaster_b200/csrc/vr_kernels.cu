@@ -15,6 +15,7 @@
 
 #include "vr_kernels.h"
 #include "vr_trace.h"
+#include "vr_canon.h"
 
 namespace {
 
@@ -99,7 +100,8 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     SmemStack stk{stack + threadIdx.x};
     uint32_t rgba;
     vr_aux a;
-    const bool write = vr_trace_svo<AUX, WALK, MULTI>(P, x, y, &rgba, &a, stk);
+    const bool write = WALK == 2 ? vr_trace_svo_canon<AUX, MULTI>(P, x, y, &rgba, &a, stk)
+                                 : vr_trace_svo<AUX, (WALK == 2 ? 0 : WALK), MULTI>(P, x, y, &rgba, &a, stk);
     if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
@@ -195,12 +197,14 @@ cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_au
         if (aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
         else vr_svo_persistent_kernel<false><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
     } else if (use_svo) {
-        const int walk = (opt && opt->walk == 1) ? 1 : 0;
+        const int walk = opt ? opt->walk : 0;
         void (*k)(vr_frame_params) =
-            walk ? (multi ? (aux ? vr_svo_kernel<true, 1, true> : vr_svo_kernel<false, 1, true>)
-                          : (aux ? vr_svo_kernel<true, 1, false> : vr_svo_kernel<false, 1, false>))
-                 : (multi ? (aux ? vr_svo_kernel<true, 0, true> : vr_svo_kernel<false, 0, true>)
-                          : (aux ? vr_svo_kernel<true, 0, false> : vr_svo_kernel<false, 0, false>));
+            walk == 2 ? (multi ? (aux ? vr_svo_kernel<true, 2, true> : vr_svo_kernel<false, 2, true>)
+                               : (aux ? vr_svo_kernel<true, 2, false> : vr_svo_kernel<false, 2, false>))
+            : walk == 1 ? (multi ? (aux ? vr_svo_kernel<true, 1, true> : vr_svo_kernel<false, 1, true>)
+                                 : (aux ? vr_svo_kernel<true, 1, false> : vr_svo_kernel<false, 1, false>))
+                        : (multi ? (aux ? vr_svo_kernel<true, 0, true> : vr_svo_kernel<false, 0, true>)
+                                 : (aux ? vr_svo_kernel<true, 0, false> : vr_svo_kernel<false, 0, false>));
         k<<<grid, block, 0, stream>>>(P);
     } else {
         void (*k)(vr_frame_params) = multi ? (aux ? vr_dense_kernel<true, true> : vr_dense_kernel<false, true>)

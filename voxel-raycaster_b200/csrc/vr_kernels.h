@@ -16,7 +16,8 @@ typedef struct vr_launch_options {
     int num_sms;
     unsigned int *counter;     /* device pixel counter */
     int walk;                  /* 0 = merged in-cell walk (bit-identical to the reference on every pixel),
-                                  1 = per-axis walk (identical except distance_traveled on exact-tie rays) */
+                                  1 = per-axis walk (identical except distance_traveled on exact-tie rays),
+                                  2 = closed-form crossing times (vr_canon.h: within BASELINE.json's tolerance) */
 } vr_launch_options;
 
 /* One frame (or one row-band slab of it).  use_svo selects the 64-tree traversal kernel, otherwise the
