@@ -169,6 +169,12 @@ int vr_native_tree_copy(vr_ctx *ctx, void *device_nodes, void *device_types);
 int vr_assign_native_tree(vr_ctx *ctx, const void *device_nodes, uint64_t node_bytes, const void *device_types,
                           uint64_t type_bytes, int32_t levels, int32_t dim);
 
+/* The top grid the closed-form walk (option walk = 2) reads instead of the upper octree levels: a dense table over the
+ * blocks of edge 1 << *grid_shift derived from the 64-tree on the device (csrc/vr_build.cu: vr_build_grid_device; layout
+ * in csrc/vr_types.h).  Builds it if necessary and copies it to `host_out` when capacity (entries) suffices.  Returns
+ * the number of entries, 0 on failure (e.g. a map of 4^3 or less has no grid).  For tests / inspection. */
+uint64_t vr_top_grid_read(vr_ctx *ctx, uint32_t *host_out, uint64_t capacity, int32_t *grid_shift, int32_t *grid_bits);
+
 /* Multi-GPU frame assembly without SM involvement: every rank pushes its band slab straight into the frame
  * buffer that lives on the root GPU with ONE strided copy-engine transfer over NVLink (cudaMemcpy2DAsync
  * through a CUDA-IPC mapping), so the ray casting kernel of the next frame is not disturbed by a gather kernel.

@@ -6,7 +6,7 @@
 #
 # `build` compiles voxel-raycaster_b200/csrc with the extra nvcc flags into build/ab/lib_<name>.so (git-ignored, but it
 # travels with gpurun); `run` times bench.py per variant through VR_CASTER_LIB (caster.py) and prints
-# "<config> <variant> <ms/frame walk 1> <ms/frame walk 0> <frame checksum>".  "main" = the in-tree library.
+# "<config> <variant> <ms/frame of bench.py's walk (default 2)> <ms/frame of the other walks> <frame checksum>".  "main" = the in-tree library.
 set -e
 cd "$(dirname "$0")/.."
 cmd=$1; shift
@@ -20,7 +20,7 @@ if [ "$cmd" = build ]; then
   for v in "$@"; do
     name=${v%%:*}
     [ -f "build/ab/lib_$name.so" ] || { echo "build of $name failed: build/ab/$name.log"; exit 1; }
-    echo "$name $(cuobjdump -res-usage build/ab/lib_$name.so 2>/dev/null | grep -A1 'vr_svo_kernelILb0ELi1ELb0' | grep -o 'REG:[0-9]* STACK:[0-9]*')"
+    echo "$name $(cuobjdump -res-usage build/ab/lib_$name.so 2>/dev/null | grep -A1 'vr_svo_kernelILb0ELi2ELb0' | grep -o 'REG:[0-9]* STACK:[0-9]*')"
   done
 elif [ "$cmd" = run ]; then
   cfg=$1; shift
@@ -28,7 +28,7 @@ elif [ "$cmd" = run ]; then
     if [ "$v" = main ]; then unset VR_CASTER_LIB; else export VR_CASTER_LIB="$PWD/build/ab/lib_$v.so"; fi
     python bench.py --config "$cfg" --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
-j=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('$cfg $v', round(j['ms_per_step'],4), j['config'].get('other_walk_ms_per_frame'), j['config']['frame_checksum'])"
+j=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('$cfg $v', round(j['ms_per_step'],4), {k: round(x, 4) for k, x in (j['config'].get('other_walk_ms_per_frame') or {}).items()}, j['config']['frame_checksum'])"
   done
 else
   echo "usage: $0 build name:flags ... | run <config> <variant> ..."; exit 2

@@ -45,6 +45,12 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
         P.nodes = tree.nodes.data(); P.leaf_types = tree.leaf_types.data();
         P.levels = tree.levels; P.root_shift = 2 * (tree.levels - 1);
     }
+    std::vector<uint32_t> grid;
+    if (use_svo == 3) {
+        int gs = 0, gb = 0;
+        if (!vr_native_grid(tree.nodes.data(), tree.levels, n, grid, &gs, &gb)) return -3;
+        P.grid = grid.data(); P.grid_shift = gs; P.grid_bits = gb;
+    }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = 0; y < height; y++)
         for (int x = 0; x < width; x++) {
@@ -91,6 +97,15 @@ extern "C" long emu_tree_from_columns(const int32_t *lo, const int32_t *hi, int 
     vr_native_tree t;
     if (!vr_native_from_columns(lo, hi, n, (uint8_t)type, t)) return -1;
     return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
+}
+
+/* the host version of the closed-form walk's top grid, from 64-tree arrays (nodes as 16-byte records) */
+extern "C" long emu_grid_from_tree(const void *nodes, int levels, int dim, uint32_t *out, long cap, int *shift, int *bits) {
+    std::vector<uint32_t> g;
+    if (!vr_native_grid((const vr_node *)nodes, levels, dim, g, shift, bits)) return -1;
+    if ((long)g.size() > cap) return -2;
+    memcpy(out, g.data(), g.size() * sizeof(uint32_t));
+    return (long)g.size();
 }
 
 /* vr_add_chain (binade jumps) against the literal chain of additions it stands for */

@@ -315,3 +315,52 @@ def test_reference_octree_importer_random_volumes(pkg):
         b = emu_lib.tree_from_ref(desc, root, n)
         assert a[2] == b[2] and a[0].shape == b[0].shape
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (n, dens)
+
+
+@pytest.mark.parametrize("kind", ["terrain64", "terrain256", "random32", "sparse128", "half32"])
+def test_top_grid_invariants(pkg, kind):
+    """The top grid of the closed-form walk (vr_octree.cpp: vr_native_grid): a block is marked non-empty exactly when it
+    holds a set voxel, its node index is the node covering it, and every empty entry describes a cell that contains the
+    block, lies inside the map and holds no set voxel (checked against the dense map)."""
+    S = pkg.scene
+    rng = np.random.default_rng(8)
+    if kind.startswith("terrain"):
+        vol = S.terrain_map(int(kind[7:]), "shell")
+    elif kind == "random32":
+        vol = (rng.random((32, 32, 32)) < 0.03).astype(np.int8) * 5
+    elif kind == "sparse128":
+        vol = (rng.random((128, 128, 128)) < 0.0003).astype(np.int8) * 6
+    else:
+        vol = np.zeros((32, 32, 32), np.int8)
+        vol[:16] = 5
+    n = vol.shape[0]
+    nodes, types, levels = emu_lib.tree_from_dense(vol)
+    grid, g, bits = emu_lib.grid_from_tree(nodes, levels, n)
+    G = 1 << bits
+    assert G == n >> g and grid.shape == (G, G, G)
+    solid = (vol == 5) | (vol == 6)
+    blocks = solid.reshape(G, 1 << g, G, 1 << g, G, 1 << g).any(axis=(1, 3, 5))          # [bz, by, bx]
+    assert np.array_equal((grid & 0x80000000) != 0, blocks)
+    # summed-area table of the set voxels: emptiness of a box in O(1)
+    sat = np.zeros((n + 1, n + 1, n + 1), np.int64)
+    sat[1:, 1:, 1:] = solid.astype(np.int64).cumsum(0).cumsum(1).cumsum(2)
+
+    def count(lo, hi):          # set voxels in [lo, hi) per axis, (z, y, x)
+        (z0, y0, x0), (z1, y1, x1) = lo, hi
+        return (sat[z1, y1, x1] - sat[z0, y1, x1] - sat[z1, y0, x1] - sat[z1, y1, x0]
+                + sat[z0, y0, x1] + sat[z0, y1, x0] + sat[z1, y0, x0] - sat[z0, y0, x0])
+
+    wide = 0
+    for bz, by, bx in np.argwhere(~blocks):
+        e = int(grid[bz, by, bx])
+        m, ext = (1 << (e & 31)) - 1, e >> 8
+        lo, hi = [], []
+        for b in (bz, by, bx):
+            p = b << g
+            lo.append((p & ~m) - ext)          # the cell is symmetric: it serves rays of either direction (mirroring)
+            hi.append((p | m) + ext + 1)
+        assert min(lo) >= 0 and max(hi) <= n, (kind, bz, by, bx, e)
+        assert count(lo, hi) == 0, (kind, bz, by, bx, e)
+        wide += hi[0] - lo[0] > (1 << g)
+    if kind != "random32":
+        assert wide > 0

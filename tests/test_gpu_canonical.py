@@ -178,3 +178,36 @@ def test_sparse_maps_all_walks(pkg, oracle, n):
         assert_equals_oracle_b(b_rgba, b_aux, c.draw(), c.read_aux(), f"sparse {n} scene {it} walk 2")
         c.close()
     assert biased >= 2
+
+
+@pytest.mark.parametrize("kind", ["features", "terrain64", "terrain256", "terrain512", "random32", "empty16", "sparse128"])
+def test_top_grid_device_equals_host(pkg, kind):
+    """The top grid of walk = 2 (vr_build.cu: vr_build_grid_device, derived from the 64-tree in HBM) equals the host
+    version (vr_octree.cpp: vr_native_grid) entry by entry, for trees built on the device."""
+    import emu_lib
+    import torch
+
+    S = pkg.scene
+    rng = np.random.default_rng(4)
+    if kind == "features":
+        vol = S.features_map(32)
+    elif kind.startswith("terrain"):
+        vol = S.terrain_map(int(kind[7:]), "shell")
+    elif kind == "random32":
+        vol = (rng.random((32, 32, 32)) < 0.05).astype(np.int8) * 5
+    elif kind == "empty16":
+        vol = np.zeros((16, 16, 16), np.int8)
+    else:
+        vol = (rng.random((128, 128, 128)) < 0.0005).astype(np.int8) * 6
+    c = pkg.CUDACaster()
+    assert c.init(0) and c.assign_map(vol), c.last_error()
+    nb, tb, levels, dim = c.native_tree_info()
+    nodes = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
+    types = torch.empty(tb, dtype=torch.uint8, device="cuda:0")
+    assert c.native_tree_copy(nodes.data_ptr(), types.data_ptr())
+    torch.cuda.synchronize()
+    grid, gs, gb = c.top_grid()
+    ref, rs, rb = emu_lib.grid_from_tree(nodes.cpu().numpy().view(np.uint32).reshape(-1, 4), levels, dim)
+    c.close()
+    assert (gs, gb) == (rs, rb) and grid.shape == ref.shape
+    assert np.array_equal(grid, ref), f"{kind}: {int((grid != ref).sum())} entries differ"

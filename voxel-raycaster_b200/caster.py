@@ -85,6 +85,7 @@ SYMBOLS = {
     "vr_read_ray_table": (_i, [_vp, _f32p, C.c_size_t]),
     "vr_native_tree_info": (_i, [_vp, _u64p, _u64p, _i32p, _i32p]),
     "vr_native_tree_copy": (_i, [_vp, _vp, _vp]),
+    "vr_top_grid_read": (C.c_uint64, [_vp, _vp, C.c_uint64, _i32p, _i32p]),
     "vr_assign_native_tree": (_i, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int32, C.c_int32]),
     "vr_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "vr_device_free": (_i, [_vp, _vp]),
@@ -340,6 +341,18 @@ class CUDACaster:
         if not self._lib.vr_native_tree_info(self._ctx, C.byref(nb), C.byref(tb), C.byref(lv), C.byref(dm)):
             raise RuntimeError(self.last_error())
         return int(nb.value), int(tb.value), int(lv.value), int(dm.value)
+
+    def top_grid(self) -> tuple[np.ndarray, int, int]:
+        """(grid entries as uint32[G, G, G] indexed [z, y, x], block shift, log2 G) of the closed-form walk's top grid."""
+        gs, gb = C.c_int32(0), C.c_int32(0)
+        n = int(self._lib.vr_top_grid_read(self._ctx, None, 0, C.byref(gs), C.byref(gb)))
+        if n == 0:
+            raise RuntimeError(self.last_error())
+        out = np.zeros(n, dtype=np.uint32)
+        if int(self._lib.vr_top_grid_read(self._ctx, out.ctypes.data_as(_vp), n, C.byref(gs), C.byref(gb))) != n:
+            raise RuntimeError(self.last_error())
+        g = 1 << gb.value
+        return out.reshape(g, g, g), int(gs.value), int(gb.value)
 
     def native_tree_copy(self, device_nodes: int, device_types: int) -> bool:
         return bool(self._lib.vr_native_tree_copy(self._ctx, _vp(device_nodes), _vp(device_types)))

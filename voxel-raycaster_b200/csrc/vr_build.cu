@@ -296,3 +296,89 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
     cleanup();
     return cudaSuccess;
 }
+
+/* ---- top grid of the closed-form walk (vr_types.h: vr_frame_params::grid), from the 64-tree in HBM ----------------
+ * Same three steps as vr_native_grid (vr_octree.cpp), which the tests hold this against entry by entry. */
+namespace {
+
+/* one thread per block of edge 1 << g: descend to the slot that is the block */
+__global__ void vr_grid_classify(const vr_node *nodes, int root_shift, int g, int G, int dim, uint32_t *grid, uint8_t *cell) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)G * G * G) return;
+    const int bx = i % G, by = (i / G) % G, bz = i / (G * G);
+    const int x = bx << g, y = by << g, z = bz << g;
+    uint32_t idx = 0, entry = 0;
+    uint8_t cs_out = 0;
+    for (int s = root_shift;; s -= 2) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nodes) + idx);
+        const unsigned long long m = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+        const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
+        if (!((m >> ci) & 1ull)) {
+            int cs = s + ((((m >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
+            while ((1 << cs) > dim) cs--;
+            cs_out = (uint8_t)cs;
+            break;
+        }
+        idx = v.z + (uint32_t)__popcll(m & ((1ull << ci) - 1ull));
+        if (s == g) { entry = 0x80000000u | idx; break; }
+    }
+    grid[i] = entry;
+    cell[i] = cs_out;
+}
+
+/* erosion step r: an empty block of radius r - 1 whose 26 neighbours all exist and have radius >= r - 1 gets radius r.
+ * In place: the test is not affected by neighbours that were already raised to r in this launch. */
+__global__ void vr_grid_erode(uint32_t *grid, int G, uint32_t r) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)G * G * G) return;
+    const int bx = i % G, by = (i / G) % G, bz = i / (G * G);
+    if (bx < 1 || by < 1 || bz < 1 || bx >= G - 1 || by >= G - 1 || bz >= G - 1) return;
+    if (grid[i] != r - 1) return;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const uint32_t e = ((volatile uint32_t *)grid)[(unsigned)(bx + dx) + (unsigned)G * ((unsigned)(by + dy) + (unsigned)G * (unsigned)(bz + dz))];
+                if (e < r - 1 || (e & 0x80000000u)) return;
+            }
+    grid[i] = r;
+}
+
+__global__ void vr_grid_finish(uint32_t *grid, const uint8_t *cell, int g, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t d = grid[i];
+    if (d & 0x80000000u) return;
+    grid[i] = (((2u * d + 1u) << g) > (1u << cell[i])) ? ((uint32_t)g | ((d << g) << 8)) : (uint32_t)cell[i];
+}
+
+}  // namespace
+
+cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cudaStream_t stream, uint32_t **grid_out,
+                                 int *grid_shift, int *grid_bits, unsigned long long *launches) {
+    const int root_shift = 2 * (levels - 1);
+    if (root_shift < 2 || dim < 8) return cudaErrorInvalidValue;
+    const int g = root_shift - 4 > 2 ? root_shift - 4 : 2;
+    const int G = dim >> g;
+    int bits = 0;
+    while ((1 << bits) < G) bits++;
+    const unsigned n = (unsigned)G * G * G;
+    uint32_t *grid = nullptr;
+    uint8_t *cell = nullptr;
+    cudaError_t e = cudaMalloc(&grid, (size_t)n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&cell, n);
+    if (e != cudaSuccess) { cudaFree(grid); cudaFree(cell); return e; }
+    const unsigned blocks = (n + 255) / 256;
+    vr_grid_classify<<<blocks, 256, 0, stream>>>(d_nodes, root_shift, g, G, dim, grid, cell);
+    const int rmax = G / 2 < 63 ? G / 2 : 63;                            /* a cube of radius r inside the grid needs G >= 2r + 1 */
+    for (int r = 1; r <= rmax; r++) vr_grid_erode<<<blocks, 256, 0, stream>>>(grid, G, (uint32_t)r);
+    vr_grid_finish<<<blocks, 256, 0, stream>>>(grid, cell, g, n);
+    if (launches) *launches += 2 + (rmax > 0 ? rmax : 0);
+    e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(cell);
+    if (e != cudaSuccess) { cudaFree(grid); return e; }
+    *grid_out = grid;
+    *grid_shift = g;
+    *grid_bits = bits;
+    return cudaSuccess;
+}

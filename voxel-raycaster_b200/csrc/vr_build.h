@@ -21,4 +21,9 @@ typedef struct vr_device_tree {
 cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stream, vr_device_tree *out,
                                  unsigned long long *launches);
 
+/* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree d_nodes: *grid_out is
+ * cudaMalloc'ed (ownership passes to the caller).  cudaErrorInvalidValue when the tree is too shallow for a grid. */
+cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cudaStream_t stream, uint32_t **grid_out,
+                                 int *grid_shift, int *grid_bits, unsigned long long *launches);
+
 #endif

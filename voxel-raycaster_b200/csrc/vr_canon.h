@@ -31,6 +31,23 @@
 #define VR_MAGIC_F 12582912.0f
 #define VR_MAGIC_I 0x4B400000
 
+/* keeps a per-ray constant in its register: without this the compiler re-derives such values from their sources inside
+ * the traversal loop (a dozen ALU instructions per lookup) to stay below the register limit */
+#if defined(__CUDA_ARCH__) && !defined(VR_CANON_NO_PIN)
+#define VR_PIN(x) asm volatile("" : "+r"(x))
+#else
+#define VR_PIN(x) ((void)0)
+#endif
+
+/* a point every lane of the warp passes once per turn of the traversal loop: without it the compiler threads the
+ * early exits of the lookup / the walk straight back to the loop head, the lanes of a warp then run the loop body
+ * in separate groups and never reconverge (measured: 20 instead of 29 active lanes per instruction) */
+#if defined(__CUDA_ARCH__)
+#define VR_JOIN(x) asm volatile("" : "+r"(x))
+#else
+#define VR_JOIN(x) ((void)0)
+#endif
+
 VR_HD int vr_hibit(int x) {          /* index of the highest set bit of x != 0 (31 for negative x) */
 #if defined(__CUDA_ARCH__)
     return 31 - __clz(x);
@@ -46,11 +63,12 @@ struct vr_cray {
     float ix, iy, iz;         /* |ray_dir| ~ 1 / delta_t: crossing-count estimates only, never a value */
     int px, py, pz;           /* mirrored voxel */
     int bx, by, bz;           /* p0 - VR_MAGIC_I (p0 = mirrored voxel at the (re)start) */
-    uint32_t flip;            /* child-slot XOR of the mirrored axes: bits 0-5 below the root, bits 8-13 at the root */
-    vr_node_regs node;        /* octree cursor: current node, its child shift, its depth */
-    int s, level;
+    uint32_t flip;            /* child-slot XOR of the mirrored axes (levels below the grid: 3 / 0xC / 0x30 per axis) */
+    uint32_t gflip;           /* grid-index XOR of the mirrored axes */
+    vr_node_regs node;        /* octree cursor below the grid: current node and its child shift */
+    int s;
     bool first_hit_done;
-    Stack stk;
+    Stack stk;                /* node indices of the current block's subtree, slot = child shift / 2 */
 };
 
 /* (re)start of a ray: from the reference state (voxel, voxel_step, intersection_t, ray_dir) to the mirrored form */
@@ -65,8 +83,10 @@ VR_HD void vr_canon_enter(const vr_frame_params &P, vr_cray<Stack> &q) {
     q.bx = q.px - VR_MAGIC_I; q.by = q.py - VR_MAGIC_I; q.bz = q.pz - VR_MAGIC_I;
     q.t0x = r.t.x; q.t0y = r.t.y; q.t0z = r.t.z;
     q.ix = fabsf(r.ray_dir.x); q.iy = fabsf(r.ray_dir.y); q.iz = fabsf(r.ray_dir.z);
-    const uint32_t rb = (uint32_t)(N - 1) >> P.root_shift;               /* slot bits of N-1 at the root level: 1 or 3 */
-    q.flip = (nx ? 3u | (rb << 8) : 0u) | (ny ? 0xCu | (rb << 10) : 0u) | (nz ? 0x30u | (rb << 12) : 0u);
+    q.flip = (nx ? 3u : 0u) | (ny ? 0xCu : 0u) | (nz ? 0x30u : 0u);
+    const uint32_t gm = (1u << P.grid_bits) - 1u;
+    q.gflip = (nx ? gm : 0u) | (ny ? gm << P.grid_bits : 0u) | (nz ? gm << (2 * P.grid_bits) : 0u);
+    VR_PIN(q.bx); VR_PIN(q.by); VR_PIN(q.bz); VR_PIN(q.flip); VR_PIN(q.gflip);
 }
 
 /* the reference's voxel / intersection_t / face_mask of the step just made */
@@ -74,6 +94,7 @@ template <class Stack>
 VR_HD void vr_canon_materialize(const vr_frame_params &P, vr_cray<Stack> &q, int fm) {
     RayState &r = q.r;
     const int N = P.dim[0];
+    r.step = {(q.flip & 1u) ? -1 : 1, (q.flip & 4u) ? -1 : 1, (q.flip & 16u) ? -1 : 1};   /* (not kept live across the walk) */
     r.voxel = {r.step.x < 0 ? N - 1 - q.px : q.px, r.step.y < 0 ? N - 1 - q.py : q.py, r.step.z < 0 ? N - 1 - q.pz : q.pz};
     r.t.x = VR_FMA(VR_SUB(vr_bits2f(q.px - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
     r.t.y = VR_FMA(VR_SUB(vr_bits2f(q.py - q.by), VR_MAGIC_F), r.delta.y, q.t0y);
@@ -81,65 +102,83 @@ VR_HD void vr_canon_materialize(const vr_frame_params &P, vr_cray<Stack> &q, int
     r.fm = fm;
 }
 
-template <class Stack>
-VR_HD void vr_canon_cursor_reset(const vr_frame_params &P, vr_cray<Stack> &q) {
-    q.s = P.root_shift;
-    q.level = 0;
-    q.node = vr_load_node(P, 0);
-}
+/* The empty cell a walk crosses: the cube [p & ~m, (p | m) + ext] per axis (mirrored coordinates) -- an aligned
+ * power-of-two cell of the octree (ext = 0) or a block of the top grid grown by its empty radius -- or a leaf brick. */
+struct vr_ccell {
+    int m, ext;
+    bool brick;
+};
 
 /* Looks the (in-map) voxel p up.  `xr` has a bit set wherever p differs from the voxel of the previous lookup.
- * Returns the voxel value if the voxel is set; otherwise 0 and the empty cell around p: edge 1 << cs, or the leaf
- * brick (4^3 voxels, occupancy = q.node.mask) when `brick`. */
+ * Returns the voxel value if the voxel is set; otherwise 0 and the empty cell around p.
+ * Two stages: the top grid (vr_types.h) answers for whole blocks in one 4-byte load, without stack or descent; only
+ * inside a non-empty block the 64-tree below it is descended, one 16-byte node per two octree levels. */
 template <bool AUX, class Stack>
-VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, int &cs, bool &brick, vr_aux *a) {
+VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, vr_ccell &c, vr_aux *a) {
+    const int g = P.grid_shift;
     if (AUX) a->lookups++;
-    if ((xr >> (q.s + 2)) != 0) {                                         /* pop to the lowest ancestor containing p */
-        int s2 = vr_hibit(xr) & ~1;
-        s2 = s2 < P.root_shift ? s2 : P.root_shift;
-        q.level -= (s2 - q.s) >> 1;
-        q.s = s2;
-        q.node = vr_load_node(P, q.stk.get(q.level));
+    if ((xr >> g) != 0) {                                                 /* another block */
+        const int G = 1 << P.grid_bits;
+        const uint32_t key = (uint32_t)((q.px >> g) + ((q.py >> g) + (q.pz >> g) * G) * G) ^ q.gflip;
+#if defined(__CUDA_ARCH__)
+        const uint32_t e = __ldg(P.grid + key);
+#else
+        const uint32_t e = P.grid[key];
+#endif
+        if (!(e & 0x80000000u)) {
+            c.m = (1 << (e & 31u)) - 1;
+            c.ext = (int)(e >> 8);
+            c.brick = false;
+            return 0;
+        }
+        const uint32_t idx = e & 0x7fffffffu;
+        q.s = g - 2;
+        q.stk.set(q.s >> 1, idx);
+        q.node = vr_load_node(P, idx);
+        if (AUX) a->node_fetches++;
+    } else if ((xr >> (q.s + 2)) != 0) {                                  /* same block: pop to the lowest ancestor containing p */
+        q.s = vr_hibit(xr) & ~1;
+        q.node = vr_load_node(P, q.stk.get(q.s >> 1));
         if (AUX) a->node_fetches++;
     }
+    const uint32_t cf = q.flip;
     for (;;) {
         const int s = q.s;
-        const uint32_t cf = (s == P.root_shift ? q.flip >> 8 : q.flip) & 63u;
-        const int ci = (int)(((uint32_t)((q.px >> s) & 3) | ((uint32_t)((q.py >> s) & 3) << 2) | ((uint32_t)((q.pz >> s) & 3) << 4)) ^ cf);
-        if (!((q.node.mask >> ci) & 1ull)) {
-            brick = s == 0;
+        const uint32_t ci = ((uint32_t)((q.px >> s) & 3) | ((uint32_t)((q.py >> s) & 3) << 2) | ((uint32_t)((q.pz >> s) & 3) << 4)) ^ cf;
+        if (!((uint32_t)(q.node.mask >> ci) & 1u)) {
             /* the 2x2x2 octant of slots around an empty slot is empty as a whole <=> the cell is twice as wide (the odd
              * levels of the reference's 2^3 octree; slots ci&0x2A + {0,1,4,5,16,17,20,21}) */
-            const bool wide = ((q.node.mask >> (ci & 0x2A)) & 0x00330033ull) == 0ull;
-            cs = brick ? 2 : s + (wide ? 1 : 0);
+            const bool wide = ((uint32_t)(q.node.mask >> (ci & 0x2Au)) & 0x00330033u) == 0u;
+            c.brick = s == 0;
+            c.m = (1 << (s + (wide ? 1 : 0))) - 1;
+            c.ext = 0;
             return 0;
         }
         const uint32_t below = (uint32_t)VR_POPC64(q.node.mask & ((1ull << ci) - 1ull));
         if (s == 0) return (int)(int8_t)P.leaf_types[q.node.base + below];
         const uint32_t child = q.node.base + below;
-        q.level++;
         q.s = s - 2;
-        q.stk.set(q.level, child);
+        q.stk.set(q.s >> 1, child);
         q.node = vr_load_node(P, child);
         if (AUX) a->node_fetches++;
     }
 }
 
-/* Walks the empty cell of edge m+1 (aligned, power of two) the mirrored voxel p lies in, up to and including the step
- * that leaves it.  T = min over the axes of the time of the crossing that leaves the cell; every axis then makes all
- * its crossings with time <= T (kernel:558: an axis steps when its time is <= the others', ties step together).
+/* Walks the empty cell `c` the mirrored voxel p lies in, up to and including the step that leaves it.
+ * T = min over the axes of the time of the crossing that leaves the cell; every axis then makes all its crossings with
+ * time <= T (kernel:558: an axis steps when its time is <= the others', ties step together).
  * Returns the number of steps (multi-axis steps inside the cell are counted per axis: see DESIGN.md, tie rays);
  * fm = axes of the last step; xr = changed voxel bits. */
 template <class Stack>
-VR_HD int vr_canon_walk(vr_cray<Stack> &q, int m, int &fm, int &xr) {
+VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, int &fm, int &xr) {
     const RayState &r = q.r;
-    const int ox = q.px | m, oy = q.py | m, oz = q.pz | m;               /* last voxel of the cell along each axis */
+    const int ox = (q.px | c.m) + c.ext, oy = (q.py | c.m) + c.ext, oz = (q.pz | c.m) + c.ext;   /* last voxel of the cell per axis */
     const float Tx = VR_FMA(VR_SUB(vr_bits2f(ox - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
     const float Ty = VR_FMA(VR_SUB(vr_bits2f(oy - q.by), VR_MAGIC_F), r.delta.y, q.t0y);
     const float Tz = VR_FMA(VR_SUB(vr_bits2f(oz - q.bz), VR_MAGIC_F), r.delta.z, q.t0z);
     const float T = vr_min3(Tx, Ty, Tz);
     /* per axis: k = the last crossing with time <= T.  The estimate RN((T - t0) / delta) is k or k + 1 (its error is
-     * below 1e-3 crossings: |ray_dir| * delta_t = 1 +- 2^-24, at most 2^22 crossings), one evaluation decides. */
+     * below 1e-2 crossings: |ray_dir| * delta_t = 1 +- 2^-24, at most 2^16 crossings), one evaluation decides. */
     const float mx = VR_ADD(VR_MUL(VR_SUB(T, q.t0x), q.ix), VR_MAGIC_F);
     const float my = VR_ADD(VR_MUL(VR_SUB(T, q.t0y), q.iy), VR_MAGIC_F);
     const float mz = VR_ADD(VR_MUL(VR_SUB(T, q.t0z), q.iz), VR_MAGIC_F);
@@ -171,7 +210,7 @@ VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, in
     float tx = VR_FMA(kx, r.delta.x, q.t0x), ty = VR_FMA(ky, r.delta.y, q.t0y), tz = VR_FMA(kz, r.delta.z, q.t0z);
     float rx = (float)(4 - lx), ry = (float)(4 - ly), rz = (float)(4 - lz), steps = 0.0f;
     float bitf = (float)(lx | (ly << 2) | (lz << 4));
-    const int cf = (int)(q.flip & 63u);     /* (a leaf is the root only in a 4^3 map, where both flips coincide) */
+    const int cf = (int)q.flip;
     float ex, ey, ez;
     bool hit;
     for (;;) {
@@ -186,7 +225,7 @@ VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, in
         steps = VR_ADD(steps, 1.0f);
         if (VR_MUL(VR_MUL(rx, ry), rz) == 0.0f) { hit = false; break; }
         bit = (int)bitf ^ cf;
-        if ((mask >> bit) & 1ull) { hit = true; break; }
+        if ((uint32_t)(mask >> bit) & 1u) { hit = true; break; }
     }
     const int nx = q.px + (4 - lx) - (int)rx, ny = q.py + (4 - ly) - (int)ry, nz = q.pz + (4 - lz) - (int)rz;
     xr = (nx ^ q.px) | (ny ^ q.py) | (nz ^ q.pz);
@@ -257,7 +296,10 @@ VR_HD int vr_canon_slow(const vr_frame_params &P, RayState &r, vr_aux *a, bool &
     }
 }
 
-/* Whole pixel.  Returns true if the pixel must be written (packed colour in *rgba_out). */
+/* Whole pixel.  Returns true if the pixel must be written (packed colour in *rgba_out).
+ * distance_traveled bookkeeping: r.dist is the reference's counter at the top of its loop (kernel:357).  A walk of n
+ * steps is n loop iterations; the last of them loads the voxel entered and, on a hit, runs the hit block with the
+ * counter at r.dist + n - 1 before kernel:714 increments it. */
 template <bool AUX, bool MULTI, class Stack>
 VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
     vr_cray<Stack> q;
@@ -270,101 +312,87 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
     }
     const int N = P.dim[0];
     q.first_hit_done = false;
+    q.s = 0;
     int status = VR_ST_MAXDIST;
-    bool slow = !vr_ray_finite(r);
-    if (!slow) {
+    bool slow = false;
+    int xr = -1;                           /* changed voxel bits since the last lookup; -1 = everything */
+    for (;;) {                             /* one turn per ray segment: primary ray, shadow ray(s), reflections */
+        if (!vr_ray_finite(r)) { slow = true; break; }
         vr_canon_enter(P, q);
-        vr_canon_cursor_reset(P, q);
-        q.stk.set(0, 0u);
-        if (AUX) a->node_fetches = 1;
-        /* the voxel a ray (re)starts in is never tested (the reference steps before it loads, kernel:555-570) and
-         * its entry is not a step: distance_traveled starts one below, the common increment below brings it to 0 */
-        r.dist = -1;
-        bool fresh = true;
-        int xr = 0, fm = 0, bit = 0;
-        bool known = false;                /* the brick walk already knows that the voxel entered is set */
-        for (;;) {
-            /* ---- (1) what does voxel p hold? */
-            int cs = 0, voxel_data = 0;
-            bool brick = false;
-            bool relight = false;          /* multi-light extension: this light is not blocked, on to the next one */
-            if (known) {
-                voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
-            } else if ((unsigned)(q.px | q.py | q.pz) < (unsigned)N) {
-                voxel_data = vr_canon_lookup<AUX>(P, q, xr, cs, brick, a);
-            } else {
-                /* a ray may start outside the map (and a redirect may restart there): that voxel is a cell of its own */
-                vr_canon_cursor_reset(P, q);
-            }
-            known = false;
-            /* ---- (2) hit handling (kernel:575-711) */
-            if ((voxel_data == 5 || voxel_data == 6) && !fresh) {
-                if (r.shadow) {                                          /* kernel:706-710; nothing else of the block is live */
-                    r.color.w = MULTI ? VR_ADD(r.alpha_before, 0.1f) : 0.1f;
-                    if (!(MULTI && vr_more_lights(P, r))) { status = VR_ST_SHADOW_HIT; break; }
-                    relight = true;
-                } else {
-                    vr_canon_materialize(P, q, fm);
-                    const vi3 hv = r.voxel;
-                    const int st = vr_hit_block<AUX, MULTI>(P, r, voxel_data, a, q.first_hit_done);
-                    if (st >= 0) { status = st; break; }
-                    /* redirected: the ray restarts in the voxel it came from; the increment of kernel:714 that ends
-                     * the hit iteration is the common one below */
-                    xr = (hv.x ^ r.voxel.x) | (hv.y ^ r.voxel.y) | (hv.z ^ r.voxel.z);
-                    if (!vr_ray_finite(r)) { slow = true; break; }
-                    vr_canon_enter(P, q);
-                    fresh = true;
-                    continue;
-                }
-            } else {
-                if (voxel_data == 5 || voxel_data == 6) { cs = 0; brick = false; }   /* a ray that starts inside a set voxel */
-                fresh = false;
-                r.dist++;                                                 /* kernel:714 */
-                /* ---- (3) kernel:357, then the walk through the empty cell around p */
-                if (!(r.dist < r.max_distance && r.bounce < 2)) {
-                    if (!(MULTI && r.bounce < 2 && vr_more_lights(P, r))) { status = r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST; break; }
-                    relight = true;
-                } else {
-                    const int nmax = r.max_distance - r.dist;
-                    int n;
-                    bool tie = false;
-                    if (brick && nmax > 12) {
-                        const int before = q.px + q.py + q.pz;
-                        known = vr_canon_brick(q, q.node.mask, n, fm, xr, bit);
-                        tie = (q.px + q.py + q.pz - before) != n;
-                    } else {
-                        n = vr_canon_walk(q, brick ? 0 : (1 << cs) - 1, fm, xr);
-                    }
-                    if (AUX && ((fm & (fm - 1)) || tie)) a->flags |= VR_FL_TIE;
-                    if (n > nmax) {                                       /* max_distance is reached inside the cell */
-                        r.dist = r.max_distance;
-                        if (!(MULTI && r.bounce < 2 && vr_more_lights(P, r))) { status = VR_ST_MAXDIST; break; }
-                        relight = true;
-                    } else {
-                        r.dist += n - 1;
-                        if (!known && (unsigned)(q.px | q.py | q.pz) >= (unsigned)N) {     /* kernel:563 */
-                            if (!(MULTI && vr_more_lights(P, r))) {
-                                r.fm = 0;                                 /* the voxel is dead: only the colour of kernel:565 */
-                                vr_out_of_bounds(r);
-                                status = VR_ST_OOB;
-                                break;
-                            }
-                            relight = true;
-                        }
-                    }
-                }
-            }
-            if (MULTI && relight) {
-                if (!vr_next_light(P, r)) { status = VR_ST_SKIP_REDIRECT; break; }
-                if (!vr_ray_finite(r)) { slow = true; break; }
-                vr_canon_enter(P, q);
-                vr_canon_cursor_reset(P, q);
-                fresh = true;
-                known = false;
-                xr = 0;
-            }
+        /* the cell around the voxel the segment starts in; that voxel itself is never tested (the reference steps before
+         * it loads, kernel:555-570) and may even lie outside the map */
+        vr_ccell c = {0, 0, false};
+        if ((unsigned)(q.px | q.py | q.pz) < (unsigned)N) {
+            if (vr_canon_lookup<AUX>(P, q, xr, c, a) != 0) c = {0, 0, false};
         }
-        if (slow) r.dist++;                /* the increment that ends the iteration of the redirect */
+        int voxel_data = 0, fm = 0;
+        enum { EV_HIT, EV_UNBLOCKED_MAXDIST, EV_UNBLOCKED_OOB } ev = EV_HIT;
+        if (!(r.bounce < 2)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
+        for (;;) {                         /* one turn per empty cell */
+            const int nmax = r.max_distance - r.dist;                      /* iterations kernel:357 still allows */
+            int n, bit = 0;
+            bool known = false;            /* the brick walk already knows that the voxel entered is set */
+            if (c.brick && nmax > 12) {
+                const int before = q.px + q.py + q.pz;
+                known = vr_canon_brick(q, q.node.mask, n, fm, xr, bit);
+                if (AUX && (q.px + q.py + q.pz - before) != n) a->flags |= VR_FL_TIE;
+            } else {
+                if (c.brick) c = {0, 0, false};                            /* the ray is about to end: voxel by voxel */
+                n = vr_canon_walk(q, c, fm, xr);
+            }
+            VR_JOIN(n);
+            if (n > nmax) {                                                /* kernel:357 ends the loop inside this cell */
+                if (nmax > 0) r.dist = r.max_distance;
+                ev = EV_UNBLOCKED_MAXDIST;
+                break;
+            }
+            r.dist += n;
+            if (AUX && (fm & (fm - 1))) a->flags |= VR_FL_TIE;
+            if (known) {                                                   /* the step landed on a set voxel of the brick */
+                voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
+            } else {
+                if ((unsigned)(q.px | q.py | q.pz) >= (unsigned)N) { ev = EV_UNBLOCKED_OOB; break; }   /* kernel:563 */
+                voxel_data = vr_canon_lookup<AUX>(P, q, xr, c, a);
+            }
+            VR_JOIN(voxel_data);
+            if (voxel_data == 5 || voxel_data == 6) { ev = EV_HIT; break; }
+            if (voxel_data != 0) c = {0, 0, false};
+        }
+        /* ---- the segment ended */
+        bool relight = false;              /* multi-light extension: this light is not blocked, on to the next one */
+        if (ev == EV_HIT) {
+            r.dist -= 1;                   /* the counter inside the iteration of the hit */
+            if (r.shadow) {                /* kernel:706-710; nothing else of the hit block is live */
+                r.color.w = MULTI ? VR_ADD(r.alpha_before, 0.1f) : 0.1f;
+                if (!(MULTI && vr_more_lights(P, r))) { status = VR_ST_SHADOW_HIT; break; }
+                relight = true;
+            } else {
+                vr_canon_materialize(P, q, fm);
+                const vi3 hv = r.voxel;
+                const int st = vr_hit_block<AUX, MULTI>(P, r, voxel_data, a, q.first_hit_done);
+                if (st >= 0) { status = st; break; }
+                /* redirected: the ray restarts in the voxel it came from */
+                xr = (hv.x ^ r.voxel.x) | (hv.y ^ r.voxel.y) | (hv.z ^ r.voxel.z);
+                r.dist += 1;               /* kernel:714 ends the iteration of the hit */
+            }
+        } else if (ev == EV_UNBLOCKED_MAXDIST) {
+            if (!(MULTI && r.bounce < 2 && vr_more_lights(P, r))) { status = VR_ST_MAXDIST; break; }
+            relight = true;
+        } else {
+            if (!(MULTI && vr_more_lights(P, r))) {
+                r.dist -= 1;
+                r.fm = 0;                  /* the voxel is dead: only the colour of kernel:565 is needed */
+                vr_out_of_bounds(r);
+                status = VR_ST_OOB;
+                break;
+            }
+            relight = true;
+        }
+        if (MULTI && relight) {
+            if (!vr_next_light(P, r)) { status = VR_ST_SKIP_REDIRECT; break; }
+            r.dist += 1;
+            xr = -1;
+        }
     }
     if (slow) status = vr_canon_slow<AUX, MULTI>(P, r, a, q.first_hit_done);
     if (status == VR_ST_SKIP_REDIRECT) {

@@ -58,6 +58,9 @@ struct vr_ctx {
     /* native 64-tree */
     vr_node *d_nodes = nullptr;
     uint8_t *d_leaf_types = nullptr;
+    uint32_t *d_grid = nullptr;        /* top grid of the closed-form walk, built from d_nodes when first needed */
+    int grid_shift = 0, grid_bits = 0;
+    bool grid_tried = false;
     int levels = 0, tree_dim = 0;
     uint64_t n_nodes = 0, n_leaf_types = 0, solid_voxels = 0;
     bool tree_valid = false, tree_from_map = false;
@@ -152,8 +155,11 @@ void make_ray_table(int w, int h, std::vector<float> &out) {
 void free_tree(vr_ctx *c) {
     if (c->d_nodes) cudaFree(c->d_nodes);
     if (c->d_leaf_types) cudaFree(c->d_leaf_types);
+    if (c->d_grid) cudaFree(c->d_grid);
     c->d_nodes = nullptr;
     c->d_leaf_types = nullptr;
+    c->d_grid = nullptr;
+    c->grid_tried = false;
     c->tree_valid = false;
     c->n_nodes = c->n_leaf_types = c->solid_voxels = 0;
 }
@@ -194,6 +200,16 @@ int ensure_tree(vr_ctx *c) {
     if (!vr_native_from_ref(c->oct_desc.data(), c->oct_desc.size(), c->oct_root, (int)octdim, nullptr, t))
         return fail(c, "malformed octree descriptor buffer");
     return upload_tree(c, t, false);
+}
+
+/* top grid of the closed-form walk, built once per tree; leaves d_grid null when the tree is too shallow for one */
+int ensure_grid(vr_ctx *c) {
+    if (c->d_grid || c->grid_tried) return 1;
+    c->grid_tried = true;
+    const cudaError_t e = vr_build_grid_device(c->d_nodes, c->levels, c->tree_dim, c->stream, &c->d_grid, &c->grid_shift,
+                                               &c->grid_bits, &c->launches);
+    if (e != cudaSuccess && e != cudaErrorInvalidValue) return fail(c, "top grid build failed: %s", cudaGetErrorString(e));
+    return 1;
 }
 
 /* Builds the launch parameters from the retained pointers and the settings buffer, i.e. what the
@@ -271,6 +287,8 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     P.leaf_types = c->d_leaf_types;
     P.levels = c->levels;
     P.root_shift = 2 * (c->levels - 1);
+    P.grid = nullptr;
+    P.grid_shift = P.grid_bits = 0;
     if (svo && (c->tree_dim != P.dim[0] || P.dim[0] != P.dim[1] || P.dim[0] != P.dim[2]))
         return fail(c, "octree traversal needs a cubic power-of-two map");
     return 1;
@@ -285,6 +303,15 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
      * < 0.2 crossings up to 4096^3, where it is tested); beyond 16384^3 the merged walk is used whatever the option says */
     vr_launch_options opt = c->opt;
     if (P.dim[0] > 16384 && opt.walk == 1) opt.walk = 0;
+    if (use_svo && opt.walk == 2) {
+        /* the closed-form walk reads the top levels of the octree from a flat table (vr_canon.h), derived from the tree
+         * in HBM when it is first needed; trees of a single level (maps up to 4^3) and maps beyond 65536^3 take walk 0 */
+        if (!ensure_grid(c)) return 0;
+        if (!c->d_grid || P.dim[0] > 65536) opt.walk = 0;
+        P.grid = c->d_grid;
+        P.grid_shift = c->grid_shift;
+        P.grid_bits = c->grid_bits;
+    }
     VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &opt));
     if (timed) {
         VR_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
@@ -825,6 +852,24 @@ int vr_native_tree_info(vr_ctx *c, uint64_t *node_bytes, uint64_t *type_bytes, i
     if (levels) *levels = c->levels;
     if (dim) *dim = c->tree_dim;
     return 1;
+}
+
+uint64_t vr_top_grid_read(vr_ctx *c, uint32_t *host_out, uint64_t capacity, int32_t *grid_shift, int32_t *grid_bits) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (!c->tree_valid && !ensure_tree(c)) return 0;
+    if (!ensure_grid(c)) return 0;
+    if (!c->d_grid) { fail(c, "top_grid_read: the octree is too shallow for a top grid"); return 0; }
+    const uint64_t n = 1ull << (3 * c->grid_bits);
+    if (grid_shift) *grid_shift = c->grid_shift;
+    if (grid_bits) *grid_bits = c->grid_bits;
+    if (host_out && capacity >= n) {
+        if (cudaMemcpy(host_out, c->d_grid, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fail(c, "top_grid_read: copy failed");
+            return 0;
+        }
+    }
+    return n;
 }
 
 int vr_native_tree_copy(vr_ctx *c, void *device_nodes, void *device_types) {

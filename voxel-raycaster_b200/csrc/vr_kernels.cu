@@ -74,6 +74,23 @@ struct SmemStack {
     __device__ __forceinline__ uint32_t get(int level) const { return base[level * kThreads]; }
 };
 
+/* the same stack addressed through a 32-bit shared-memory address held in a register (the generic pointer above is
+ * re-derived from %tid and the CTA's shared window at every access) */
+struct SmemStackA {
+    uint32_t addr;
+    __device__ __forceinline__ void set(int level, uint32_t v) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + (uint32_t)level * (kThreads * 4)), "r"(v));
+    }
+    __device__ __forceinline__ uint32_t get(int level) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)level * (kThreads * 4)));
+        return v;
+    }
+};
+#ifndef VR_CANON_MIN_CTAS
+#define VR_CANON_MIN_CTAS 8
+#endif
+
 /* MULTI = the multi-light extension (LIGHT_COUNT > 1): a separate instantiation, so that the reference-parity
  * kernels do not carry its per-ray state */
 template <bool AUX, bool MULTI>
@@ -91,17 +108,23 @@ vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
 }
 
 template <bool AUX, int WALK, bool MULTI>
-__global__ void __launch_bounds__(kThreads, VR_SVO_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, WALK == 2 ? VR_CANON_MIN_CTAS : VR_SVO_MIN_CTAS)
 vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
     int x, y;
     size_t local;
     if (!cta_pixel(P, x, y, local)) return;
-    SmemStack stk{stack + threadIdx.x};
     uint32_t rgba;
     vr_aux a;
-    const bool write = WALK == 2 ? vr_trace_svo_canon<AUX, MULTI>(P, x, y, &rgba, &a, stk)
-                                 : vr_trace_svo<AUX, (WALK == 2 ? 0 : WALK), MULTI>(P, x, y, &rgba, &a, stk);
+    bool write;
+    if constexpr (WALK == 2) {
+        SmemStackA stk{(uint32_t)__cvta_generic_to_shared(stack + threadIdx.x)};
+        VR_PIN(stk.addr);
+        write = vr_trace_svo_canon<AUX, MULTI>(P, x, y, &rgba, &a, stk);
+    } else {
+        SmemStack stk{stack + threadIdx.x};
+        write = vr_trace_svo<AUX, WALK, MULTI>(P, x, y, &rgba, &a, stk);
+    }
     if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);

@@ -416,3 +416,67 @@ int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shif
         s -= 2;
     }
 }
+
+/* ---- top grid of the closed-form walk ------------------------------------------------------------------------- */
+bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits) {
+    const int root_shift = 2 * (levels - 1);
+    if (root_shift < 2 || dim < 8) return false;
+    const int g = root_shift - 4 > 2 ? root_shift - 4 : 2;
+    const int G = dim >> g;
+    if (G < 1) return false;
+    int bits = 0;
+    while ((1 << bits) < G) bits++;
+    grid.assign((size_t)G * G * G, 0u);
+    std::vector<uint8_t> cell((size_t)G * G * G, 0);      /* empty blocks: log2 edge of the aligned empty octree cell around */
+    /* (1) classify every block: descend to the slot of edge 1 << g that is the block */
+    for (int bz = 0; bz < G; bz++)
+        for (int by = 0; by < G; by++)
+            for (int bx = 0; bx < G; bx++) {
+                const int x = bx << g, y = by << g, z = bz << g;
+                const size_t i = (size_t)bx + (size_t)G * ((size_t)by + (size_t)G * bz);
+                uint32_t idx = 0, entry = 0;
+                for (int s = root_shift;; s -= 2) {
+                    const vr_node &n = nodes[idx];
+                    const unsigned long long m = (unsigned long long)n.mask_lo | ((unsigned long long)n.mask_hi << 32);
+                    const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
+                    if (!((m >> ci) & 1ull)) {
+                        int cs = s + ((((m >> (ci & 0x2A)) & 0x00330033ull) == 0ull) ? 1 : 0);
+                        while ((1 << cs) > dim) cs--;                  /* (a root wider than the map) */
+                        cell[i] = (uint8_t)cs;
+                        break;
+                    }
+                    idx = n.child_base + (uint32_t)__builtin_popcountll(m & ((1ull << ci) - 1ull));
+                    if (s == g) { entry = 0x80000000u | idx; break; }
+                }
+                grid[i] = entry;
+            }
+    /* (2) Chebyshev distance to the nearest non-empty block or to the outside of the map, minus one, by repeated erosion
+     * with the 3x3x3 cube: an empty block gets radius r when its 26 neighbours all exist and have radius >= r - 1 */
+    for (uint32_t r = 1; r <= VR_GRID_MAX_RADIUS; r++) {
+        bool any = false;
+        for (int bz = 1; bz < G - 1; bz++)
+            for (int by = 1; by < G - 1; by++)
+                for (int bx = 1; bx < G - 1; bx++) {
+                    const size_t i = (size_t)bx + (size_t)G * ((size_t)by + (size_t)G * bz);
+                    if (grid[i] != r - 1) continue;
+                    bool ok = true;
+                    for (int dz = -1; dz <= 1 && ok; dz++)
+                        for (int dy = -1; dy <= 1 && ok; dy++)
+                            for (int dx = -1; dx <= 1; dx++) {
+                                const uint32_t e = grid[(size_t)(bx + dx) + (size_t)G * ((size_t)(by + dy) + (size_t)G * (bz + dz))];
+                                if (e < r - 1 || (e & 0x80000000u)) { ok = false; break; }
+                            }
+                    if (ok) { grid[i] = r; any = true; }
+                }
+        if (!any) break;
+    }
+    /* (3) final form of the empty entries (vr_types.h): the wider of the two empty cells known around the block */
+    for (size_t i = 0; i < grid.size(); i++) {
+        if (grid[i] & 0x80000000u) continue;
+        const uint32_t d = grid[i];
+        grid[i] = (((2u * d + 1u) << g) > (1u << cell[i])) ? ((uint32_t)g | ((d << g) << 8)) : (uint32_t)cell[i];
+    }
+    *grid_shift = g;
+    *grid_bits = bits;
+    return true;
+}

@@ -49,6 +49,12 @@ bool vr_native_from_ref(const uint64_t *desc, uint64_t len, uint64_t root_index,
  * value `type`.  Produces exactly the arrays vr_native_from_dense gives for the equivalent dense map. */
 bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8_t type, vr_native_tree &out);
 
+/* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree: host version (the caster builds
+ * it on the device, vr_build.cu: vr_build_grid_device; this one serves the host emulation and checks that one).
+ * Returns false when the tree is too shallow for a grid (a single level: maps up to 4^3). */
+bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits);
+#define VR_GRID_MAX_RADIUS 63
+
 /* Point query on the native tree: voxel value (5/6) or 0, and the empty-cell shift if empty. */
 int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shift);
 

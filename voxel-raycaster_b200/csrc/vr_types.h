@@ -104,6 +104,15 @@ typedef struct vr_frame_params {
     const uint8_t *leaf_types;
     int32_t root_shift;            /* child shift of the root node = 2*(levels-1)             */
     int32_t levels;
+    /* top grid of the closed-form walk (walk = 2, vr_canon.h): the octree levels with child shift >= grid_shift flattened
+     * into one dense table over the blocks of edge 1 << grid_shift, grid[bx + (by + bz * G) * G] with G = 1 << grid_bits.
+     * Entry: bit 31 set = the block is not empty, bits 0-30 = index of the node (child shift grid_shift - 2) that covers
+     * it; bit 31 clear = the block is empty and lies in an empty cell [p & ~m, (p | m) + ext] per axis with
+     * m = (1 << (entry & 31)) - 1 and ext = entry >> 8: either the aligned empty octree cell around the block (ext = 0) or
+     * the block grown by its empty radius in blocks (Chebyshev distance to the nearest non-empty block or to the map
+     * boundary, minus one) -- whichever is wider. */
+    const uint32_t *grid;
+    int32_t grid_shift, grid_bits;
 } vr_frame_params;
 
 #endif
