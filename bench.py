@@ -144,6 +144,27 @@ def measured_peak_gbs() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def use_all_host_threads() -> int:
+    """The CPU legs run on every host core the process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    the OpenMP runtime of the oracle / reference libraries would obey: override it (before those libraries initialise
+    OpenMP, and through omp_set_num_threads for a runtime that is already up) and return the team size OpenMP will
+    actually use -- that number, not the core count, is what the JSON line reports as `cores`."""
+    import ctypes as C
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        g = C.CDLL("libgomp.so.1")
+        g.omp_set_num_threads(C.c_int(n))
+        g.omp_get_max_threads.restype = C.c_int
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return n
+
+
 def oracle_sample(scene, row_stride: int, threads: int = 0, lights: int = 1) -> tuple[float, int, int]:
     """Times the CPU restatement of the reference kernel (dense DDA over the char map, kernel:555-570) on
     every row_stride-th row.  Returns (seconds, rays in the sample, host threads)."""
@@ -160,7 +181,7 @@ def oracle_sample(scene, row_stride: int, threads: int = 0, lights: int = 1) -> 
     rays = int((a["status"] != O.ST_SKIP_PRIMARY).sum() + ((a["flags"] & O.FL_LIT) != 0).sum())
     if lights > 1:
         rays = int(cnt["primary_rays"] + cnt["shadow_rays"])
-    return dt, rays, threads or O.num_procs()
+    return dt, rays, threads or use_all_host_threads()
 
 
 class CpuReference:
@@ -174,6 +195,7 @@ class CpuReference:
     def __init__(self, scene, row_stride: int, lights: int = 1) -> None:
         self.scene, self.stride, self.lights = scene, row_stride, lights
         self.kind, self.lib = "port", None
+        use_all_host_threads()
         self.note = "reference OpenCL kernel restated in C++ (oracle/, no OpenCL runtime in the image)"
         self.dt0, self.rays, self.threads = oracle_sample(scene, row_stride, lights=lights)      # also the ray count of the sample
         if lights == 1 and scene.volume is not None:
@@ -211,6 +233,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()                       # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core
     scene = bench_scene(args.config, lights=args.lights)
     stride = args.ref_row_stride
     cpu = CpuReference(scene, stride, args.lights)

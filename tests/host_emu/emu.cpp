@@ -49,7 +49,7 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
     if (use_svo == 3) {
         int gs = 0, gb = 0;
         if (!vr_native_grid(tree.nodes.data(), tree.levels, n, grid, &gs, &gb)) return -3;
-        P.grid = grid.data(); P.grid_shift = gs; P.grid_bits = gb;
+        P.grid = grid.data(); P.grid_shift = gs; P.grid_bits = gb; P.grid_dim = 1 << gb;
     }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = 0; y < height; y++)

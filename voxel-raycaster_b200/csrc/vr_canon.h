@@ -48,6 +48,14 @@
 #define VR_JOIN(x) ((void)0)
 #endif
 
+/* marks a branch as one that must stay a branch (rare path): keeps ptxas from turning it into a chain of selects
+ * that every turn of the loop would pay for */
+#if defined(__CUDA_ARCH__)
+#define VR_RARE() asm volatile("" ::: "memory")
+#else
+#define VR_RARE() ((void)0)
+#endif
+
 VR_HD int vr_hibit(int x) {          /* index of the highest set bit of x != 0 (31 for negative x) */
 #if defined(__CUDA_ARCH__)
     return 31 - __clz(x);
@@ -89,17 +97,22 @@ VR_HD void vr_canon_enter(const vr_frame_params &P, vr_cray<Stack> &q) {
     VR_PIN(q.bx); VR_PIN(q.by); VR_PIN(q.bz); VR_PIN(q.flip); VR_PIN(q.gflip);
 }
 
-/* the reference's voxel / intersection_t / face_mask of the step just made */
+/* the reference's voxel / intersection_t / face_mask of the step just made, whose time was T: the axes of that step
+ * are those whose latest crossing has exactly that time (kernel:558: every axis whose time equals the minimum steps) */
 template <class Stack>
-VR_HD void vr_canon_materialize(const vr_frame_params &P, vr_cray<Stack> &q, int fm) {
+VR_HD void vr_canon_materialize(const vr_frame_params &P, vr_cray<Stack> &q, float T) {
     RayState &r = q.r;
     const int N = P.dim[0];
     r.step = {(q.flip & 1u) ? -1 : 1, (q.flip & 4u) ? -1 : 1, (q.flip & 16u) ? -1 : 1};   /* (not kept live across the walk) */
     r.voxel = {r.step.x < 0 ? N - 1 - q.px : q.px, r.step.y < 0 ? N - 1 - q.py : q.py, r.step.z < 0 ? N - 1 - q.pz : q.pz};
-    r.t.x = VR_FMA(VR_SUB(vr_bits2f(q.px - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
-    r.t.y = VR_FMA(VR_SUB(vr_bits2f(q.py - q.by), VR_MAGIC_F), r.delta.y, q.t0y);
-    r.t.z = VR_FMA(VR_SUB(vr_bits2f(q.pz - q.bz), VR_MAGIC_F), r.delta.z, q.t0z);
-    r.fm = fm;
+    const float kx = VR_SUB(vr_bits2f(q.px - q.bx), VR_MAGIC_F), ky = VR_SUB(vr_bits2f(q.py - q.by), VR_MAGIC_F),
+                kz = VR_SUB(vr_bits2f(q.pz - q.bz), VR_MAGIC_F);
+    r.t.x = VR_FMA(kx, r.delta.x, q.t0x);
+    r.t.y = VR_FMA(ky, r.delta.y, q.t0y);
+    r.t.z = VR_FMA(kz, r.delta.z, q.t0z);
+    r.fm = ((kx >= 1.0f && VR_FMA(VR_SUB(kx, 1.0f), r.delta.x, q.t0x) == T) ? 1 : 0) |
+           ((ky >= 1.0f && VR_FMA(VR_SUB(ky, 1.0f), r.delta.y, q.t0y) == T) ? 2 : 0) |
+           ((kz >= 1.0f && VR_FMA(VR_SUB(kz, 1.0f), r.delta.z, q.t0z) == T) ? 4 : 0);
 }
 
 /* The empty cell a walk crosses: the cube [p & ~m, (p | m) + ext] per axis (mirrored coordinates) -- an aligned
@@ -118,7 +131,7 @@ VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, v
     const int g = P.grid_shift;
     if (AUX) a->lookups++;
     if ((xr >> g) != 0) {                                                 /* another block */
-        const int G = 1 << P.grid_bits;
+        const int G = P.grid_dim;
         const uint32_t key = (uint32_t)((q.px >> g) + ((q.py >> g) + (q.pz >> g) * G) * G) ^ q.gflip;
 #if defined(__CUDA_ARCH__)
         const uint32_t e = __ldg(P.grid + key);
@@ -168,15 +181,15 @@ VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, v
  * T = min over the axes of the time of the crossing that leaves the cell; every axis then makes all its crossings with
  * time <= T (kernel:558: an axis steps when its time is <= the others', ties step together).
  * Returns the number of steps (multi-axis steps inside the cell are counted per axis: see DESIGN.md, tie rays);
- * fm = axes of the last step; xr = changed voxel bits. */
+ * T = time of the last step; tie = that step moved along more than one axis; xr = changed voxel bits. */
 template <class Stack>
-VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, int &fm, int &xr) {
+VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, float &T, bool &tie, int &xr) {
     const RayState &r = q.r;
     const int ox = (q.px | c.m) + c.ext, oy = (q.py | c.m) + c.ext, oz = (q.pz | c.m) + c.ext;   /* last voxel of the cell per axis */
     const float Tx = VR_FMA(VR_SUB(vr_bits2f(ox - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
     const float Ty = VR_FMA(VR_SUB(vr_bits2f(oy - q.by), VR_MAGIC_F), r.delta.y, q.t0y);
     const float Tz = VR_FMA(VR_SUB(vr_bits2f(oz - q.bz), VR_MAGIC_F), r.delta.z, q.t0z);
-    const float T = vr_min3(Tx, Ty, Tz);
+    T = vr_min3(Tx, Ty, Tz);
     /* per axis: k = the last crossing with time <= T.  The estimate RN((T - t0) / delta) is k or k + 1 (its error is
      * below 1e-2 crossings: |ray_dir| * delta_t = 1 +- 2^-24, at most 2^16 crossings), one evaluation decides. */
     const float mx = VR_ADD(VR_MUL(VR_SUB(T, q.t0x), q.ix), VR_MAGIC_F);
@@ -189,9 +202,13 @@ VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, int &fm, int &xr) 
     /* an axis whose next crossing lies beyond T makes none: the linear estimate may point far below that when T is
      * much smaller than the axis' first crossing time (negative get_oct_vox bias, kernel:353) */
     nx = nx > q.px ? nx : q.px; ny = ny > q.py ? ny : q.py; nz = nz > q.pz ? nz : q.pz;
-    fm = (Tx == T ? 1 : 0) | (Ty == T ? 2 : 0) | (Tz == T ? 4 : 0);
     int n = (nx - q.px) + (ny - q.py) + (nz - q.pz);
-    if (fm & (fm - 1)) n -= (fm == 7) ? 2 : 1;                            /* the axes of the last step moved together */
+    const bool ex = Tx == T, ey = Ty == T, ez = Tz == T;
+    tie = (ex && (ey || ez)) || (ey && ez);
+    if (tie) {                                                            /* the axes of the last step moved together */
+        VR_RARE();
+        n -= (ex && ey && ez) ? 2 : 1;
+    }
     xr = (nx ^ q.px) | (ny ^ q.py) | (nz ^ q.pz);
     q.px = nx; q.py = ny; q.pz = nz;
     return n;
@@ -202,7 +219,7 @@ VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, int &fm, int &xr) 
  * `bit` = its slot).  The caller guarantees that max_distance cannot be reached inside (a brick holds <= 10 steps).
  * Every step is observed here, so multi-axis steps are exact (n counts them once). */
 template <class Stack>
-VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, int &fm, int &xr, int &bit) {
+VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, float &T, int &xr, int &bit) {
     const RayState &r = q.r;
     const int lx = q.px & 3, ly = q.py & 3, lz = q.pz & 3;
     float kx = VR_SUB(vr_bits2f(q.px - q.bx), VR_MAGIC_F), ky = VR_SUB(vr_bits2f(q.py - q.by), VR_MAGIC_F),
@@ -213,8 +230,9 @@ VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, in
     const int cf = (int)q.flip;
     float ex, ey, ez;
     bool hit;
+    float mn;
     for (;;) {
-        const float mn = vr_min3(tx, ty, tz);
+        mn = vr_min3(tx, ty, tz);
         ex = (tx == mn) ? 1.0f : 0.0f;
         ey = (ty == mn) ? 1.0f : 0.0f;
         ez = (tz == mn) ? 1.0f : 0.0f;
@@ -230,7 +248,7 @@ VR_HD bool vr_canon_brick(vr_cray<Stack> &q, unsigned long long mask, int &n, in
     const int nx = q.px + (4 - lx) - (int)rx, ny = q.py + (4 - ly) - (int)ry, nz = q.pz + (4 - lz) - (int)rz;
     xr = (nx ^ q.px) | (ny ^ q.py) | (nz ^ q.pz);
     q.px = nx; q.py = ny; q.pz = nz;
-    fm = (ex != 0.0f ? 1 : 0) | (ey != 0.0f ? 2 : 0) | (ez != 0.0f ? 4 : 0);
+    T = mn;
     n = (int)steps;
     return hit;
 }
@@ -325,20 +343,25 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
         if ((unsigned)(q.px | q.py | q.pz) < (unsigned)N) {
             if (vr_canon_lookup<AUX>(P, q, xr, c, a) != 0) c = {0, 0, false};
         }
-        int voxel_data = 0, fm = 0;
+        int voxel_data = 0;
+        float T = 0.0f;                    /* time of the last step */
         enum { EV_HIT, EV_UNBLOCKED_MAXDIST, EV_UNBLOCKED_OOB } ev = EV_HIT;
         if (!(r.bounce < 2)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
         for (;;) {                         /* one turn per empty cell */
             const int nmax = r.max_distance - r.dist;                      /* iterations kernel:357 still allows */
             int n, bit = 0;
             bool known = false;            /* the brick walk already knows that the voxel entered is set */
+            bool tie = false;
             if (c.brick && nmax > 12) {
                 const int before = q.px + q.py + q.pz;
-                known = vr_canon_brick(q, q.node.mask, n, fm, xr, bit);
-                if (AUX && (q.px + q.py + q.pz - before) != n) a->flags |= VR_FL_TIE;
+                known = vr_canon_brick(q, q.node.mask, n, T, xr, bit);
+                if (AUX) tie = (q.px + q.py + q.pz - before) != n;
             } else {
-                if (c.brick) c = {0, 0, false};                            /* the ray is about to end: voxel by voxel */
-                n = vr_canon_walk(q, c, fm, xr);
+                if (c.brick) {                                             /* the ray is about to end: voxel by voxel */
+                    VR_RARE();
+                    c = {0, 0, false};
+                }
+                n = vr_canon_walk(q, c, T, tie, xr);
             }
             VR_JOIN(n);
             if (n > nmax) {                                                /* kernel:357 ends the loop inside this cell */
@@ -347,7 +370,7 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
                 break;
             }
             r.dist += n;
-            if (AUX && (fm & (fm - 1))) a->flags |= VR_FL_TIE;
+            if (AUX && tie) a->flags |= VR_FL_TIE;
             if (known) {                                                   /* the step landed on a set voxel of the brick */
                 voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
             } else {
@@ -367,7 +390,7 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
                 if (!(MULTI && vr_more_lights(P, r))) { status = VR_ST_SHADOW_HIT; break; }
                 relight = true;
             } else {
-                vr_canon_materialize(P, q, fm);
+                vr_canon_materialize(P, q, T);
                 const vi3 hv = r.voxel;
                 const int st = vr_hit_block<AUX, MULTI>(P, r, voxel_data, a, q.first_hit_done);
                 if (st >= 0) { status = st; break; }

@@ -288,7 +288,7 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     P.levels = c->levels;
     P.root_shift = 2 * (c->levels - 1);
     P.grid = nullptr;
-    P.grid_shift = P.grid_bits = 0;
+    P.grid_shift = P.grid_bits = P.grid_dim = 0;
     if (svo && (c->tree_dim != P.dim[0] || P.dim[0] != P.dim[1] || P.dim[0] != P.dim[2]))
         return fail(c, "octree traversal needs a cubic power-of-two map");
     return 1;
@@ -311,6 +311,7 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
         P.grid = c->d_grid;
         P.grid_shift = c->grid_shift;
         P.grid_bits = c->grid_bits;
+        P.grid_dim = 1 << c->grid_bits;
     }
     VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &opt));
     if (timed) {

@@ -112,7 +112,7 @@ typedef struct vr_frame_params {
      * the block grown by its empty radius in blocks (Chebyshev distance to the nearest non-empty block or to the map
      * boundary, minus one) -- whichever is wider. */
     const uint32_t *grid;
-    int32_t grid_shift, grid_bits;
+    int32_t grid_shift, grid_bits, grid_dim;       /* grid_dim = G */
 } vr_frame_params;
 
 #endif
