@@ -52,8 +52,8 @@ def test_canonical_walk_small(pkg, oracle, name):
     scene = pkg.scene.make_scene(name)
     desc, root = pkg.octree_generate(scene.volume)
     ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), canonical_t=True)
-    c = make_caster(pkg, scene, True)
-    assert c.set_option("walk", 2) and c.compute(), c.last_error()
+    c = make_caster(pkg, scene, True, walk=None)        # the library default IS the closed-form walk
+    assert c.compute(), c.last_error()
     assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 {name}")
     c.close()
 

@@ -14,9 +14,11 @@ pytestmark = pytest.mark.gpu
 SMALL = ["head", "tiny", "small", "features", "features-low", "features-high", "features-mirror"]
 
 
-def make_caster(pkg, scene, use_octree, assign_octree=True, aux=True):
+def make_caster(pkg, scene, use_octree, assign_octree=True, aux=True, walk=0):
+    """walk 0 (literal additions, merged walk: bit-identical to the reference) unless a test asks for another; the library
+    default is walk 2 (test_gpu_canonical.py)"""
     c = pkg.CUDACaster()
-    c.load_scene(scene, use_octree=use_octree, assign_octree=assign_octree)
+    c.load_scene(scene, use_octree=use_octree, assign_octree=assign_octree, walk=walk)
     if aux:
         assert c.enable_aux(True)
     return c
@@ -128,6 +130,7 @@ def test_octree_only_import(pkg, oracle):
     assert c.assign_octree(desc, root)
     assert c.assign_camera(scene.cam_dir, scene.cam_pos) and c.create_viewport(scene.width, scene.height)
     assert c.assign_lights(scene.lights) and c.create_texture_atlas(scene.atlas) and c.validate(), c.last_error()
+    assert c.set_option("walk", 0)
     assert c.enable_aux(True) and c.compute(), c.last_error()
     assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), "octree-only")
     # dense traversal without a map must fail loudly, not fall back
@@ -170,7 +173,7 @@ def test_bands_and_pipelined_frames(pkg, oracle):
         nb = (H + band_rows - 1) // band_rows
         for first in range(stride):
             c = pkg.CUDACaster()
-            c.load_scene(scene, use_octree=True, assign_octree=False)
+            c.load_scene(scene, use_octree=True, assign_octree=False, walk=0)
             assert c.set_bands(band_rows, stride, first)
             assert c.compute(), c.last_error()
             slab = c.draw()
@@ -180,7 +183,7 @@ def test_bands_and_pipelined_frames(pkg, oracle):
             c.close()
         assert np.array_equal(out, ref_rgba), (band_rows, stride)
     c = pkg.CUDACaster()
-    c.load_scene(scene, use_octree=True, assign_octree=False)
+    c.load_scene(scene, use_octree=True, assign_octree=False, walk=0)
     assert c.frame_begin() and c.frame_begin() and not c.frame_begin()      # at most two frames in flight
     a = c.frame_end().copy()
     b = c.frame_end().copy()
@@ -195,7 +198,7 @@ def test_native_tree_broadcast_roundtrip(pkg, oracle):
 
     scene = pkg.scene.make_scene("features")
     a = pkg.CUDACaster()
-    a.load_scene(scene, use_octree=True, assign_octree=False)
+    a.load_scene(scene, use_octree=True, assign_octree=False, walk=0)
     nb, tb, levels, dim = a.native_tree_info()
     nodes = torch.empty(nb, dtype=torch.uint8, device="cuda:0")
     types = torch.empty(tb, dtype=torch.uint8, device="cuda:0")
@@ -210,7 +213,7 @@ def test_native_tree_broadcast_roundtrip(pkg, oracle):
     assert b.assign_native_tree(nodes.data_ptr(), nb, types.data_ptr(), tb, levels, dim), b.last_error()
     assert b.assign_camera(scene.cam_dir, scene.cam_pos) and b.create_viewport(scene.width, scene.height)
     assert b.assign_lights(scene.lights) and b.create_texture_atlas(scene.atlas) and b.validate(), b.last_error()
-    assert b.compute(), b.last_error()
+    assert b.set_option("walk", 0) and b.compute(), b.last_error()
     assert np.array_equal(b.draw(), want)
     a.close()
     b.close()
@@ -362,7 +365,7 @@ def test_octree_save_load_and_l2_window(pkg, oracle, tmp_path):
     assert b.octree_load(str(path)), b.last_error()
     assert b.assign_camera(scene.cam_dir, scene.cam_pos) and b.create_viewport(scene.width, scene.height)
     assert b.assign_lights(scene.lights) and b.create_texture_atlas(scene.atlas) and b.validate(), b.last_error()
-    assert b.compute() and np.array_equal(b.draw(), ref_rgba)
+    assert b.set_option("walk", 0) and b.compute() and np.array_equal(b.draw(), ref_rgba)
     bad = tmp_path / "bad.vr64"
     bad.write_bytes(b"VR64" + bytes(40))
     assert not b.octree_load(str(bad)) and "not a valid octree" in b.last_error()
@@ -526,7 +529,7 @@ def test_multi_light_extension(pkg, oracle, name, count):
     one_rgba, one_aux, _ = oracle.raycast(scene, octree=(desc, root))
     for use_octree in (False, True):
         c = pkg.CUDACaster()
-        c.load_scene(scene, use_octree=use_octree, shadow_lights=count)
+        c.load_scene(scene, use_octree=use_octree, shadow_lights=count, walk=0)
         assert c.enable_aux(True) and c.compute(), c.last_error()
         assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"{name} lights={count} octree={use_octree}")
         if use_octree:
@@ -549,7 +552,7 @@ def test_multi_light_terrain_256(pkg, oracle):
     ref_rgba, ref_aux, cnt = oracle.raycast(scene, shadow_lights=2, want_counters=True)
     assert cnt["shadow_rays"] == 2 * int(((ref_aux["flags"] & 1) != 0).sum())
     c = pkg.CUDACaster()
-    c.load_scene(scene, use_octree=True, assign_octree=False, shadow_lights=2)
+    c.load_scene(scene, use_octree=True, assign_octree=False, shadow_lights=2, walk=0)
     assert c.enable_aux(True) and c.compute(), c.last_error()
     assert_same_frame(ref_rgba, ref_aux, c.draw(), c.read_aux(), "terrain 256, 2 lights")
     assert c.set_option("walk", 1) and c.compute()
@@ -674,10 +677,53 @@ def test_cuda_random_scenes(pkg, oracle):
         ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=nl)
         for use_octree in (False, True):
             c = pkg.CUDACaster()
-            c.load_scene(scene, use_octree=use_octree, shadow_lights=nl)
+            c.load_scene(scene, use_octree=use_octree, shadow_lights=nl, walk=0)
             assert c.enable_aux(True) and c.compute(), c.last_error()
             assert_walk_matches(ref_rgba, ref_aux, c.draw(), c.read_aux(), False, f"scene {it} octree={use_octree}")
             if use_octree:
                 assert c.set_option("walk", 1) and c.compute()
                 assert_walk_matches(ref_rgba, ref_aux, c.draw(), c.read_aux(), True, f"scene {it} per-axis walk")
             c.close()
+
+
+@pytest.mark.gpu
+def test_octree_load_rejects_corrupt_files(pkg, tmp_path):
+    """vr_octree_load (the on-disk format of the never-implemented Octree::Load, include/map/Octree.h:38) validates a
+    file before anything of it reaches the device: sizes against the file length before allocating, child pointers
+    level by level (inner levels inside the node array and in BFS order, the leaf level inside the type array)."""
+    import struct
+
+    scene = pkg.scene.make_scene("features")
+    a = make_caster(pkg, scene, True, assign_octree=False, aux=False)
+    good = tmp_path / "good.vr64"
+    assert a.octree_save(str(good))
+    a.close()
+    blob = bytearray(good.read_bytes())
+    magic, version, dim, levels, nn, nt = struct.unpack_from("<4sIiiQQ", blob, 0)
+    assert magic == b"VR64" and nn > 4 and len(blob) == 32 + 16 * nn + nt
+    b = pkg.CUDACaster()
+    assert b.init(0)
+
+    def rejected(data, what):
+        p = tmp_path / "bad.vr64"
+        p.write_bytes(bytes(data))
+        assert not b.octree_load(str(p)), what
+        assert "octree" in b.last_error()
+
+    assert b.octree_load(str(good)), b.last_error()
+    rejected(blob[:-7], "truncated")
+    rejected(blob + b"\0" * 5, "trailing bytes")
+    huge = bytearray(blob)
+    struct.pack_into("<Q", huge, 16, (1 << 32) - 1)                       # node count far beyond the file: no 64 GB resize
+    rejected(huge, "node count beyond the file")
+    ptr = bytearray(blob)
+    struct.pack_into("<I", ptr, 32 + 8, nn + 5)                            # root child_base beyond the node array
+    rejected(ptr, "inner child pointer out of range")
+    leaf = bytearray(blob)
+    struct.pack_into("<I", leaf, 32 + 16 * (nn - 1) + 8, nt)               # last leaf: types beyond the type array
+    rejected(leaf, "leaf child pointer out of range")
+    back = bytearray(blob)
+    struct.pack_into("<I", back, 32 + 16 * 1 + 8, 0)                       # a level-1 node pointing back at the root
+    rejected(back, "child pointer not in BFS order")
+    assert b.octree_load(str(good)), b.last_error()
+    b.close()

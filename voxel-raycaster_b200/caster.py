@@ -406,7 +406,8 @@ class CUDACaster:
         return s
 
     # -- convenience: the reference's init order (ref src/Application.cpp:27-88) -----------------
-    def load_scene(self, scene, use_octree: bool, assign_octree: bool = True, device: int = 0, shadow_lights: int = 1) -> None:
+    def load_scene(self, scene, use_octree: bool, assign_octree: bool = True, device: int = 0, shadow_lights: int = 1,
+                   walk: int | None = None) -> None:
         def must(ok: bool, what: str) -> None:
             if not ok:
                 raise RuntimeError(f"{what} failed: {self.last_error()}")
@@ -429,3 +430,5 @@ class CUDACaster:
         must(self.assign_lights(scene.lights), "assign_lights")
         must(self.create_texture_atlas(scene.atlas, (scene.tile, scene.tile)), "create_texture_atlas")
         must(self.validate(), "validate")
+        if walk is not None:       # None = the library default (2: closed-form crossing times); 0 / 1 = the exact walks
+            must(self.set_option("walk", walk), "set_option walk")

@@ -61,6 +61,8 @@ struct vr_ctx {
     uint32_t *d_grid = nullptr;        /* top grid of the closed-form walk, built from d_nodes when first needed */
     int grid_shift = 0, grid_bits = 0;
     bool grid_tried = false;
+    bool l2_persist = false;           /* option "l2_persist": access-policy window over d_nodes, re-applied per tree */
+    const void *l2_base = nullptr;
     int levels = 0, tree_dim = 0;
     uint64_t n_nodes = 0, n_leaf_types = 0, solid_voxels = 0;
     bool tree_valid = false, tree_from_map = false;
@@ -82,11 +84,12 @@ struct vr_ctx {
     int64_t *settings = nullptr;
     unsigned settings_pos = 0;
     std::map<std::string, unsigned> settings_indices;
+    std::map<std::string, std::string> setting_define;   /* setting name -> the define registered with it */
     std::map<std::string, std::string> defines;
 
     int used_svo = 0;
     int bias[3] = {0, 0, 0};
-    vr_launch_options opt = {0, 8, 3, 148, nullptr, 0};
+    vr_launch_options opt = {0, 8, 3, 148, nullptr, 2};      /* walk 2 = the closed-form walk is the default */
 };
 
 namespace {
@@ -107,6 +110,15 @@ int fail(vr_ctx *c, const char *fmt, ...) {
         cudaError_t e__ = (call);                                                               \
         if (e__ != cudaSuccess) return fail((c), "%s failed: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
+
+/* Host -> device copy that the kernels on c->stream are ordered after: the stream is created non-blocking, so a plain
+ * cudaMemcpy from pageable memory (which may return once the data is staged, before the DMA has landed) would not be. */
+cudaError_t upload(vr_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e;
+}
 
 int local_rows_padded(const vr_ctx *c) {
     if (c->height <= 0) return 0;
@@ -152,6 +164,8 @@ void make_ray_table(int w, int h, std::vector<float> &out) {
     }
 }
 
+int apply_l2_window(vr_ctx *c);
+
 void free_tree(vr_ctx *c) {
     if (c->d_nodes) cudaFree(c->d_nodes);
     if (c->d_leaf_types) cudaFree(c->d_leaf_types);
@@ -160,6 +174,11 @@ void free_tree(vr_ctx *c) {
     c->d_leaf_types = nullptr;
     c->d_grid = nullptr;
     c->grid_tried = false;
+    if (c->l2_persist && c->stream) {               /* the access-policy window pointed into the arrays just freed */
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     c->tree_valid = false;
     c->n_nodes = c->n_leaf_types = c->solid_voxels = 0;
 }
@@ -168,8 +187,8 @@ int upload_tree(vr_ctx *c, const vr_native_tree &t, bool from_map) {
     free_tree(c);
     VR_CUDA(c, cudaMalloc(&c->d_nodes, t.nodes.size() * sizeof(vr_node)));
     VR_CUDA(c, cudaMalloc(&c->d_leaf_types, t.leaf_types.size()));
-    VR_CUDA(c, cudaMemcpy(c->d_nodes, t.nodes.data(), t.nodes.size() * sizeof(vr_node), cudaMemcpyHostToDevice));
-    VR_CUDA(c, cudaMemcpy(c->d_leaf_types, t.leaf_types.data(), t.leaf_types.size(), cudaMemcpyHostToDevice));
+    VR_CUDA(c, upload(c, c->d_nodes, t.nodes.data(), t.nodes.size() * sizeof(vr_node)));
+    VR_CUDA(c, upload(c, c->d_leaf_types, t.leaf_types.data(), t.leaf_types.size()));
     c->levels = t.levels;
     c->tree_dim = t.dim;
     c->n_nodes = t.nodes.size();
@@ -190,6 +209,28 @@ bool setting_value(const vr_ctx *c, const char *define, int64_t *out) {
     return true;
 }
 
+/* (re)applies or clears the L2 access-policy window of option "l2_persist" for the CURRENT node array */
+int apply_l2_window(vr_ctx *c) {
+    cudaSetDevice(c->device);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (c->l2_persist && c->d_nodes) {
+        int max_win = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        size_t bytes = c->n_nodes * sizeof(vr_node);
+        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;      /* BFS order: top levels first */
+        VR_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+        attr.accessPolicyWindow.base_ptr = c->d_nodes;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    VR_CUDA(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (!c->l2_persist) cudaCtxResetPersistingL2Cache();
+    return 1;
+}
+
 int ensure_tree(vr_ctx *c) {
     if (c->tree_valid) return 1;
     if (!c->has_octree) return fail(c, "octree traversal requested but neither a cubic map nor an octree is assigned");
@@ -197,8 +238,12 @@ int ensure_tree(vr_ctx *c) {
     if (!setting_value(c, "OCTDIM", &octdim) || octdim < 2)
         return fail(c, "octree assigned but the OCTDIM setting is missing");
     vr_native_tree t;
-    if (!vr_native_from_ref(c->oct_desc.data(), c->oct_desc.size(), c->oct_root, (int)octdim, nullptr, t))
-        return fail(c, "malformed octree descriptor buffer");
+    try {                                                   /* (no exception may cross the C ABI: a huge OCTDIM means bad_alloc) */
+        if (!vr_native_from_ref(c->oct_desc.data(), c->oct_desc.size(), c->oct_root, (int)octdim, nullptr, t))
+            return fail(c, "malformed octree descriptor buffer");
+    } catch (const std::exception &e) {
+        return fail(c, "octree import failed: %s", e.what());
+    }
     return upload_tree(c, t, false);
 }
 
@@ -303,6 +348,10 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
      * < 0.2 crossings up to 4096^3, where it is tested); beyond 16384^3 the merged walk is used whatever the option says */
     vr_launch_options opt = c->opt;
     if (P.dim[0] > 16384 && opt.walk == 1) opt.walk = 0;
+    if (c->l2_persist && use_svo && c->l2_base != (const void *)c->d_nodes) {   /* the tree was rebuilt since the window was set */
+        if (!apply_l2_window(c)) return 0;
+        c->l2_base = c->d_nodes;
+    }
     if (use_svo && opt.walk == 2) {
         /* the closed-form walk reads the top levels of the octree from a flat table (vr_canon.h), derived from the tree
          * in HBM when it is first needed; trees of a single level (maps up to 4^3) and maps beyond 65536^3 take walk 0 */
@@ -359,7 +408,7 @@ int vr_init(vr_ctx **out, int device, unsigned flags) {
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess) {
         fail(c, "failed to create CUDA stream/events on device %d: %s", c->device, cudaGetErrorString(cudaGetLastError()));
-        delete c;
+        vr_destroy(c);                              /* releases whatever was created before the failure */
         return 0;
     }
     for (int i = 0; i < 2; i++) {
@@ -368,8 +417,8 @@ int vr_init(vr_ctx **out, int device, unsigned flags) {
     }
     c->stream = c->own_stream;
     cudaDeviceGetAttribute(&c->opt.num_sms, cudaDevAttrMultiProcessorCount, c->device);
-    if (cudaMalloc(&c->opt.counter, sizeof(unsigned int)) != cudaSuccess) { fail(c, "cudaMalloc failed"); delete c; return 0; }
-    if (!vr_create_settings_buffer(c)) { delete c; return 0; }
+    if (cudaMalloc(&c->opt.counter, sizeof(unsigned int)) != cudaSuccess) { fail(c, "cudaMalloc failed"); vr_destroy(c); return 0; }
+    if (!vr_create_settings_buffer(c)) { vr_destroy(c); return 0; }
     *out = c;
     return 1;
 }
@@ -441,7 +490,7 @@ int vr_create_viewport(vr_ctx *c, int width, int height, float v_fov, float h_fo
     make_ray_table(width, height, table);
     const size_t tbytes = table.size() * sizeof(float), ibytes = (size_t)width * height * 4;
     VR_CUDA(c, cudaMalloc(&c->d_ray_table, tbytes));
-    VR_CUDA(c, cudaMemcpy(c->d_ray_table, table.data(), tbytes, cudaMemcpyHostToDevice));
+    VR_CUDA(c, upload(c, c->d_ray_table, table.data(), tbytes));
     for (int i = 0; i < 2; i++) {
         VR_CUDA(c, cudaMalloc(&c->d_image[i], ibytes));
         VR_CUDA(c, cudaMallocHost(&c->h_image[i], ibytes));
@@ -502,14 +551,27 @@ int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
     if (c->d_map) vr_release_map(c);                       /* ref store_buffer: silently replaces (host:859-863) */
     const size_t bytes = (size_t)nx * ny * nz;
     VR_CUDA(c, cudaMalloc(&c->d_map, bytes));
-    VR_CUDA(c, cudaMemcpy(c->d_map, voxels, bytes, cudaMemcpyHostToDevice));
+    VR_CUDA(c, upload(c, c->d_map, voxels, bytes));
     c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
     /* traversal structure for the octree branch, built from the same voxels (types included) */
     if (nx == ny && ny == nz && (nx & (nx - 1)) == 0 && c->gpu_build && nx >= 4) {
         /* on the device, from the copy just uploaded (vr_build.cu) */
         vr_device_tree dt;
         memset(&dt, 0, sizeof(dt));
-        VR_CUDA(c, vr_build_tree_device(c->d_map, nx, c->stream, &dt, &c->launches));
+        const cudaError_t be = vr_build_tree_device(c->d_map, nx, c->stream, &dt, &c->launches);
+        if (be != cudaSuccess) {
+            /* e.g. out of memory for the builder's workspace: the host builder produces the same arrays */
+            cudaGetLastError();
+            fprintf(stderr, "[vrcaster] device octree build failed (%s): building on the host\n", cudaGetErrorString(be));
+            vr_native_tree t;
+            try {
+                if (!vr_native_from_dense(voxels, nx, t)) { vr_release_map(c); return fail(c, "assign_map: 64-tree build failed"); }
+            } catch (const std::exception &e) {
+                vr_release_map(c);
+                return fail(c, "assign_map: 64-tree build failed: %s", e.what());
+            }
+            return upload_tree(c, t, true);
+        }
         free_tree(c);
         c->d_nodes = dt.nodes;
         c->d_leaf_types = dt.types;
@@ -524,7 +586,11 @@ int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
         c->build_masks_ms = dt.masks_ms;
     } else if (nx == ny && ny == nz && (nx & (nx - 1)) == 0) {
         vr_native_tree t;
-        if (!vr_native_from_dense(voxels, nx, t)) return fail(c, "assign_map: 64-tree build failed");
+        try {
+            if (!vr_native_from_dense(voxels, nx, t)) return fail(c, "assign_map: 64-tree build failed");
+        } catch (const std::exception &e) {
+            return fail(c, "assign_map: 64-tree build failed: %s", e.what());
+        }
         if (!upload_tree(c, t, true)) return 0;
     } else if (c->tree_from_map) {
         free_tree(c);
@@ -538,7 +604,11 @@ int vr_assign_columns(vr_ctx *c, const int32_t *lo, const int32_t *hi, int dim, 
     cudaSetDevice(c->device);
     if (c->d_map) vr_release_map(c);
     vr_native_tree t;
-    if (!vr_native_from_columns(lo, hi, dim, (uint8_t)type, t)) return fail(c, "assign_columns: 64-tree build failed");
+    try {
+        if (!vr_native_from_columns(lo, hi, dim, (uint8_t)type, t)) return fail(c, "assign_columns: 64-tree build failed");
+    } catch (const std::exception &e) {
+        return fail(c, "assign_columns: 64-tree build failed: %s", e.what());
+    }
     return upload_tree(c, t, true);
 }
 
@@ -601,7 +671,7 @@ int vr_create_texture_atlas(vr_ctx *c, const uint8_t *rgba, int width, int heigh
     td.normalizedCoords = 0;
     VR_CUDA(c, cudaCreateTextureObject(&c->atlas_tex, &res, &td, nullptr));
     VR_CUDA(c, cudaMalloc(&c->d_atlas, (size_t)width * height * 4));
-    VR_CUDA(c, cudaMemcpy(c->d_atlas, rgba, (size_t)width * height * 4, cudaMemcpyHostToDevice));
+    VR_CUDA(c, upload(c, c->d_atlas, rgba, (size_t)width * height * 4));
     c->atlas_dim[0] = width; c->atlas_dim[1] = height;
     c->tile_dim[0] = tile_w; c->tile_dim[1] = tile_h;
     return 1;
@@ -613,6 +683,10 @@ int vr_create_settings_buffer(vr_ctx *c) {
     delete[] c->settings;
     c->settings = new int64_t[VR_SETTINGS_BUFFER_SIZE]();
     c->settings_pos = 0;
+    /* the defines registered through add_to_settings_buffer name slots of the buffer that is gone: with them left in
+     * place OCTENABLED would read 0 from the zeroed buffer (= the octree branch) and could not be added again */
+    for (auto &kv : c->settings_indices) c->defines.erase(c->setting_define[kv.first]);
+    c->setting_define.clear();
     c->settings_indices.clear();
     return 1;
 }
@@ -621,6 +695,10 @@ int vr_release_settings_buffer(vr_ctx *c) {
     if (!c || !c->settings) return 0;
     delete[] c->settings;
     c->settings = nullptr;
+    for (auto &kv : c->settings_indices) c->defines.erase(c->setting_define[kv.first]);
+    c->setting_define.clear();
+    c->settings_indices.clear();
+    c->settings_pos = 0;
     return 1;
 }
 
@@ -633,6 +711,7 @@ int vr_add_to_settings_buffer(vr_ctx *c, const char *setting_name, const char *d
     c->defines[define_name] = std::to_string(c->settings_pos);
     c->settings[c->settings_pos] = value;
     c->settings_indices[setting_name] = c->settings_pos;
+    c->setting_define[setting_name] = define_name;
     c->settings_pos++;
     return 1;
 }
@@ -790,23 +869,8 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     else if (n == "l2_persist") {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
         if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");
-        cudaSetDevice(c->device);
-        cudaStreamAttrValue attr;
-        memset(&attr, 0, sizeof(attr));
-        if (value) {
-            int max_win = 0;
-            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-            size_t bytes = c->n_nodes * sizeof(vr_node);
-            if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;      /* BFS order: top levels first */
-            VR_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
-            attr.accessPolicyWindow.base_ptr = c->d_nodes;
-            attr.accessPolicyWindow.num_bytes = bytes;
-            attr.accessPolicyWindow.hitRatio = 1.0f;
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        }
-        VR_CUDA(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-        if (!value) cudaCtxResetPersistingL2Cache();
+        c->l2_persist = value != 0;
+        if (!apply_l2_window(c)) return 0;
     }
     else return fail(c, "set_option: unknown option [%s]", name);
     return 1;
@@ -1001,22 +1065,57 @@ int vr_octree_load(vr_ctx *c, const char *path) {
     uint64_t nn = 0, nt = 0;
     bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "VR64", 4) == 0 && fread(&version, 4, 1, f) == 1 && version == 1 &&
               fread(&dim, 4, 1, f) == 1 && fread(&levels, 4, 1, f) == 1 && fread(&nn, 8, 1, f) == 1 && fread(&nt, 8, 1, f) == 1 &&
-              nn >= 1 && nn < (1ull << 32) && nt >= 1 && levels >= 1 && levels <= VR_MAX_LEVELS && dim >= 1 &&
-              !(dim & (dim - 1)) && (1 << (2 * levels)) >= dim;
-    vr_native_tree t;
+              nn >= 1 && nn < (1ull << 32) && nt >= 1 && nt < (1ull << 32) && levels >= 1 && levels <= VR_MAX_LEVELS && dim >= 1 &&
+              !(dim & (dim - 1)) && (1ll << (2 * levels)) >= dim;
+    /* the arrays must fit in what is left of the file BEFORE anything is allocated for them */
     if (ok) {
-        t.nodes.resize(nn);
-        t.leaf_types.resize(nt);
-        ok = fread(t.nodes.data(), sizeof(vr_node), nn, f) == nn && fread(t.leaf_types.data(), 1, nt, f) == nt;
+        const long at = ftell(f);
+        ok = at >= 0 && fseek(f, 0, SEEK_END) == 0;
+        const long end = ok ? ftell(f) : -1;
+        ok = ok && end >= at && (uint64_t)(end - at) == nn * sizeof(vr_node) + nt && fseek(f, at, SEEK_SET) == 0;
+    }
+    vr_native_tree t;
+    try {
+        if (ok) {
+            t.nodes.resize(nn);
+            t.leaf_types.resize(nt);
+            ok = fread(t.nodes.data(), sizeof(vr_node), nn, f) == nn && fread(t.leaf_types.data(), 1, nt, f) == nt;
+        }
+    } catch (const std::exception &) {
+        ok = false;
     }
     fclose(f);
     if (!ok) return fail(c, "octree_load: %s is not a valid octree file", path);
-    /* every child pointer must stay inside the arrays */
-    for (vr_node &n : t.nodes) {
-        const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
-        const uint64_t pc = (uint64_t)__builtin_popcountll(m);
-        if ((uint64_t)n.child_base + pc > (nn > nt ? nn : nt)) return fail(c, "octree_load: corrupt child pointer in %s", path);
-        n.aux = vr_node_planes(m);           /* derived from the mask: never trusted from the file */
+    /* Level by level from the root (nodes are stored in BFS order, the children of a level form one contiguous run):
+     * the child pointers of an inner level must stay inside the node array and land on the next level's run, those of
+     * the leaf level inside the type array.  A corrupt or truncated file must fail here, not as an out-of-bounds load
+     * on the device. */
+    {
+        uint64_t lo = 0, hi = 1;                                /* nodes [lo, hi) = the current level */
+        for (int l = 0; l < levels && ok; l++) {
+            const bool leaf = l == levels - 1;
+            uint64_t next_lo = ~0ull, next_hi = 0;
+            for (uint64_t i = lo; i < hi && ok; i++) {
+                vr_node &n = t.nodes[i];
+                const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
+                const uint64_t pc = (uint64_t)__builtin_popcountll(m);
+                n.aux = vr_node_planes(m);                      /* derived from the mask: never trusted from the file */
+                if (!pc) { ok = nn == 1; continue; }            /* only the root of an all-empty map has no children */
+                const uint64_t b = n.child_base;
+                if (leaf) { ok = b + pc <= nt; continue; }
+                ok = b >= hi && b + pc <= nn;
+                next_lo = b < next_lo ? b : next_lo;
+                next_hi = b + pc > next_hi ? b + pc : next_hi;
+            }
+            if (!leaf && ok) {
+                if (next_hi == 0) { ok = hi == nn; break; }     /* no children at all: the tree ends here */
+                ok = next_lo == hi;                             /* BFS order: the next level starts right after this one */
+                lo = next_lo; hi = next_hi;
+            } else if (leaf && ok) {
+                ok = hi == nn;                                  /* nothing may follow the leaf level */
+            }
+        }
+        if (!ok) return fail(c, "octree_load: corrupt child pointer in %s", path);
     }
     t.levels = levels;
     t.dim = dim;
@@ -1047,7 +1146,11 @@ int vr_octree_generate(const int8_t *voxels, int dim, uint64_t *out, uint64_t *e
     if (!voxels || !entries) return 0;
     std::vector<uint64_t> buf;
     uint64_t root = 0;
-    if (!vr_ref_octree_generate(voxels, dim, buf, &root)) return 0;
+    try {
+        if (!vr_ref_octree_generate(voxels, dim, buf, &root)) return 0;
+    } catch (const std::exception &) {
+        return 0;
+    }
     if (out) {
         if (*entries < buf.size()) { *entries = buf.size(); return 0; }
         memcpy(out, buf.data(), buf.size() * sizeof(uint64_t));

@@ -135,8 +135,8 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
  * pixel, ONE lane reserves that many new pixels with a single atomicAdd and the reservation is handed out to
  * the idle lanes with __ballot_sync / __shfl_sync / popc-prefix, so lanes never idle behind the slowest ray of
  * their tile.  Pixel order: index -> 8x4 tile -> 32x8 super tile (same as the static kernel), so one refill
- * batch is a compact screen block. */
-template <bool AUX>
+ * batch is a compact screen block.  WALK = the in-cell walk (0 merged, 1 per-axis), as in vr_svo_kernel. */
+template <bool AUX, int WALK>
 __global__ void __launch_bounds__(kThreads)
 vr_svo_persistent_kernel(const __grid_constant__ vr_frame_params P, unsigned int *counter, int refill_min) {
     __shared__ uint32_t stack[VR_MAX_LEVELS * kThreads];
@@ -183,7 +183,7 @@ vr_svo_persistent_kernel(const __grid_constant__ vr_frame_params P, unsigned int
             if (idle == 0xffffffffu && !more && !__any_sync(0xffffffffu, active)) break;
         }
         if (active) {
-            const int rc = vr_svo_round<AUX, 0, false>(P, q, &a);
+            const int rc = vr_svo_round<AUX, WALK, false>(P, q, &a);
             if (rc != VR_CELL_CONTINUE) {
                 if (rc != VR_CELL_NO_WRITE) reinterpret_cast<uint32_t *>(P.image)[local] = vr_svo_finish<AUX>(q, rc, &a);
                 if (AUX) {
@@ -217,8 +217,12 @@ cudaError_t vr_launch_raycast(const vr_frame_params &P, int use_svo, int with_au
         if (e != cudaSuccess) return e;
         unsigned ctas = (unsigned)(opt->num_sms * opt->ctas_per_sm);
         if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
-        if (aux) vr_svo_persistent_kernel<true><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
-        else vr_svo_persistent_kernel<false><<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
+        /* literal walks only (0 merged, 1 per-axis): the closed-form walk keeps 30 of 32 lanes busy with static tiles
+         * (profiles/r2_persistent_l2_evidence.txt), so it has no persistent variant and renders as walk 1 here */
+        void (*k)(vr_frame_params, unsigned int *, int) =
+            opt->walk == 0 ? (aux ? vr_svo_persistent_kernel<true, 0> : vr_svo_persistent_kernel<false, 0>)
+                           : (aux ? vr_svo_persistent_kernel<true, 1> : vr_svo_persistent_kernel<false, 1>);
+        k<<<ctas, block, 0, stream>>>(P, opt->counter, opt->refill_min);
     } else if (use_svo) {
         const int walk = opt ? opt->walk : 0;
         void (*k)(vr_frame_params) =
