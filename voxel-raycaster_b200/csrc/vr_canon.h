@@ -180,10 +180,13 @@ VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, v
 /* Walks the empty cell `c` the mirrored voxel p lies in, up to and including the step that leaves it.
  * T = min over the axes of the time of the crossing that leaves the cell; every axis then makes all its crossings with
  * time <= T (kernel:558: an axis steps when its time is <= the others', ties step together).
- * Returns the number of steps (multi-axis steps inside the cell are counted per axis: see DESIGN.md, tie rays);
- * T = time of the last step; tie = that step moved along more than one axis; xr = changed voxel bits. */
+ * Step count: the walk does not count steps, it moves the voxel.  Between multi-axis steps every step changes exactly one
+ * coordinate by one, so distance_traveled = dbase + px + py + pz with a per-segment constant dbase; a step along k axes
+ * at once lowers dbase by k - 1 (done here for the last step of the cell; ties strictly inside a cell are not observed:
+ * see DESIGN.md, tie rays).  Returns the new px + py + pz; T = time of the last step; tie = that step moved along more
+ * than one axis; xr = changed voxel bits.  `biased`: the frame has a get_oct_vox start bias (kernel:353). */
 template <class Stack>
-VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, float &T, bool &tie, int &xr) {
+VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, bool biased, float &T, int &dbase, bool &tie, int &xr) {
     const RayState &r = q.r;
     const int ox = (q.px | c.m) + c.ext, oy = (q.py | c.m) + c.ext, oz = (q.pz | c.m) + c.ext;   /* last voxel of the cell per axis */
     const float Tx = VR_FMA(VR_SUB(vr_bits2f(ox - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
@@ -199,19 +202,22 @@ VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, float &T, bool &ti
     if (VR_FMA(VR_SUB(mx, VR_MAGIC_F), r.delta.x, q.t0x) > T) nx -= 1;
     if (VR_FMA(VR_SUB(my, VR_MAGIC_F), r.delta.y, q.t0y) > T) ny -= 1;
     if (VR_FMA(VR_SUB(mz, VR_MAGIC_F), r.delta.z, q.t0z) > T) nz -= 1;
-    /* an axis whose next crossing lies beyond T makes none: the linear estimate may point far below that when T is
-     * much smaller than the axis' first crossing time (negative get_oct_vox bias, kernel:353) */
-    nx = nx > q.px ? nx : q.px; ny = ny > q.py ? ny : q.py; nz = nz > q.pz ? nz : q.pz;
-    int n = (nx - q.px) + (ny - q.py) + (nz - q.pz);
-    const bool ex = Tx == T, ey = Ty == T, ez = Tz == T;
-    tie = (ex && (ey || ez)) || (ey && ez);
+    if (biased) {
+        VR_RARE();
+        /* an axis whose first crossing lies beyond T makes none.  With 0 <= t0 <= delta_t and T >= 0 the estimate above is
+         * never below that; a negative start bias (a camera in a collapsed empty octree cell, kernel:353) makes T negative
+         * and the linear estimate of such an axis point far below zero */
+        nx = nx > q.px ? nx : q.px; ny = ny > q.py ? ny : q.py; nz = nz > q.pz ? nz : q.pz;
+    }
+    const float together = VR_ADD(VR_ADD(Tx == T ? 1.0f : 0.0f, Ty == T ? 1.0f : 0.0f), Tz == T ? 1.0f : 0.0f);
+    tie = together > 1.5f;
     if (tie) {                                                            /* the axes of the last step moved together */
         VR_RARE();
-        n -= (ex && ey && ez) ? 2 : 1;
+        dbase -= (int)together - 1;
     }
     xr = (nx ^ q.px) | (ny ^ q.py) | (nz ^ q.pz);
     q.px = nx; q.py = ny; q.pz = nz;
-    return n;
+    return nx + ny + nz;
 }
 
 /* Leaf brick (4^3 voxels, occupancy = mask): the step of kernel:558-560 with closed-form times, followed by a bit test
@@ -317,7 +323,8 @@ VR_HD int vr_canon_slow(const vr_frame_params &P, RayState &r, vr_aux *a, bool &
 /* Whole pixel.  Returns true if the pixel must be written (packed colour in *rgba_out).
  * distance_traveled bookkeeping: r.dist is the reference's counter at the top of its loop (kernel:357).  A walk of n
  * steps is n loop iterations; the last of them loads the voxel entered and, on a hit, runs the hit block with the
- * counter at r.dist + n - 1 before kernel:714 increments it. */
+ * counter one below the value it has at the top of the next iteration (kernel:714 increments it afterwards).  Inside
+ * the cell loop the counter is not kept: it is dbase + px + py + pz (vr_canon_walk). */
 template <bool AUX, bool MULTI, class Stack>
 VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *rgba_out, vr_aux *a, Stack &stk) {
     vr_cray<Stack> q;
@@ -329,6 +336,7 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
         return false;
     }
     const int N = P.dim[0];
+    const bool biased = P.bias[0] != 0.0f || P.bias[1] != 0.0f || P.bias[2] != 0.0f;      /* frame-uniform */
     q.first_hit_done = false;
     q.s = 0;
     int status = VR_ST_MAXDIST;
@@ -345,41 +353,51 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
         }
         int voxel_data = 0;
         float T = 0.0f;                    /* time of the last step */
-        enum { EV_HIT, EV_UNBLOCKED_MAXDIST, EV_UNBLOCKED_OOB } ev = EV_HIT;
+        enum { EV_HIT, EV_UNBLOCKED_MAXDIST, EV_UNBLOCKED_OOB } ev = EV_UNBLOCKED_MAXDIST;
         if (!(r.bounce < 2)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
-        for (;;) {                         /* one turn per empty cell */
-            const int nmax = r.max_distance - r.dist;                      /* iterations kernel:357 still allows */
-            int n, bit = 0;
-            bool known = false;            /* the brick walk already knows that the voxel entered is set */
-            bool tie = false;
-            if (c.brick && nmax > 12) {
-                const int before = q.px + q.py + q.pz;
-                known = vr_canon_brick(q, q.node.mask, n, T, xr, bit);
-                if (AUX) tie = (q.px + q.py + q.pz - before) != n;
-            } else {
-                if (c.brick) {                                             /* the ray is about to end: voxel by voxel */
-                    VR_RARE();
-                    c = {0, 0, false};
+        if (r.dist < r.max_distance) {                                     /* kernel:357 */
+            int dbase = r.dist - (q.px + q.py + q.pz);                     /* distance_traveled = dbase + px + py + pz */
+            for (;;) {                     /* one turn per empty cell */
+                int sum, bit = 0;
+                bool known = false;        /* the brick walk already knows that the voxel entered is set */
+                bool tie = false;
+                bool as_brick = false;
+                if (c.brick) {
+                    /* a brick holds at most 10 steps: walked as such unless the ray is about to end (then voxel by voxel) */
+                    as_brick = r.max_distance - (dbase + q.px + q.py + q.pz) > 12;
+                    if (!as_brick) c = {0, 0, false};
                 }
-                n = vr_canon_walk(q, c, T, tie, xr);
+                if (as_brick) {
+                    const int before = q.px + q.py + q.pz;
+                    int n;
+                    known = vr_canon_brick(q, q.node.mask, n, T, xr, bit);
+                    sum = q.px + q.py + q.pz;
+                    if (sum - before != n) {                               /* multi-axis steps inside the brick */
+                        VR_RARE();
+                        dbase -= sum - before - n;
+                        tie = true;
+                    }
+                } else {
+                    sum = vr_canon_walk(q, c, biased, T, dbase, tie, xr);
+                }
+                VR_JOIN(sum);
+                r.dist = dbase + sum;
+                if (r.dist > r.max_distance) {                             /* kernel:357 ended the loop inside this cell */
+                    r.dist = r.max_distance;
+                    ev = EV_UNBLOCKED_MAXDIST;
+                    break;
+                }
+                if (AUX && tie) a->flags |= VR_FL_TIE;
+                if (known) {                                               /* the step landed on a set voxel of the brick */
+                    voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
+                } else {
+                    if ((unsigned)(q.px | q.py | q.pz) >= (unsigned)N) { ev = EV_UNBLOCKED_OOB; break; }   /* kernel:563 */
+                    voxel_data = vr_canon_lookup<AUX>(P, q, xr, c, a);
+                }
+                VR_JOIN(voxel_data);
+                if (voxel_data == 5 || voxel_data == 6) { ev = EV_HIT; break; }
+                if (voxel_data != 0) c = {0, 0, false};
             }
-            VR_JOIN(n);
-            if (n > nmax) {                                                /* kernel:357 ends the loop inside this cell */
-                if (nmax > 0) r.dist = r.max_distance;
-                ev = EV_UNBLOCKED_MAXDIST;
-                break;
-            }
-            r.dist += n;
-            if (AUX && tie) a->flags |= VR_FL_TIE;
-            if (known) {                                                   /* the step landed on a set voxel of the brick */
-                voxel_data = (int)(int8_t)P.leaf_types[q.node.base + (uint32_t)VR_POPC64(q.node.mask & ((1ull << bit) - 1ull))];
-            } else {
-                if ((unsigned)(q.px | q.py | q.pz) >= (unsigned)N) { ev = EV_UNBLOCKED_OOB; break; }   /* kernel:563 */
-                voxel_data = vr_canon_lookup<AUX>(P, q, xr, c, a);
-            }
-            VR_JOIN(voxel_data);
-            if (voxel_data == 5 || voxel_data == 6) { ev = EV_HIT; break; }
-            if (voxel_data != 0) c = {0, 0, false};
         }
         /* ---- the segment ended */
         bool relight = false;              /* multi-light extension: this light is not blocked, on to the next one */
