@@ -356,6 +356,173 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
         dist.destroy_process_group()
 
 
+def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
+    """N > 1 with the multi-GPU frame scheduler of the C library (voxel-raycaster_b200/csrc/vr_mgpu.cu: vr_mgpu_*): one
+    process per GPU, the octree broadcast once with NCCL from rank 0, every rank's kernel storing its 32x4-pixel tiles
+    in place into the frame on the root GPU over NVLink, completion through device-stored counters polled by the root's
+    CPU (no per-frame collective), three frame buffers.  torch.distributed only supplies the barrier around the timed
+    region and the MAX over ranks of the device times, as the bench contract asks."""
+    import ctypes as C
+
+    use_svo = True
+    scene = bench_scene(args.config, with_volume=(rank == 0), lights=args.lights)
+    c = pkg.CUDACaster()
+
+    def must(ok, what):
+        if not ok:
+            raise RuntimeError(f"{what}: {c.last_error()}")
+
+    must(c.init(local_rank), "init")
+    must(c.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n), "OCTDIM")
+    must(c.add_to_settings_buffer("using_octree", "OCTENABLED", 0), "OCTENABLED")
+    must(c.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance), "MAX_DISTANCE")
+    if args.lights > 1:
+        must(c.add_to_settings_buffer("light_count", "LIGHT_COUNT", args.lights), "LIGHT_COUNT")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    must(c.set_stream(stream.cuda_stream), "set_stream")
+    t_build = time.perf_counter()
+    if rank == 0:
+        if scene.volume is not None:
+            must(c.assign_map(scene.volume), "assign_map")
+        else:
+            must(c.assign_columns(scene.columns[0], scene.columns[1]), "assign_columns")
+    t_build = time.perf_counter() - t_build
+    must(c.assign_camera(scene.cam_dir, scene.cam_pos), "assign_camera")
+    W, H = scene.width, scene.height
+    must(c.create_viewport(W, H, 0.625 * 90.0, 90.0), "create_viewport")
+    must(c.assign_lights(scene.lights), "assign_lights")
+    must(c.create_texture_atlas(scene.atlas, (scene.tile, scene.tile)), "create_texture_atlas")
+    # a session name unique to this launch, the same on every rank
+    nonce = [f"{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"]
+    dist.broadcast_object_list(nonce, src=0)
+    session = f"b{nonce[0]}"
+    must(c.mgpu_init(session + "d", world, rank, 0), "mgpu_init")
+    must(c.mgpu_broadcast_octree(), "mgpu_broadcast_octree")
+    must(c.validate(), "validate")
+    must(c.set_option("walk", args.walk), "walk")
+    st0 = c.stats()
+    bcast_bytes = int(st0.native_bytes)
+
+    # rays per frame: one untimed full-frame pass with aux records on rank 0
+    primary = shadow = node_fetches = lookups = steps_total = 0
+    if rank == 0:
+        must(c.set_tiles(1, 0) and c.enable_aux(True), "aux")
+        tmp = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        must(c.compute_into(tmp.data_ptr()), "compute_into")
+        torch.cuda.synchronize()
+        aux = c.read_aux()
+        primary, shadow = int((aux["status"] != 0).sum()), int(((aux["flags"] & 1) != 0).sum()) * args.lights
+        node_fetches, lookups = int(aux["node_fetches"].astype(np.int64).sum()), int(aux["lookups"].astype(np.int64).sum())
+        steps_total = int(aux["steps_total"].astype(np.int64).sum())
+        must(c.enable_aux(False) and c.set_tiles(world, rank), "aux off")
+        del aux, tmp
+    rays = primary + shadow
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def frames(count):
+        """`count` frames; the root collects (waits for and releases) frame k - 2 while frames k - 1 and k render, so the
+        CPU stays two frames ahead of the GPUs; the other ranks never wait -- the frame ring of the scheduler (4 buffers)
+        holds them back when they run ahead of the root"""
+        issued = []
+        for i in range(count):
+            k = c.mgpu_frame()
+            must(k >= 0, "mgpu_frame")
+            issued.append(k)
+            if rank == 0 and len(issued) > 2:
+                done = issued.pop(0)
+                must(c.mgpu_frame_wait(done) is not None, "mgpu_frame_wait")
+                c.mgpu_frame_release(done)
+        must(c.mgpu_flush(), "mgpu_flush")               # `stream` now waits for every frame: events on it bracket them all
+        ptr = 0
+        for k in issued:                                  # the last frames: everybody waits (the root for all ranks)
+            ptr = c.mgpu_frame_wait(k)
+            must(ptr is not None, "mgpu_frame_wait")
+            if k != issued[-1]:
+                c.mgpu_frame_release(k)
+        return issued[-1], ptr
+
+    last, ptr = frames(args.warmup)
+    c.mgpu_frame_release(last)
+    barrier()
+    launches0 = c.stats().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        last, ptr = frames(args.steps)
+        ev1.record(stream)
+        barrier()
+    launches = c.stats().kernel_launches - launches0
+    device_checksum = None
+    if rank == 0:
+        frame = torch.as_tensor(pkg.tiles._RawCuda(ptr, (H, W, 4)), device=dev)
+        device_checksum = int(frame[::64, ::64].sum().item())
+    c.mgpu_frame_release(last)
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    must(c.mgpu_shutdown(), "mgpu_shutdown")
+
+    # ---- end to end with the result in HOST memory: every rank copies its bands into a shared pinned host frame
+    must(c.mgpu_init(session + "h", world, rank, c.MGPU_HOST_FRAME), "mgpu_init host")
+    last, ptr = frames(args.warmup)
+    c.mgpu_frame_release(last)
+    barrier()
+    t0 = time.perf_counter()
+    last, ptr = frames(args.steps)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
+    checksum = 0
+    if rank == 0:
+        host = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(H, W, 4))
+        checksum = int(host[::64, ::64].astype(np.int64).sum())
+    c.mgpu_frame_release(last)
+    must(c.mgpu_shutdown(), "mgpu_shutdown host")
+
+    if rank == 0:
+        value = rays / (ms_per_step / 1e3) / 1e6
+        peak, peak_how = measured_peak_gbs()
+        ab = load_algorithmic_bytes(args.config, args.lights)
+        algo_bytes = float(ab["bytes_svo"]) if ab else None
+        st = c.stats()
+        roofline = None
+        if algo_bytes:
+            # consecutive frames overlap on the stream of a rank, so the effective duration per launch is the step time
+            achieved = algo_bytes / world / (ms_per_step / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": peak_how, "kernel": "vr_svo_kernel", "kernel_ms": ms_per_step,
+                        "algorithmic_bytes_per_launch": algo_bytes / world,
+                        "bytes_model": "P*(16+4) + 8*D_svo + 4*T from oracle counters (profiles/algorithmic_bytes_%s.json), 1/N per rank" % args.config}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gpu_launches": int(launches),
+            "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}",
+                       "mode": "svo", "walk": WALK_NOTES[args.walk],
+                       "kernel_variant": "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM",
+                       "parallelism": f"tiles{world}: C-library scheduler (vr_mgpu_*), 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place "
+                                      "into the root GPU's frame over NVLink (CUDA IPC), device-stored completion counters polled by the root's CPU, 4 frame buffers; "
+                                      "2 launches per frame and rank (ray kernel + 1-thread signal kernel)",
+                       "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
+                       "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
+                       "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
+                       "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
+                       "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum, "device_frame_checksum": device_checksum},
+            "roofline": roofline, "cpu_baseline": None,
+            "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": (5 * 4 + 10 * 4 + 64 * 8) * world,
+                    "d2h_bytes_per_step": W * H * 4,
+                    "how": "vr_mgpu_* with VR_MGPU_HOST_FRAME: every rank copies its row bands D2H into a shared page-locked host frame (POSIX shm), all PCIe links in parallel"},
+            "clocks": clocks.summary()}))
+    c.close()
+    dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,9 +548,10 @@ def main() -> None:
                     "first CTAs fill the tail of the current one); the kernel events then overlap, so roofline.kernel_ms is the step time")
     ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
                     help="N > 1 end-to-end leg: 'shared' = every rank copies its bands into a shared pinned host frame; 'root' = rank 0 copies the gathered frame")
-    ap.add_argument("--gather", default="direct", choices=["direct", "p2p", "nccl"],
-                    help="N > 1 frame assembly on the root GPU: 'direct' = 2-D tile interleave, the render kernels store their pixels in place into the "
-                    "root's frame over NVLink (CUDA IPC); 'p2p' = row bands + copy-engine push into the root's frame; 'nccl' = row bands + all_gather")
+    ap.add_argument("--gather", default="mgpu", choices=["mgpu", "direct", "p2p", "nccl"],
+                    help="N > 1 frame assembly on the root GPU: 'mgpu' (default) = the C library's scheduler (vr_mgpu_*: tiles stored in place over NVLink, "
+                    "device-stored completion counters); the others are the round-1 Python pipelines kept for comparison: 'direct' = the same tile stores with an "
+                    "NCCL all_reduce as completion token, 'p2p' = row bands + copy-engine push into the root's frame, 'nccl' = row bands + all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -409,6 +577,9 @@ def main() -> None:
     pkg = package()
     if args.config == "c5":
         run_views(args, pkg, torch, dist, rank, world, local_rank, dev)
+        return
+    if world > 1 and args.gather == "mgpu" and args.mode == "svo":
+        run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev)
         return
     use_svo = args.mode == "svo"
     scene = bench_scene(args.config, with_volume=(rank == 0 or not use_svo), lights=args.lights)

@@ -190,6 +190,39 @@ int vr_ipc_get_handle(vr_ctx *ctx, void *device_ptr, void *handle64);
 int vr_ipc_open_handle(vr_ctx *ctx, const void *handle64, void **device_ptr);
 int vr_ipc_close_handle(vr_ctx *ctx, void *device_ptr);
 int vr_push_bands(vr_ctx *ctx, const void *slab, void *frame, void *cuda_stream);
+/* ---- Multi-GPU frame scheduler (csrc/vr_mgpu.cu): what CLCaster::run_kernel (src/CLCaster.cpp:946-987) is to one OpenCL
+ * device, for the GPUs of one node.  ONE process per GPU, each with its own context that has been given the scene and
+ * the viewport like a single-GPU caster (rank 0 the map / octree; the others receive the octree by broadcast); a frame
+ * is split into the ray kernel's 32x4-pixel tiles, tile (tx, ty) on rank (tx + ty) mod world.
+ *   vr_mgpu_init            collective.  `session`: a name unique to this run, the same on every rank (it names the POSIX
+ *                           shared-memory segment through which the ranks find each other; nothing else is needed).
+ *                           flags 0: the frame is assembled in the root GPU's memory -- every rank's kernel stores its
+ *                           pixels in place over NVLink (CUDA-IPC mapping), no gather.  VR_MGPU_HOST_FRAME: the frame is
+ *                           assembled in shared pinned host memory, every rank copies its own row bands there over its
+ *                           own PCIe link.  Call after create_viewport.
+ *   vr_mgpu_broadcast_octree collective: rank 0's 64-tree to every rank (ncclBroadcast over NVLink), once per scene.
+ *   vr_mgpu_frame           every rank: enqueue this rank's share of the next frame (camera / lights / settings are read
+ *                           from the retained host pointers, as in vr_compute).  Does not wait for the GPU; blocks only
+ *                           while all `ring` (4) frame buffers are still unreleased.  *frame_no = the frame's number.
+ *   vr_mgpu_frame_wait      root: returns when every rank has finished frame_no; *rgba = the assembled frame (a device
+ *                           pointer, or a host pointer with VR_MGPU_HOST_FRAME), valid until vr_mgpu_frame_release.
+ *                           Other ranks: returns when their own share is done.
+ *   vr_mgpu_frame_release   root: the frame's buffer may be rendered into again.  (No-op elsewhere.)
+ *   vr_mgpu_flush           makes the context's stream (vr_set_stream) wait for the frames enqueued so far: consecutive frames
+ *                           run on two alternating streams of the scheduler (the next frame's first CTAs fill the tail
+ *                           of the current one), host-frame copies on a third.
+ *   vr_mgpu_shutdown        collective.
+ * Completion is signalled through per-rank counters in the shared segment, stored by the device after the rank's kernel
+ * and polled by the CPU with time-outs: no per-frame collective.  All calls return 1 on success, 0 + last error. */
+#define VR_MGPU_HOST_FRAME 1u
+int vr_mgpu_init(vr_ctx *ctx, const char *session, int world, int rank, unsigned flags);
+int vr_mgpu_broadcast_octree(vr_ctx *ctx);
+int vr_mgpu_frame(vr_ctx *ctx, uint64_t *frame_no);
+int vr_mgpu_frame_wait(vr_ctx *ctx, uint64_t frame_no, const uint8_t **rgba);
+int vr_mgpu_frame_release(vr_ctx *ctx, uint64_t frame_no);
+int vr_mgpu_flush(vr_ctx *ctx);        /* the context's stream waits for every frame enqueued so far (they run on the scheduler's own streams) */
+int vr_mgpu_shutdown(vr_ctx *ctx);
+
 /* Page-locks host memory the caller owns (e.g. a frame in a POSIX shared-memory segment mapped by every rank) so
  * that vr_push_bands can take it as `frame`: each rank then copies its own bands device->host over its own PCIe
  * link, straight into frame order -- the end-to-end path with a HOST result needs no gather on the device. */

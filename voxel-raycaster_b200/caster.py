@@ -86,6 +86,13 @@ SYMBOLS = {
     "vr_native_tree_info": (_i, [_vp, _u64p, _u64p, _i32p, _i32p]),
     "vr_native_tree_copy": (_i, [_vp, _vp, _vp]),
     "vr_top_grid_read": (C.c_uint64, [_vp, _vp, C.c_uint64, _i32p, _i32p]),
+    "vr_mgpu_init": (_i, [_vp, C.c_char_p, _i, _i, C.c_uint]),
+    "vr_mgpu_broadcast_octree": (_i, [_vp]),
+    "vr_mgpu_frame": (_i, [_vp, _u64p]),
+    "vr_mgpu_frame_wait": (_i, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "vr_mgpu_frame_release": (_i, [_vp, C.c_uint64]),
+    "vr_mgpu_flush": (_i, [_vp]),
+    "vr_mgpu_shutdown": (_i, [_vp]),
     "vr_assign_native_tree": (_i, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int32, C.c_int32]),
     "vr_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "vr_device_free": (_i, [_vp, _vp]),
@@ -341,6 +348,40 @@ class CUDACaster:
         if not self._lib.vr_native_tree_info(self._ctx, C.byref(nb), C.byref(tb), C.byref(lv), C.byref(dm)):
             raise RuntimeError(self.last_error())
         return int(nb.value), int(tb.value), int(lv.value), int(dm.value)
+
+    # ---- multi-GPU frame scheduler (csrc/vr_mgpu.cu); thin bindings, one call each
+    MGPU_HOST_FRAME = 1
+
+    def mgpu_init(self, session: str, world: int, rank: int, flags: int = 0) -> bool:
+        try:                       # the scheduler uses the NCCL copy the process has already loaded: PyTorch's, if it is around
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+        return bool(self._lib.vr_mgpu_init(self._ctx, session.encode(), world, rank, flags))
+
+    def mgpu_broadcast_octree(self) -> bool:
+        return bool(self._lib.vr_mgpu_broadcast_octree(self._ctx))
+
+    def mgpu_frame(self) -> int:
+        """enqueues this rank's share of the next frame; returns the frame number (-1 on failure)"""
+        k = C.c_uint64(0)
+        return int(k.value) if self._lib.vr_mgpu_frame(self._ctx, C.byref(k)) else -1
+
+    def mgpu_frame_wait(self, frame_no: int) -> int | None:
+        """root: address of the assembled frame (device, or host with MGPU_HOST_FRAME); None on failure; 0 on other ranks"""
+        ptr = _vp()
+        if not self._lib.vr_mgpu_frame_wait(self._ctx, frame_no, C.byref(ptr)):
+            return None
+        return int(ptr.value or 0)
+
+    def mgpu_frame_release(self, frame_no: int) -> bool:
+        return bool(self._lib.vr_mgpu_frame_release(self._ctx, frame_no))
+
+    def mgpu_flush(self) -> bool:
+        return bool(self._lib.vr_mgpu_flush(self._ctx))
+
+    def mgpu_shutdown(self) -> bool:
+        return bool(self._lib.vr_mgpu_shutdown(self._ctx))
 
     def top_grid(self) -> tuple[np.ndarray, int, int]:
         """(grid entries as uint32[G, G, G] indexed [z, y, x], block shift, log2 G) of the closed-form walk's top grid."""
