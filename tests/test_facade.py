@@ -8,6 +8,8 @@ ROOT = Path(__file__).resolve().parent.parent
 SRC = r'''
 #include "CUDACaster.hpp"
 #include <cstdio>
+#include <cstring>
+#include <unistd.h>
 int main() {
     CUDACaster c;
     bool ok = c.init(0);                       // false without a GPU: must not crash, must report why
@@ -25,6 +27,19 @@ int main() {
     std::vector<uint8_t> frame;
     ok = ok && c.draw(frame) && frame.size() == 64u * 48u * 4u;
     std::printf("frame=%d\n", (int)ok);
+    if (!ok) return 1;
+    // the multi-GPU frame loop of the library with a world of one: same frame, in shared host memory
+    char session[64];
+    std::snprintf(session, sizeof(session), "facade_%d", (int)getpid());
+    ok = c.mgpu_init(session, 1, 0, true) && c.mgpu_broadcast_octree();
+    for (int i = 0; ok && i < 6; i++) {
+        uint64_t k = 0;
+        const uint8_t *rgba = nullptr;
+        ok = c.mgpu_frame(&k) && k == (uint64_t)i && c.mgpu_frame_wait(k, &rgba) && rgba != nullptr
+          && std::memcmp(rgba, frame.data(), frame.size()) == 0 && c.mgpu_frame_release(k);
+    }
+    ok = ok && c.mgpu_shutdown();
+    std::printf("mgpu=%d %s\n", (int)ok, ok ? "" : c.last_error());
     return ok ? 0 : 1;
 }
 '''
@@ -41,3 +56,21 @@ def test_facade_compiles_and_links(pkg, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "init=" in r.stdout
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_facade_renders_and_schedules_on_gpu(pkg, tmp_path):
+    """The same C++ program on a GPU: one frame through CUDACaster (compute + draw) and six frames through the library's
+    multi-GPU frame loop (vr_mgpu_*, world of one, frame in shared host memory) that must equal it byte for byte."""
+    src = tmp_path / "facade.cpp"
+    src.write_text(SRC)
+    exe = tmp_path / "facade"
+    lib_dir = ROOT / "voxel-raycaster_b200"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++14", "-Wall", "-I", str(lib_dir / "csrc"), str(src), "-o", str(exe),
+                        "-L", str(lib_dir), "-lvrcaster", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "init=1" in r.stdout and "frame=1" in r.stdout and "mgpu=1" in r.stdout, r.stdout + r.stderr

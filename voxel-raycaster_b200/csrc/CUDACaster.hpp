@@ -91,6 +91,19 @@ public:
         return vr_remove_from_settings_buffer(ctx_, setting_name.c_str()) != 0;
     }
 
+    /* ---- beyond the reference: one CUDACaster per process and GPU, frames split over the GPUs of the node
+     * (include/vr_caster.h: vr_mgpu_*).  Where Application::game_loop calls compute() + draw() (ref src/Application.cpp:
+     * 151-159), a multi-GPU loop calls frame() on every rank and frame_wait() / frame_release() on rank 0. */
+    bool set_option(const std::string &name, int64_t value) { return vr_set_option(ctx_, name.c_str(), value) != 0; }
+    bool mgpu_init(const std::string &session, int world, int rank, bool host_frame = false) {
+        return vr_mgpu_init(ctx_, session.c_str(), world, rank, host_frame ? VR_MGPU_HOST_FRAME : 0u) != 0;
+    }
+    bool mgpu_broadcast_octree() { return vr_mgpu_broadcast_octree(ctx_) != 0; }
+    bool mgpu_frame(uint64_t *frame_no) { return vr_mgpu_frame(ctx_, frame_no) != 0; }
+    bool mgpu_frame_wait(uint64_t frame_no, const uint8_t **rgba) { return vr_mgpu_frame_wait(ctx_, frame_no, rgba) != 0; }
+    bool mgpu_frame_release(uint64_t frame_no) { return vr_mgpu_frame_release(ctx_, frame_no) != 0; }
+    bool mgpu_shutdown() { return vr_mgpu_shutdown(ctx_) != 0; }
+
     const char *last_error() const { return vr_last_error(ctx_); }
     vr_ctx *handle() { return ctx_; }
 
