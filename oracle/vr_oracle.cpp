@@ -253,6 +253,7 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
     int distance_traveled = 0;                                            /* kernel:325-337 */
     int max_distance = s->max_distance;
     unsigned bounce_count = 0;
+    const unsigned max_bounces = s->max_bounces > 0 ? (unsigned)s->max_bounces : 2u;   /* kernel:357 hard-codes 2; 0 = that */
     i3 face_mask = {0, 0, 0};
     int voxel_data = 0;
     f3 face_position = {0, 0, 0};
@@ -333,8 +334,8 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
 
     uint8_t status = VRO_ST_MAXDIST;
     for (;;) {
-        if (!(distance_traveled < max_distance && bounce_count < 2)) {    /* kernel:357 */
-            if (shadow_ray && light_i + 1 < n_lights && bounce_count < 2) {   /* extension: this light is not blocked */
+        if (!(distance_traveled < max_distance && bounce_count < max_bounces)) {    /* kernel:357 */
+            if (shadow_ray && light_i + 1 < n_lights && bounce_count < max_bounces) {   /* extension: this light is not blocked */
                 if (!next_light()) { finish(VRO_ST_SKIP_REDIRECT, distance_traveled); return; }
                 continue;
             }
@@ -525,7 +526,7 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
         }
         distance_traveled++;                                              /* kernel:714 */
     }
-    if (status == VRO_ST_MAXDIST && bounce_count >= 2) status = VRO_ST_BOUNCES;
+    if (status == VRO_ST_MAXDIST && bounce_count >= max_bounces) status = VRO_ST_BOUNCES;
 
     float m = 1.0f - cl_max(fog_distance / 700.0f, 0.0f);                 /* kernel:716 */
     color = {0.0f + (color.x - 0.0f) * m, 0.0f + (color.y - 0.0f) * m, 0.0f + (color.z - 0.0f) * m,

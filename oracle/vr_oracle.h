@@ -79,6 +79,9 @@ typedef struct vro_scene {
      * parity chain: crossing times in closed form, t(k) = fma(k, delta_t, t0) -- the arithmetic of
      * the octree kernel's walk = 2.  Not part of the reference; see vr_oracle.cpp. */
     int32_t canonical_t;
+    /* kernel:357 `bounce_count < 2`: lifted into a parameter like max_distance (0 = the reference's 2).  The reflection
+     * limit as a setting is on the reference's own TODO list (src/main.cpp:31-33). */
+    int32_t max_bounces;
 } vro_scene;
 
 /* Per-pixel auxiliary record, 32 bytes.  The reference kernel only writes RGBA8; these expose

@@ -40,6 +40,7 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
     P.atlas = atlas; P.atlas_dim[0] = atlas_w; P.atlas_dim[1] = atlas_h;
     P.atlas_scale[0] = atlas_w / tile_w; P.atlas_scale[1] = atlas_h / tile_h;
     P.max_distance = max_distance;
+    P.max_bounces = 2;
     if (use_svo) {
         if (!vr_native_from_dense(map, n, tree)) return -1;
         P.nodes = tree.nodes.data(); P.leaf_types = tree.leaf_types.data();

@@ -68,6 +68,7 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
     P.atlas = atlas; P.atlas_dim[0] = atlas_w; P.atlas_dim[1] = atlas_h;
     P.atlas_scale[0] = atlas_w / tile_w; P.atlas_scale[1] = atlas_h / tile_h;
     P.max_distance = max_distance;
+    P.max_bounces = 2;
     P.nodes = tree.nodes.data(); P.leaf_types = tree.leaf_types.data();
     P.levels = tree.levels; P.root_shift = 2 * (tree.levels - 1);
 

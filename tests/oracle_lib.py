@@ -36,7 +36,7 @@ class VroScene(C.Structure):
         ("octdim", C.c_int64), ("oct_root_index", C.c_int64),
         ("max_distance", C.c_int32), ("shadow_lights", C.c_int32),
         ("col_lo", C.POINTER(C.c_int32)), ("col_hi", C.POINTER(C.c_int32)),
-        ("canonical_t", C.c_int32),
+        ("canonical_t", C.c_int32), ("max_bounces", C.c_int32),
     ]
 
 
@@ -112,7 +112,7 @@ def trig_of(cam_dir) -> np.ndarray:
 def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None,
             rows: tuple[int, int] | None = None, want_aux: bool = True, want_counters: bool = False,
             count_svo: bool = False, threads: int = 0, max_distance: int | None = None, row_stride: int = 1,
-            shadow_lights: int = 1, canonical_t: bool = False, keep_near: bool = False):
+            shadow_lights: int = 1, canonical_t: bool = False, keep_near: bool = False, max_bounces: int = 0):
     """Runs the restated reference kernel (dense branch) on a scene.Scene.
     Returns (rgba [H,W,4] prefilled with (255,255,255,100), aux or None, counters dict or None)."""
     w, h = scene.width, scene.height
@@ -150,6 +150,7 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
     s.octdim = scene.n
     s.max_distance = scene.max_distance if max_distance is None else max_distance
     s.shadow_lights = shadow_lights          # 1 = the reference (light 0 only); > 1 = the multi-light extension
+    s.max_bounces = max_bounces              # 0 = the reference's 2 (kernel:357)
     s.canonical_t = 1 if canonical_t else 0  # False = the reference; True = "Oracle-B" (closed-form crossing times)
     rgba = np.empty((h, w, 4), dtype=np.uint8)
     rgba[...] = (255, 255, 255, 100)

@@ -211,3 +211,33 @@ def test_top_grid_device_equals_host(pkg, kind):
     c.close()
     assert (gs, gb) == (rs, rb) and grid.shape == ref.shape
     assert np.array_equal(grid, ref), f"{kind}: {int((grid != ref).sum())} entries differ"
+
+
+@pytest.mark.parametrize("limit", [1, 3, 5])
+def test_bounce_limit_setting(pkg, oracle, limit):
+    """kernel:357 hard-codes `bounce_count < 2`; the limit as a setting (MAX_BOUNCES) is on the reference's TODO list
+    (src/main.cpp:31-33).  64^3 terrain with 5 % mirrors (type-6 voxels): dense kernel and octree kernel (exact walk) equal the
+    oracle with the same limit on every pixel, the closed-form walk equals Oracle-B; without the setting the limit is 2."""
+    from conftest import assert_same_frame
+
+    S = pkg.scene
+    vol = S.terrain_map(64, "shell", reflect_fraction=0.05)
+    pos, direction = S.make_camera(64, S.heightfield(64), 3)
+    scene = S.Scene(64, vol, 320, 180, pos, direction, S.make_lights(64), max_distance=192)
+    desc, root = pkg.octree_generate(scene.volume)
+    a_rgba, a_aux, _ = oracle.raycast(scene, octree=(desc, root), max_bounces=limit)
+    b_rgba, b_aux, _ = oracle.raycast(scene, octree=(desc, root), max_bounces=limit, canonical_t=True)
+    two, two_aux, _ = oracle.raycast(scene, octree=(desc, root))
+    assert ((a_aux["flags"] & 2) != 0).any()
+    if limit != 3:                                             # (in this scene every ray that bounces twice also bounces a third time)
+        assert not np.array_equal(two_aux["status"], a_aux["status"])
+    for use_octree in (False, True):
+        c = make_caster(pkg, scene, use_octree)
+        assert c.compute() and np.array_equal(c.draw(), two)
+        assert c.add_to_settings_buffer("max_bounces", "MAX_BOUNCES", limit)
+        assert c.compute(), c.last_error()
+        assert_same_frame(a_rgba, a_aux, c.draw(), c.read_aux(), f"limit {limit} octree={use_octree}")
+        if use_octree:
+            assert c.set_option("walk", 2) and c.compute()
+            assert_equals_oracle_b(b_rgba, b_aux, c.draw(), c.read_aux(), f"limit {limit} walk 2")
+        c.close()

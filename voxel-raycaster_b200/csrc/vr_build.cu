@@ -23,7 +23,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include "vr_build.h"
@@ -380,5 +383,253 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cu
     *grid_out = grid;
     *grid_shift = g;
     *grid_bits = bits;
+    return cudaSuccess;
+}
+
+/* ---- 64-tree from a column description, built in HBM without the N^3 volume and without a dense workspace ----------
+ * Column (x, y) is solid for lo[x + N y] <= z <= hi[x + N y] (vr_assign_columns; 4096^3 = 64 GiB dense cannot exist).
+ * Only the bricks that can hold a voxel are ever materialised ("streaming SVO builder ... without a dense
+ * array"):
+ *   1. vr_col_count     per brick column (4x4 voxel columns): the range of brick layers its columns touch;
+ *   2. exclusive scan   -> where the brick column's (key, mask) pairs go;
+ *   3. vr_col_bricks    per brick column: the 64-bit occupancy mask of every touched brick + its hierarchical key;
+ *   4. radix sort by key (empty masks get the key ~0 and fall off the end): ascending key = breadth-first order;
+ *   5. per level, bottom up: reduce-by-key over key >> 6 -- OR of the child bits = the parent's mask, MIN of the child
+ *      positions = where its children start -- then vr_pair_nodes writes the level's nodes.
+ * Emits exactly the arrays vr_native_from_columns (vr_octree.cpp) produces. */
+namespace {
+
+struct KeyParent {
+    __host__ __device__ uint32_t operator()(uint32_t k) const { return k >> 6; }
+};
+struct KeyBit {
+    __host__ __device__ unsigned long long operator()(uint32_t k) const { return 1ull << (k & 63u); }
+};
+struct BitOr {
+    __host__ __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a | b; }
+};
+struct MinU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; }
+};
+
+__device__ __forceinline__ void col_range(const int32_t *lo, const int32_t *hi, int dim, unsigned bx, unsigned by, int &zmin, int &zmax) {
+    zmin = 0x7fffffff; zmax = -1;
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++) {
+            const size_t c = (size_t)(4 * bx + x) + (size_t)dim * (size_t)(4 * by + y);
+            int a = lo[c], b = hi[c];
+            a = a < 0 ? 0 : a;
+            b = b > dim - 1 ? dim - 1 : b;
+            if (a > b) continue;
+            zmin = a < zmin ? a : zmin;
+            zmax = b > zmax ? b : zmax;
+        }
+}
+
+__global__ void vr_col_count(const int32_t *__restrict__ lo, const int32_t *__restrict__ hi, int dim, int nb, uint32_t *__restrict__ count) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)(nb * nb)) return;
+    int zmin, zmax;
+    col_range(lo, hi, dim, i % (unsigned)nb, i / (unsigned)nb, zmin, zmax);
+    count[i] = zmax < 0 ? 0u : (uint32_t)((zmax >> 2) - (zmin >> 2) + 1);
+}
+
+__global__ void vr_col_bricks(const int32_t *__restrict__ lo, const int32_t *__restrict__ hi, int dim, int nb, int digits,
+                              const uint32_t *__restrict__ offset, uint32_t *__restrict__ keys, unsigned long long *__restrict__ masks) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)(nb * nb)) return;
+    const unsigned bx = i % (unsigned)nb, by = i / (unsigned)nb;
+    int zmin, zmax;
+    col_range(lo, hi, dim, bx, by, zmin, zmax);
+    if (zmax < 0) return;
+    int a[16], b[16];
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++) {
+            const size_t c = (size_t)(4 * bx + x) + (size_t)dim * (size_t)(4 * by + y);
+            a[x + 4 * y] = lo[c] < 0 ? 0 : lo[c];
+            b[x + 4 * y] = hi[c] > dim - 1 ? dim - 1 : hi[c];
+        }
+    uint32_t at = offset[i];
+    for (int bz = zmin >> 2; bz <= (zmax >> 2); bz++, at++) {
+        unsigned long long m = 0ull;
+        for (int c = 0; c < 16; c++) {
+            const int z0 = a[c] > 4 * bz ? a[c] : 4 * bz, z1 = b[c] < 4 * bz + 3 ? b[c] : 4 * bz + 3;
+            for (int z = z0; z <= z1; z++) m |= 1ull << (c + 16 * (z - 4 * bz));
+        }
+        keys[at] = m ? brick_key(bx, by, (unsigned)bz, digits) : 0xffffffffu;
+        masks[at] = m;
+    }
+}
+
+/* nodes of one level from its sorted (key, mask) arrays; first = per node the position of its first child in the next
+ * level (inner levels) or of its first voxel type (leaf level) */
+__global__ void vr_pair_nodes(const unsigned long long *__restrict__ masks, const uint32_t *__restrict__ first, unsigned n,
+                              uint32_t level_start, uint32_t child_start, vr_node *__restrict__ nodes) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long m = masks[i];
+    vr_node nd;
+    nd.mask_lo = (uint32_t)m;
+    nd.mask_hi = (uint32_t)(m >> 32);
+    nd.child_base = child_start + first[i];
+    nd.aux = vr_node_planes(m);
+    reinterpret_cast<uint4 *>(nodes)[level_start + i] = *reinterpret_cast<uint4 *>(&nd);
+}
+
+}  // namespace
+
+cudaError_t vr_build_tree_columns_device(const int32_t *d_lo, const int32_t *d_hi, int dim, uint8_t type, cudaStream_t stream,
+                                         vr_device_tree *out, unsigned long long *launches) {
+    if (!d_lo || !d_hi || !out || dim < 4 || (dim & (dim - 1))) return cudaErrorInvalidValue;
+    int L = 1;
+    while ((1 << (2 * L)) < dim) L++;
+    if (L > 6) return cudaErrorInvalidValue;                     /* 32-bit keys: 6 bits per level below the root, up to 4096^3 */
+    const int nb = dim / 4, digits = L - 1;
+    const unsigned ncol = (unsigned)nb * (unsigned)nb;
+
+    uint32_t *count = nullptr, *offset = nullptr, *keys[2] = {nullptr, nullptr}, *first[2] = {nullptr, nullptr}, *pkeys = nullptr, *d_num = nullptr;
+    unsigned long long *masks[2] = {nullptr, nullptr}, *pmasks[VR_MAX_LEVELS] = {};
+    uint32_t *pfirst[VR_MAX_LEVELS] = {}, *lkeys[VR_MAX_LEVELS] = {};
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    vr_node *nodes = nullptr;
+    uint8_t *types = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(count); cudaFree(offset); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(masks[0]); cudaFree(masks[1]);
+        cudaFree(first[0]); cudaFree(first[1]); cudaFree(pkeys); cudaFree(d_num); cudaFree(tmp);
+        for (int l = 0; l < VR_MAX_LEVELS; l++) { cudaFree(pmasks[l]); cudaFree(pfirst[l]); cudaFree(lkeys[l]); }
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    auto need_tmp = [&](size_t bytes) -> cudaError_t {
+        if (bytes <= tmp_bytes) return cudaSuccess;
+        cudaFree(tmp);
+        tmp = nullptr;
+        tmp_bytes = bytes;
+        return cudaMalloc(&tmp, bytes);
+    };
+    VRB(cudaEventCreate(&e0));
+    VRB(cudaEventCreate(&e1));
+    VRB(cudaEventRecord(e0, stream));
+    /* 1-2. brick layers per brick column and where they go */
+    VRB(cudaMalloc(&count, (size_t)(ncol + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&offset, (size_t)(ncol + 1) * sizeof(uint32_t)));
+    VRB(cudaMemsetAsync(count + ncol, 0, sizeof(uint32_t), stream));
+    vr_col_count<<<(ncol + 255) / 256, 256, 0, stream>>>(d_lo, d_hi, dim, nb, count);
+    {
+        size_t b = 0;
+        VRB(cub::DeviceScan::ExclusiveSum(nullptr, b, count, offset, (int)(ncol + 1), stream));
+        VRB(need_tmp(b));
+        VRB(cub::DeviceScan::ExclusiveSum(tmp, b, count, offset, (int)(ncol + 1), stream));
+    }
+    uint32_t npairs = 0;
+    VRB(cudaMemcpyAsync(&npairs, offset + ncol, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VRB(cudaStreamSynchronize(stream));
+    if (launches) *launches += 1;
+    const size_t cap = npairs ? npairs : 1;
+    for (int i = 0; i < 2; i++) {
+        VRB(cudaMalloc(&keys[i], cap * sizeof(uint32_t)));
+        VRB(cudaMalloc(&masks[i], cap * sizeof(unsigned long long)));
+        VRB(cudaMalloc(&first[i], cap * sizeof(uint32_t)));
+    }
+    VRB(cudaMalloc(&pkeys, cap * sizeof(uint32_t)));
+    VRB(cudaMalloc(&d_num, sizeof(uint32_t)));
+    uint32_t nleaf = 0;
+    if (npairs) {
+        /* 3-4. the bricks, then breadth-first (= ascending key) order; empty masks sort to the end */
+        vr_col_bricks<<<(ncol + 127) / 128, 128, 0, stream>>>(d_lo, d_hi, dim, nb, digits, offset, keys[0], masks[0]);
+        size_t b = 0;
+        VRB(cub::DeviceRadixSort::SortPairs(nullptr, b, keys[0], keys[1], masks[0], masks[1], (int)npairs, 0, 32, stream));
+        VRB(need_tmp(b));
+        VRB(cub::DeviceRadixSort::SortPairs(tmp, b, keys[0], keys[1], masks[0], masks[1], (int)npairs, 0, 32, stream));
+        auto nz = thrust::make_transform_iterator((const unsigned long long *)masks[1], NonZero());
+        VRB(cub::DeviceReduce::Sum(nullptr, b, nz, d_num, (int)npairs, stream));
+        VRB(need_tmp(b));
+        VRB(cub::DeviceReduce::Sum(tmp, b, nz, d_num, (int)npairs, stream));
+        VRB(cudaMemcpyAsync(&nleaf, d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        VRB(cudaStreamSynchronize(stream));
+        if (launches) *launches += 3;
+    }
+    /* 5. the levels, bottom up.  Level l (0 = root) has n[l] nodes; lkeys / pmasks / pfirst hold its keys, masks and the
+     * position of each node's first child (leaf level: first voxel type) */
+    uint32_t n[VR_MAX_LEVELS + 1] = {0};
+    const int leaf = L - 1;
+    n[leaf] = nleaf;
+    unsigned long long solid = 0;
+    if (nleaf) {
+        VRB(cudaMalloc(&pmasks[leaf], (size_t)nleaf * sizeof(unsigned long long)));
+        VRB(cudaMalloc(&pfirst[leaf], (size_t)nleaf * sizeof(uint32_t)));
+        VRB(cudaMalloc(&lkeys[leaf], (size_t)nleaf * sizeof(uint32_t)));
+        VRB(cudaMemcpyAsync(pmasks[leaf], masks[1], (size_t)nleaf * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+        VRB(cudaMemcpyAsync(lkeys[leaf], keys[1], (size_t)nleaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+        auto pc = thrust::make_transform_iterator((const unsigned long long *)pmasks[leaf], PopCount());
+        size_t b = 0;
+        VRB(cub::DeviceScan::ExclusiveSum(nullptr, b, pc, pfirst[leaf], (int)nleaf, stream));
+        VRB(need_tmp(b));
+        VRB(cub::DeviceScan::ExclusiveSum(tmp, b, pc, pfirst[leaf], (int)nleaf, stream));
+        uint32_t last_first = 0;
+        unsigned long long last_mask = 0;
+        VRB(cudaMemcpyAsync(&last_first, pfirst[leaf] + nleaf - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        VRB(cudaMemcpyAsync(&last_mask, pmasks[leaf] + nleaf - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        VRB(cudaStreamSynchronize(stream));
+        solid = (unsigned long long)last_first + (unsigned long long)__builtin_popcountll(last_mask);
+        for (int l = leaf - 1; l >= 0; l--) {
+            const uint32_t nc = n[l + 1];
+            auto parent = thrust::make_transform_iterator((const uint32_t *)lkeys[l + 1], KeyParent());
+            auto bit = thrust::make_transform_iterator((const uint32_t *)lkeys[l + 1], KeyBit());
+            thrust::counting_iterator<uint32_t> pos(0u);
+            VRB(cudaMalloc(&pmasks[l], (size_t)nc * sizeof(unsigned long long)));
+            VRB(cudaMalloc(&pfirst[l], (size_t)nc * sizeof(uint32_t)));
+            VRB(cudaMalloc(&lkeys[l], (size_t)nc * sizeof(uint32_t)));
+            size_t b1 = 0, b2 = 0;
+            VRB(cub::DeviceReduce::ReduceByKey(nullptr, b1, parent, lkeys[l], bit, pmasks[l], d_num, BitOr(), (int)nc, stream));
+            VRB(cub::DeviceReduce::ReduceByKey(nullptr, b2, parent, pkeys, pos, pfirst[l], d_num, MinU32(), (int)nc, stream));
+            VRB(need_tmp(b1 > b2 ? b1 : b2));
+            VRB(cub::DeviceReduce::ReduceByKey(tmp, b1, parent, lkeys[l], bit, pmasks[l], d_num, BitOr(), (int)nc, stream));
+            VRB(cub::DeviceReduce::ReduceByKey(tmp, b2, parent, pkeys, pos, pfirst[l], d_num, MinU32(), (int)nc, stream));
+            VRB(cudaMemcpyAsync(&n[l], d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            VRB(cudaStreamSynchronize(stream));
+            if (launches) *launches += 2;
+        }
+    }
+    /* output arrays */
+    uint32_t start[VR_MAX_LEVELS + 1];
+    const bool empty = nleaf == 0;
+    if (empty) for (int l = 0; l < L; l++) n[l] = l == 0 ? 1u : 0u;
+    start[0] = 0;
+    for (int l = 0; l < L; l++) start[l + 1] = start[l] + n[l];
+    const uint64_t n_nodes = start[L], n_types = solid ? solid : 1;
+    {
+        cudaError_t e = cudaMalloc(&nodes, n_nodes * sizeof(vr_node));
+        if (e == cudaSuccess) e = cudaMalloc(&types, n_types);
+        if (e == cudaSuccess) e = cudaMemsetAsync(types, solid ? (int)type : 0, n_types, stream);
+        if (e == cudaSuccess && empty) e = cudaMemsetAsync(nodes, 0, sizeof(vr_node), stream);     /* an empty root (planes: all empty) */
+        if (e != cudaSuccess) { cudaFree(nodes); cudaFree(types); cleanup(); return e; }
+    }
+    if (empty) {
+        vr_node root = {0u, 0u, L > 1 ? 1u : 0u, vr_node_planes(0ull)};      /* child_base as the host builder leaves it */
+        cudaError_t e = cudaMemcpyAsync(nodes, &root, sizeof(root), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { cudaFree(nodes); cudaFree(types); cleanup(); return e; }
+    } else {
+        for (int l = 0; l < L; l++) {
+            vr_pair_nodes<<<(n[l] + 255) / 256, 256, 0, stream>>>(pmasks[l], pfirst[l], n[l], start[l], l == leaf ? 0u : start[l + 1], nodes);
+            if (launches) ++*launches;
+        }
+    }
+    cudaError_t e = cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(nodes); cudaFree(types); cleanup(); return e; }
+    out->masks_ms = 0.f;
+    cudaEventElapsedTime(&out->total_ms, e0, e1);
+    out->nodes = nodes;
+    out->types = types;
+    out->n_nodes = n_nodes;
+    out->n_types = n_types;
+    out->solid_voxels = solid;
+    out->levels = L;
+    cleanup();
     return cudaSuccess;
 }

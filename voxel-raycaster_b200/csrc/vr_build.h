@@ -21,6 +21,13 @@ typedef struct vr_device_tree {
 cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stream, vr_device_tree *out,
                                  unsigned long long *launches);
 
+/* The same tree from a column description (device pointers, lo/hi[x + dim*y]: column (x, y) is solid for lo <= z <= hi,
+ * every solid voxel has value `type`), without the N^3 volume and without any dense workspace: only the bricks that hold
+ * a voxel are materialised (4096^3: 64 GiB dense).  dim a power of two, 4 .. 4096.  Emits exactly the arrays
+ * vr_native_from_columns (vr_octree.cpp) produces. */
+cudaError_t vr_build_tree_columns_device(const int32_t *d_lo, const int32_t *d_hi, int dim, uint8_t type, cudaStream_t stream,
+                                         vr_device_tree *out, unsigned long long *launches);
+
 /* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree d_nodes: *grid_out is
  * cudaMalloc'ed (ownership passes to the caller).  cudaErrorInvalidValue when the tree is too shallow for a grid. */
 cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cudaStream_t stream, uint32_t **grid_out,

@@ -282,14 +282,14 @@ VR_HD int vr_canon_slow(const vr_frame_params &P, RayState &r, vr_aux *a, bool &
     vf3 t0 = r.t;
     float kx = 0.0f, ky = 0.0f, kz = 0.0f;
     for (;;) {
-        if (!(r.dist < r.max_distance && r.bounce < 2)) {
-            if (MULTI && r.bounce < 2 && vr_more_lights(P, r)) {
+        if (!(r.dist < r.max_distance && r.bounce < P.max_bounces)) {
+            if (MULTI && r.bounce < P.max_bounces && vr_more_lights(P, r)) {
                 if (!vr_next_light(P, r)) return VR_ST_SKIP_REDIRECT;
                 r.dist++;
                 t0 = r.t; kx = ky = kz = 0.0f;
                 continue;
             }
-            return r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST;
+            return r.bounce >= P.max_bounces ? VR_ST_BOUNCES : VR_ST_MAXDIST;
         }
         const int mx = (r.t.x <= vr_min(r.t.y, r.t.z)) ? 1 : 0;
         const int my = (r.t.y <= vr_min(r.t.z, r.t.x)) ? 1 : 0;
@@ -354,7 +354,7 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
         int voxel_data = 0;
         float T = 0.0f;                    /* time of the last step */
         enum { EV_HIT, EV_UNBLOCKED_MAXDIST, EV_UNBLOCKED_OOB } ev = EV_UNBLOCKED_MAXDIST;
-        if (!(r.bounce < 2)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
+        if (!(r.bounce < P.max_bounces)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
         if (r.dist < r.max_distance) {                                     /* kernel:357 */
             int dbase = r.dist - (q.px + q.py + q.pz);                     /* distance_traveled = dbase + px + py + pz */
             for (;;) {                     /* one turn per empty cell */
@@ -417,7 +417,7 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
                 r.dist += 1;               /* kernel:714 ends the iteration of the hit */
             }
         } else if (ev == EV_UNBLOCKED_MAXDIST) {
-            if (!(MULTI && r.bounce < 2 && vr_more_lights(P, r))) { status = VR_ST_MAXDIST; break; }
+            if (!(MULTI && r.bounce < P.max_bounces && vr_more_lights(P, r))) { status = VR_ST_MAXDIST; break; }
             relight = true;
         } else {
             if (!(MULTI && vr_more_lights(P, r))) {

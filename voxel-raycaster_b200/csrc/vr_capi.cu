@@ -262,6 +262,8 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     P.atlas_scale[1] = c->atlas_dim[1] / c->tile_dim[1];
     P.max_distance = 20;                                             /* kernel:326 */
     if (setting_value(c, "MAX_DISTANCE", &v)) P.max_distance = (int)v;
+    P.max_bounces = 2;                                               /* kernel:357 */
+    if (setting_value(c, "MAX_BOUNCES", &v) && v >= 0 && v <= 64) P.max_bounces = (int)v;
     P.nodes = c->d_nodes;
     P.leaf_types = c->d_leaf_types;
     P.levels = c->levels;
@@ -553,6 +555,37 @@ int vr_assign_columns(vr_ctx *c, const int32_t *lo, const int32_t *hi, int dim, 
     if (!lo || !hi || dim < 1 || (dim & (dim - 1)) || (type != 5 && type != 6)) return fail(c, "assign_columns: bad arguments");
     cudaSetDevice(c->device);
     if (c->d_map) vr_release_map(c);
+    c->build_ms = c->build_masks_ms = 0.f;
+    if (c->gpu_build && dim >= 4 && dim <= 4096) {
+        /* on the device, from the two column tables (vr_build.cu: only the bricks that hold a voxel are materialised) */
+        const size_t bytes = (size_t)dim * dim * sizeof(int32_t);
+        int32_t *d_lo = nullptr, *d_hi = nullptr;
+        cudaError_t e = cudaMalloc(&d_lo, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&d_hi, bytes);
+        if (e == cudaSuccess) e = upload(c, d_lo, lo, bytes);
+        if (e == cudaSuccess) e = upload(c, d_hi, hi, bytes);
+        vr_device_tree dt;
+        memset(&dt, 0, sizeof(dt));
+        if (e == cudaSuccess) e = vr_build_tree_columns_device(d_lo, d_hi, dim, (uint8_t)type, c->stream, &dt, &c->launches);
+        cudaFree(d_lo);
+        cudaFree(d_hi);
+        if (e == cudaSuccess) {
+            free_tree(c);
+            c->d_nodes = dt.nodes;
+            c->d_leaf_types = dt.types;
+            c->levels = dt.levels;
+            c->tree_dim = dim;
+            c->n_nodes = dt.n_nodes;
+            c->n_leaf_types = dt.n_types;
+            c->solid_voxels = dt.solid_voxels;
+            c->tree_valid = true;
+            c->tree_from_map = true;
+            c->build_ms = dt.total_ms;
+            return 1;
+        }
+        cudaGetLastError();
+        fprintf(stderr, "[vrcaster] device octree build from columns failed (%s): building on the host\n", cudaGetErrorString(e));
+    }
     vr_native_tree t;
     try {
         if (!vr_native_from_columns(lo, hi, dim, (uint8_t)type, t)) return fail(c, "assign_columns: 64-tree build failed");

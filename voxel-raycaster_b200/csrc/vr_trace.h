@@ -369,9 +369,9 @@ VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba
     bool first_hit_done = false;
     int status = VR_ST_MAXDIST;
     for (;;) {
-        if (!(r.dist < r.max_distance && r.bounce < 2)) {
+        if (!(r.dist < r.max_distance && r.bounce < P.max_bounces)) {
             /* multi-light extension: this light is not blocked, on to the next one */
-            if (MULTI && r.bounce < 2 && vr_more_lights(P, r)) {
+            if (MULTI && r.bounce < P.max_bounces && vr_more_lights(P, r)) {
                 if (!vr_next_light(P, r)) { status = VR_ST_SKIP_REDIRECT; break; }
                 r.dist++;
                 continue;
@@ -402,7 +402,7 @@ VR_HD bool vr_trace_dense(const vr_frame_params &P, int x, int y, uint32_t *rgba
         if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
         return false;
     }
-    if (status == VR_ST_MAXDIST && r.bounce >= 2) status = VR_ST_BOUNCES;
+    if (status == VR_ST_MAXDIST && r.bounce >= P.max_bounces) status = VR_ST_BOUNCES;
     if (AUX) { a->status = (uint8_t)status; a->steps_total = (uint32_t)r.dist; }
     *rgba_out = vr_epilogue(r);
     return true;
@@ -782,7 +782,7 @@ VR_HD bool vr_svo_begin(const vr_frame_params &P, int x, int y, vr_svo_ray<Stack
 template <bool AUX, int WALK, bool MULTI, class Stack>
 VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
     RayState &r = q.r;
-    if (!(r.dist < r.max_distance && r.bounce < 2)) return r.bounce >= 2 ? VR_ST_BOUNCES : VR_ST_MAXDIST;
+    if (!(r.dist < r.max_distance && r.bounce < P.max_bounces)) return r.bounce >= P.max_bounces ? VR_ST_BOUNCES : VR_ST_MAXDIST;
     const int N = P.dim[0];
     /* ---- (1) walk inside the cached cell: no memory access, no bounds test */
     bool tie_cell = false;
@@ -942,7 +942,7 @@ VR_HD uint32_t vr_svo_finish(vr_svo_ray<Stack> &q, int status, vr_aux *a) {
 template <bool AUX, int WALK, bool MULTI, class Stack>
 VR_HD int vr_svo_round(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a) {
     int rc = vr_svo_cell<AUX, WALK, MULTI>(P, q, a);
-    if (MULTI && (rc == VR_CELL_NEXT_LIGHT || (rc == VR_ST_MAXDIST && q.r.bounce < 2 && vr_more_lights(P, q.r)))) {
+    if (MULTI && (rc == VR_CELL_NEXT_LIGHT || (rc == VR_ST_MAXDIST && q.r.bounce < P.max_bounces && vr_more_lights(P, q.r)))) {
         if (!vr_next_light(P, q.r)) {
             if (AUX) { a->status = (uint8_t)VR_ST_SKIP_REDIRECT; a->steps_total = (uint32_t)q.r.dist; }
             return VR_CELL_NO_WRITE;

@@ -99,6 +99,7 @@ typedef struct vr_frame_params {
     int32_t atlas_scale[2];        /* atlas_dim / tile_dim, integer (kernel:654)              */
     /* settings */
     int32_t max_distance;          /* kernel:326                                              */
+    int32_t max_bounces;           /* kernel:357 `bounce_count < 2`; setting MAX_BOUNCES (TODO list, ref src/main.cpp:31-33) */
     /* native 64-tree */
     const vr_node *nodes;
     const uint8_t *leaf_types;
