@@ -257,6 +257,20 @@ def run_reference(args) -> None:
     }))
 
 
+def c5_roofline(ms_per_batch: float, world: int) -> dict | None:
+    """algorithmic bytes of the 64-view batch (profiles/algorithmic_bytes_c5.json, oracle counters of all views) over the
+    batch time: every launch renders one view, a rank renders 64 / world of them back to back"""
+    ab = load_algorithmic_bytes("c5")
+    if not ab:
+        return None
+    peak, peak_how = measured_peak_gbs()
+    per_view = float(ab["bytes_svo"]) / ab["views"]
+    achieved = float(ab["bytes_svo"]) / world / (ms_per_batch / 1e3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_how,
+            "kernel": "vr_svo_kernel", "kernel_ms": ms_per_batch / (ab["views"] / world), "algorithmic_bytes_per_launch": per_view,
+            "bytes_model": "P*(16+4) + 8*D_svo + 4*T summed over the 64 views (profiles/algorithmic_bytes_c5.json); one launch = one view"}
+
+
 def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     """--config c5 (BASELINE configs[4], not the headline): 64 cameras x 1920x1080 over the 1024^3 SVO, view-batch
     split: view v is rendered by rank v % world with vr_compute_views; a step is the whole batch."""
@@ -347,7 +361,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                        "parallelism": f"views{world}: view v on rank v % {world}", "views": views, "rays_per_batch": rays,
                        "walk": WALK_NAMES[args.walk],
                        "ms_per_view": ms / (views / world) if world else None},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": c5_roofline(ms, world), "cpu_baseline": None,
             "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(mine.nbytes), "d2h_bytes_per_step": int(frames.numel())},
             "clocks": clocks.summary()}))
@@ -733,6 +747,19 @@ def main() -> None:
         kernel_ms = ms_per_step      # launches of consecutive frames overlap: effective duration per launch
     value = rays / (ms_per_step / 1e3) / 1e6
 
+    # a longer look at the same thing (N = 1): back-to-back frames for at least half a second, with their own clock samples
+    sustained = None
+    if world == 1:
+        n_sus = max(args.steps, int(0.6e3 / max(ms_per_step, 1e-3)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as sus_clocks:
+            s0.record(stream)
+            for _ in range(n_sus):
+                must(c.compute_into(slab.data_ptr()), "compute_into")
+            s1.record(stream)
+            torch.cuda.synchronize()
+        sustained = {"frames": n_sus, "ms_per_frame": s0.elapsed_time(s1) / n_sus, "clocks": sus_clocks.summary()}
+
     # the other in-cell walks, for the record (a few frames outside the timed region, kernel only)
     other_walk_ms = None
     if use_svo and world == 1:
@@ -832,7 +859,7 @@ def main() -> None:
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
                        "mode": args.mode,
                        "walk": WALK_NOTES[args.walk] if use_svo else "dense DDA",
-                       "other_walk_ms_per_frame": other_walk_ms,
+                       "other_walk_ms_per_frame": other_walk_ms, "sustained": sustained,
                        "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
@@ -841,7 +868,9 @@ def main() -> None:
                        "octree_build": ({"where": "device (vr_build.cu) from the uploaded dense map", "ms": round(float(st.build_ms), 3),
                                          "map_read_ms": round(float(st.build_masks_ms), 3),
                                          "map_read_gbs": round(scene.n ** 3 / max(float(st.build_masks_ms), 1e-6) / 1e6, 1)}
-                                        if st.build_ms > 0 else {"where": "host (column builder or broadcast)"}),
+                                        if st.build_masks_ms > 0 else
+                                        {"where": "device (vr_build.cu) from the column tables: only the bricks that hold a voxel are materialised (no N^3 volume, no dense workspace)",
+                                         "ms": round(float(st.build_ms), 3)} if st.build_ms > 0 else {"where": "host (column builder or broadcast)"}),
                        "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum, "device_frame_checksum": device_checksum},
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -33,6 +33,34 @@ ap.add_argument("--row-stride", type=int, default=8)
 ap.add_argument("--lights", type=int, default=1)
 args = ap.parse_args()
 
+if args.config == "c5":
+    # BASELINE configs[4]: 64 cameras x 1920x1080 over the 1024^3 SVO (bench.py run_views): the counters of all views added up
+    S = pkg.scene
+    n, W, H, views = 1024, 1920, 1080, 64
+    base = bench.bench_scene("c3")
+    h = S.heightfield(n)
+    desc, root = pkg.octree_generate(base.volume)
+    tot = None
+    t0 = time.time()
+    for i in range(views):
+        pos, direction = S.make_camera(n, h, i)
+        sc = S.Scene(n, base.volume, W, H, pos, direction, base.lights, atlas=base.atlas, max_distance=3 * n)
+        _, _, cnt = O.raycast(sc, octree=(desc, root), want_aux=False, want_counters=True, count_svo=True, row_stride=args.row_stride)
+        tot = cnt if tot is None else {k: tot[k] + v for k, v in cnt.items()}
+    print(f"oracle counters of {views} views over 1/{args.row_stride} of the rows in {time.time() - t0:.1f} s")
+    k = views * W * H / tot["pixels"]
+    P = views * W * H
+    out = {"config": "c5", "views": views, "width": W, "height": H, "n": n, "row_stride": args.row_stride, "pixels": P,
+           "primary_rays": tot["primary_rays"] * k, "shadow_rays": tot["shadow_rays"] * k, "dda_steps": tot["dda_steps"] * k,
+           "texel_fetches": tot["texel_fetches"] * k, "svo_desc_fetches": tot["svo_desc_fetches"] * k,
+           "svo_cell_changes": tot["svo_cell_changes"] * k}
+    out["bytes_svo"] = P * 20 + 8 * out["svo_desc_fetches"] + 4 * out["texel_fetches"]
+    out["bytes_dense"] = P * 20 + 1 * out["dda_steps"] + 4 * out["texel_fetches"]
+    out["rays"] = out["primary_rays"] + out["shadow_rays"]
+    (ROOT / "profiles" / "algorithmic_bytes_c5.json").write_text(json.dumps(out, indent=1) + "\n")
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
+
 scene = bench.bench_scene(args.config, lights=args.lights)
 t0 = time.time()
 desc, root = pkg.octree_generate(scene.volume)

@@ -360,7 +360,7 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cu
                                  int *grid_shift, int *grid_bits, unsigned long long *launches) {
     const int root_shift = 2 * (levels - 1);
     if (root_shift < 2 || dim < 8) return cudaErrorInvalidValue;
-    const int g = root_shift - 4 > 2 ? root_shift - 4 : 2;
+    const int g = vr_grid_shift_for(root_shift, dim);
     const int G = dim >> g;
     int bits = 0;
     while ((1 << bits) < G) bits++;

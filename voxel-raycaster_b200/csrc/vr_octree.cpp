@@ -421,7 +421,7 @@ int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shif
 bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits) {
     const int root_shift = 2 * (levels - 1);
     if (root_shift < 2 || dim < 8) return false;
-    const int g = root_shift - 4 > 2 ? root_shift - 4 : 2;
+    const int g = vr_grid_shift_for(root_shift, dim);
     const int G = dim >> g;
     if (G < 1) return false;
     int bits = 0;

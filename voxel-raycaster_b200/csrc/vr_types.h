@@ -43,6 +43,19 @@ VR_HD uint32_t vr_node_planes(unsigned long long m) {
     return e;
 }
 
+/* Block edge (log2) of the top grid of the closed-form walk (vr_frame_params::grid) for a map of edge `dim` whose 64-tree
+ * root has child shift root_shift: the finest one whose table stays within VR_GRID_MAX_BITS index bits (2^24 entries =
+ * 64 MB: L2-resident on B200), never finer than a leaf brick (shift 2).  1024^3 -> bricks (256^3 entries), 4096^3 ->
+ * 16^3 blocks. */
+#ifndef VR_GRID_MAX_BITS
+#define VR_GRID_MAX_BITS 24
+#endif
+VR_HD int vr_grid_shift_for(int root_shift, int dim) {
+    int g = 2;
+    while (g < root_shift && 3 * (31 - __builtin_clz((unsigned)(dim >> g))) > VR_GRID_MAX_BITS) g += 2;
+    return g;
+}
+
 /* Per-pixel auxiliary record (32 bytes), layout-identical to the oracle's vro_aux. */
 typedef struct vr_aux {
     int32_t hit[3];
