@@ -476,6 +476,9 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
         device_checksum = int(frame[::64, ::64].sum().item())
     c.mgpu_frame_release(last)
     t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(per_rank, t_ms)                      # how evenly the tile interleave spreads the frame
+    per_rank_ms = [round(float(t.item()) / args.steps, 4) for t in per_rank]
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
     must(c.mgpu_shutdown(), "mgpu_shutdown")
@@ -524,6 +527,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                                       "into the root GPU's frame over NVLink (CUDA IPC), device-stored completion counters polled by the root's CPU, 4 frame buffers; "
                                       "2 launches per frame and rank (ray kernel + 1-thread signal kernel)",
                        "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
+                       "per_rank_ms_per_frame": per_rank_ms,
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
@@ -862,6 +866,7 @@ def main() -> None:
                        "other_walk_ms_per_frame": other_walk_ms, "sustained": sustained,
                        "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
+                       "per_rank_ms_per_frame": per_rank_ms,
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "scene_build_s": round(t_build, 2),

@@ -108,6 +108,7 @@ void free_tree(vr_ctx *c) {
     c->d_leaf_types = nullptr;
     c->d_grid = nullptr;
     c->grid_tried = false;
+    c->l2_base = nullptr;
     if (c->l2_persist && c->stream) {               /* the access-policy window pointed into the arrays just freed */
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
@@ -151,10 +152,11 @@ int apply_l2_window(vr_ctx *c) {
     if (c->l2_persist && c->d_nodes) {
         int max_win = 0;
         cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-        size_t bytes = c->n_nodes * sizeof(vr_node);
+        const bool grid = c->l2_base && c->l2_base == (const void *)c->d_grid;
+        size_t bytes = grid ? ((size_t)4 << (3 * c->grid_bits)) : c->n_nodes * sizeof(vr_node);
         if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;      /* BFS order: top levels first */
         VR_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
-        attr.accessPolicyWindow.base_ptr = c->d_nodes;
+        attr.accessPolicyWindow.base_ptr = grid ? (void *)c->d_grid : (void *)c->d_nodes;
         attr.accessPolicyWindow.num_bytes = bytes;
         attr.accessPolicyWindow.hitRatio = 1.0f;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -284,10 +286,6 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
      * < 0.2 crossings up to 4096^3, where it is tested); beyond 16384^3 the merged walk is used whatever the option says */
     vr_launch_options opt = c->opt;
     if (P.dim[0] > 16384 && opt.walk == 1) opt.walk = 0;
-    if (c->l2_persist && use_svo && c->l2_base != (const void *)c->d_nodes) {   /* the tree was rebuilt since the window was set */
-        if (!apply_l2_window(c)) return 0;
-        c->l2_base = c->d_nodes;
-    }
     if (use_svo && opt.walk == 2) {
         /* the closed-form walk reads the top levels of the octree from a flat table (vr_canon.h), derived from the tree
          * in HBM when it is first needed; trees of a single level (maps up to 4^3) and maps beyond 65536^3 take walk 0 */
@@ -297,6 +295,14 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
         P.grid_shift = c->grid_shift;
         P.grid_bits = c->grid_bits;
         P.grid_dim = 1 << c->grid_bits;
+    }
+    if (c->l2_persist && use_svo) {
+        /* the window covers what the selected walk reads at random: the top grid (closed-form walk) or the node array */
+        const void *want = (opt.walk == 2 && c->d_grid) ? (const void *)c->d_grid : (const void *)c->d_nodes;
+        if (c->l2_base != want) {                                  /* first frame, or the tree / the walk changed since */
+            c->l2_base = want;
+            if (!apply_l2_window(c)) return 0;
+        }
     }
     VR_CUDA(c, vr_launch_raycast(P, use_svo, c->aux_on ? 1 : 0, c->stream, &c->launches, &opt));
     if (timed) {
@@ -853,7 +859,8 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
         if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");
         c->l2_persist = value != 0;
-        if (!apply_l2_window(c)) return 0;
+        c->l2_base = nullptr;                       /* (re)applied at the next frame, for what that frame's walk reads */
+        if (!value && !apply_l2_window(c)) return 0;
     }
     else return fail(c, "set_option: unknown option [%s]", name);
     return 1;

@@ -102,7 +102,7 @@ vr_dense_kernel(const __grid_constant__ vr_frame_params P) {
     uint32_t rgba;
     vr_aux a;
     const bool write = vr_trace_dense<AUX, MULTI>(P, x, y, &rgba, &a);
-    if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
+    if (write) __stcs(reinterpret_cast<uint32_t *>(P.image) + local, rgba);       /* written once, not read by this kernel: streaming */
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
 }
@@ -125,7 +125,7 @@ vr_svo_kernel(const __grid_constant__ vr_frame_params P) {
         SmemStack stk{stack + threadIdx.x};
         write = vr_trace_svo<AUX, WALK, MULTI>(P, x, y, &rgba, &a, stk);
     }
-    if (write) reinterpret_cast<uint32_t *>(P.image)[local] = rgba;
+    if (write) __stcs(reinterpret_cast<uint32_t *>(P.image) + local, rgba);       /* written once, not read by this kernel: streaming */
     if (AUX) reinterpret_cast<uint4 *>(P.aux)[2 * local] = *reinterpret_cast<uint4 *>(&a),
              reinterpret_cast<uint4 *>(P.aux)[2 * local + 1] = *(reinterpret_cast<uint4 *>(&a) + 1);
 }

@@ -105,7 +105,8 @@ struct RayState {
 /* kernel:276-337 + 353.  Returns false when the pixel is skipped (kernel:293). */
 VR_HD bool vr_ray_setup(const vr_frame_params &P, int x, int y, RayState &r) {
 #if defined(__CUDA_ARCH__)
-    const float4 rt = __ldg(reinterpret_cast<const float4 *>(P.ray_table) + ((size_t)x + (size_t)P.width * (size_t)y));
+    /* read once per frame: streaming (evict-first), so that the 133 MB table does not push the octree / top grid out of L2 */
+    const float4 rt = __ldcs(reinterpret_cast<const float4 *>(P.ray_table) + ((size_t)x + (size_t)P.width * (size_t)y));
     vf3 d = {rt.x, rt.y, rt.z};
 #else
     const float *rt = P.ray_table + 4 * ((size_t)x + (size_t)P.width * (size_t)y);
