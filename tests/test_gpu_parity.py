@@ -494,8 +494,8 @@ def test_gpu_builder_equals_host_builder(pkg, kind):
 
 @pytest.mark.gpu
 def test_gpu_builder_full_size_c3(pkg):
-    """1024^3 (1 GiB map): the device-built tree renders the frame the column-built (host) tree renders, and the
-    voxel count is the map's."""
+    """1024^3 (1 GiB map): the tree built on the device from the dense map, the tree built on the device from the column
+    tables and the tree built on the host from the column tables render the same frame; the voxel count is the map's."""
     import bench
 
     S = pkg.scene
@@ -509,11 +509,16 @@ def test_gpu_builder_full_size_c3(pkg):
     lo, hi = S.terrain_columns(scene.n, "shell")
     scene2 = S.Scene(scene.n, None, scene.width, scene.height, scene.cam_pos, scene.cam_dir, scene.lights,
                      max_distance=scene.max_distance, columns=(lo, hi))
-    d = make_caster(pkg, scene2, True, assign_octree=False, aux=False)
-    assert d.stats().build_ms == 0 and d.stats().native_nodes == st.native_nodes
+    d = make_caster(pkg, scene2, True, assign_octree=False, aux=False)      # assign_columns -> device build from the tables
+    assert d.stats().build_ms > 0 and d.stats().native_nodes == st.native_nodes
     assert d.set_option("walk", 1) and d.compute()
     assert np.array_equal(got, d.draw())
     d.close()
+    e = pkg.CUDACaster()
+    e.load_scene(scene2, use_octree=True, assign_octree=False, walk=1, gpu_build=False)      # ... and on the host
+    assert e.stats().build_ms == 0 and e.stats().native_nodes == st.native_nodes
+    assert e.compute() and np.array_equal(got, e.draw())
+    e.close()
 
 
 @pytest.mark.gpu
