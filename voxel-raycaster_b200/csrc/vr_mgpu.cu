@@ -23,6 +23,7 @@
  * NCCL is loaded with dlopen (libnccl.so.2: the copy a host framework already loaded, else the system one), so that
  * libvrcaster.so has no link-time dependency on it.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <errno.h>
@@ -82,6 +83,9 @@ struct vr_mgpu {
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    /* cuStreamWriteValue64 (driver API, resolved at run time): the completion counter is written by the stream itself,
+     * after everything before it in the stream, with a system-wide memory barrier -- no kernel launch for the signal */
+    CUresult (*WriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
 };
 
 namespace {
@@ -316,6 +320,14 @@ int vr_mgpu_init(vr_ctx *c, const char *session, int world, int rank, unsigned f
         for (int i = 0; i < VR_MGPU_RING && ok; i++) ok = cudaEventCreateWithFlags(&m->ev_rendered[i], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { vr_i_fail(c, "mgpu_init: stream / event creation failed"); teardown(c); return 0; }
     }
+    if (!getenv("VR_MGPU_SIGNAL_KERNEL")) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            *(void **)&m->WriteValue64 = fn;
+        else
+            cudaGetLastError();
+    }
     /* ---- NCCL communicator (scene broadcast) */
     {
         ncclUniqueId id;
@@ -401,9 +413,14 @@ int vr_mgpu_frame(vr_ctx *c, uint64_t *frame_no) {
                                    cudaMemcpyDeviceToHost, m->copy));
         tail = m->copy;
     }
-    vr_mgpu_signal<<<1, 1, 0, tail>>>(m->d_done, k + 1);
-    c->launches++;
-    VR_CU(c, cudaGetLastError());
+    if (m->WriteValue64 && m->WriteValue64((CUstream)tail, (CUdeviceptr)(uintptr_t)m->d_done, (cuuint64_t)(k + 1), CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) {
+        /* done: a stream memory operation, ordered after the kernel (and the copy) like a kernel would be */
+    } else {
+        m->WriteValue64 = nullptr;                       /* not supported here: a one-thread kernel does the same */
+        vr_mgpu_signal<<<1, 1, 0, tail>>>(m->d_done, k + 1);
+        c->launches++;
+        VR_CU(c, cudaGetLastError());
+    }
     m->issued = k + 1;
     if (frame_no) *frame_no = k;
     return 1;
