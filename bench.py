@@ -525,7 +525,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                        "kernel_variant": "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM",
                        "parallelism": f"tiles{world}: C-library scheduler (vr_mgpu_*), 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place "
                                       "into the root GPU's frame over NVLink (CUDA IPC), device-stored completion counters polled by the root's CPU, 4 frame buffers; "
-                                      "2 launches per frame and rank (ray kernel + 1-thread signal kernel)",
+                                      "1 launch per frame and rank (the completion counter is a stream memory operation, cuStreamWriteValue64)",
                        "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
                        "per_rank_ms_per_frame": per_rank_ms,
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
