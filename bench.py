@@ -302,6 +302,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     must(c.create_texture_atlas(S.synthetic_atlas(), (16, 16)), "atlas")
     must(c.validate(), "validate")
     must(c.set_option("walk", args.walk), "walk")
+    must(c.set_option("directed_grid", args.directed_grid), "directed_grid")
     frames = torch.empty((len(mine), H, W, 4), dtype=torch.uint8, device=dev)
     # rays per batch from one untimed aux pass per view
     must(c.enable_aux(True), "aux")
@@ -359,7 +360,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
             "gpu_launches": int(launches),
             "config": {"workload": "c5: 64 random cameras x 1920x1080, 1024^3 shell terrain SVO, primary + 1 shadow light (BASELINE configs[4], not the headline)",
                        "parallelism": f"views{world}: view v on rank v % {world}", "views": views, "rays_per_batch": rays,
-                       "walk": WALK_NAMES[args.walk],
+                       "walk": WALK_NAMES[args.walk], "top_grid": "directed" if args.directed_grid else "undirected",
                        "ms_per_view": ms / (views / world) if world else None},
             "roofline": c5_roofline(ms, world), "cpu_baseline": None,
             "e2e": {"value": rays / (e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
@@ -415,6 +416,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     must(c.mgpu_broadcast_octree(), "mgpu_broadcast_octree")
     must(c.validate(), "validate")
     must(c.set_option("walk", args.walk), "walk")
+    must(c.set_option("directed_grid", args.directed_grid), "directed_grid")
     st0 = c.stats()
     bcast_bytes = int(st0.native_bytes)
 
@@ -521,7 +523,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}",
-                       "mode": "svo", "walk": WALK_NOTES[args.walk],
+                       "mode": "svo", "walk": WALK_NOTES[args.walk], "top_grid": "directed" if args.directed_grid else "undirected",
                        "kernel_variant": "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM",
                        "parallelism": f"tiles{world}: C-library scheduler (vr_mgpu_*), 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place "
                                       "into the root GPU's frame over NVLink (CUDA IPC), device-stored completion counters polled by the root's CPU, 4 frame buffers; "
@@ -562,6 +564,8 @@ def main() -> None:
                     help="in-cell walk of the octree kernel: 2 = closed-form crossing times (default: within BASELINE.json's tolerance of the reference walk, "
                     "see DESIGN.md section 2), 1 = literal additions walked per axis (exact except the step count of exact-tie rays), "
                     "0 = literal additions, merged walk (bit-identical to the reference on every pixel)")
+    ap.add_argument("--directed-grid", type=int, default=1, choices=[0, 1],
+                    help="top grid of the closed-form walk: 1 = one table per direction octant of the ray (default), 0 = the single undirected table")
     ap.add_argument("--overlap-frames", type=int, default=1, help="N > 1: 1 = consecutive frames are launched on two alternating streams (the next frame's "
                     "first CTAs fill the tail of the current one); the kernel events then overlap, so roofline.kernel_ms is the step time")
     ap.add_argument("--host-frame", default="shared", choices=["shared", "root"],
@@ -650,6 +654,7 @@ def main() -> None:
     must(c.set_option("persistent", args.persistent) and c.set_option("refill_min", args.refill_min)
          and c.set_option("ctas_per_sm", args.ctas_per_sm), "set_option")
     must(c.set_option("walk", args.walk), "walk")
+    must(c.set_option("directed_grid", args.directed_grid), "directed_grid")
     if args.l2_persist and use_svo:
         must(c.set_option("l2_persist", 1), "l2_persist")
 
@@ -781,6 +786,20 @@ def main() -> None:
             torch.cuda.synchronize()
             other_walk_ms[WALK_NAMES[w]] = o0.elapsed_time(o1) / 10
         must(c.set_option("walk", args.walk), "walk")
+        if args.walk == 2:
+            # the same walk over the other kind of top grid (the tables are rebuilt, outside the timed frames)
+            must(c.set_option("directed_grid", 0 if args.directed_grid else 1), "directed_grid")
+            must(c.compute_into(slab.data_ptr()), "compute_into")
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(3 + 10):
+                if i == 3:
+                    o0.record(stream)
+                must(c.compute_into(slab.data_ptr()), "compute_into")
+            o1.record(stream)
+            torch.cuda.synchronize()
+            other_walk_ms["closed-form, " + ("undirected" if args.directed_grid else "directed") + " top grid"] = o0.elapsed_time(o1) / 10
+            must(c.set_option("directed_grid", args.directed_grid), "directed_grid")
+            must(c.compute_into(slab.data_ptr()), "compute_into")
 
     # ---- end to end through the public API with HOST buffers: camera/lights are read from host memory at every
     # call, the frame is copied back to pinned host memory inside the timed region (double buffered at N = 1)
@@ -862,7 +881,7 @@ def main() -> None:
             "data": "synthetic", "gpu_launches": int(launches),
             "config": {"workload": f"{args.config}: {scene.n}^3 shell terrain SVO, {W}x{H}, primary + {args.lights} shadow light{'s (multi-light extension)' if args.lights > 1 else ''}, max_distance {scene.max_distance}" + (" (BASELINE configs[3], not the headline)" if args.config == "c4" else ""),
                        "mode": args.mode,
-                       "walk": WALK_NOTES[args.walk] if use_svo else "dense DDA",
+                       "walk": WALK_NOTES[args.walk] if use_svo else "dense DDA", "top_grid": "directed" if args.directed_grid else "undirected",
                        "other_walk_ms_per_frame": other_walk_ms, "sustained": sustained,
                        "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",

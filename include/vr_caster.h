@@ -172,7 +172,10 @@ int vr_assign_native_tree(vr_ctx *ctx, const void *device_nodes, uint64_t node_b
 /* The top grid the closed-form walk (option walk = 2) reads instead of the upper octree levels: a dense table over the
  * blocks of edge 1 << *grid_shift derived from the 64-tree on the device (csrc/vr_build.cu: vr_build_grid_device; layout
  * in csrc/vr_types.h).  Builds it if necessary and copies it to `host_out` when capacity (entries) suffices.  Returns
- * the number of entries, 0 on failure (e.g. a map of 4^3 or less has no grid).  For tests / inspection. */
+ * the number of entries, 0 on failure (e.g. a map of 4^3 or less has no grid).  For tests / inspection.
+ * With option "directed_grid" = 1 (the default) the grid is eight tables, one per direction octant of a ray (bit a of the
+ * octant number set = the ray moves towards lower coordinates on axis a), 8 << (3 * *grid_bits) entries, octant 0 first;
+ * with 0 it is the single undirected table of 1 << (3 * *grid_bits) entries. */
 uint64_t vr_top_grid_read(vr_ctx *ctx, uint32_t *host_out, uint64_t capacity, int32_t *grid_shift, int32_t *grid_bits);
 
 /* Multi-GPU frame assembly without SM involvement: every rank pushes its band slab straight into the frame

@@ -24,11 +24,12 @@ if [ "$cmd" = build ]; then
   done
 elif [ "$cmd" = run ]; then
   cfg=$1; shift
-  for v in "$@"; do
+  for vv in "$@"; do
+    v=${vv%%@*}; extra=""; [ "$v" != "$vv" ] && extra=${vv#*@}      # name@--bench-arg=value,--other=value
     if [ "$v" = main ]; then unset VR_CASTER_LIB; else export VR_CASTER_LIB="$PWD/build/ab/lib_$v.so"; fi
-    python bench.py --config "$cfg" --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+    python bench.py --config "$cfg" --steps 30 --warmup 5 --no-cpu-baseline ${extra//,/ } 2>/dev/null | python -c "
 import json,sys
-j=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('$cfg $v', round(j['ms_per_step'],4), {k: round(x, 4) for k, x in (j['config'].get('other_walk_ms_per_frame') or {}).items()}, j['config']['frame_checksum'])"
+j=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('$cfg $vv', round(j['ms_per_step'],4), {k: round(x, 4) for k, x in (j['config'].get('other_walk_ms_per_frame') or {}).items()}, j['config']['frame_checksum'])"
   done
 else
   echo "usage: $0 build name:flags ... | run <config> <variant> ..."; exit 2

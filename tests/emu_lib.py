@@ -83,16 +83,17 @@ def tree_from_ref(desc: np.ndarray, root: int, dim: int):
     return _tree(lib().emu_tree_from_ref, d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size), C.c_uint64(root), C.c_int(dim))
 
 
-def grid_from_tree(nodes: np.ndarray, levels: int, dim: int):
-    """host version of the closed-form walk's top grid (vr_octree.cpp: vr_native_grid): (uint32[G,G,G], shift, bits)"""
+def grid_from_tree(nodes: np.ndarray, levels: int, dim: int, directed: bool = False):
+    """host version of the closed-form walk's top grid (vr_octree.cpp): vr_native_grid -> (uint32[G,G,G], shift, bits);
+    directed: vr_native_grid_directed -> (uint32[8,G,G,G], shift, bits), one table per direction octant"""
     nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
-    cap = 1 << 24
+    cap = 1 << (27 if directed else 24)
     out = np.zeros(cap, dtype=np.uint32)
     gs, gb = C.c_int(0), C.c_int(0)
-    fn = lib().emu_grid_from_tree
+    fn = lib().emu_grid_directed_from_tree if directed else lib().emu_grid_from_tree
     fn.restype = C.c_long
     n = fn(nodes.ctypes.data_as(C.c_void_p), C.c_int(levels), C.c_int(dim), out.ctypes.data_as(C.c_void_p), C.c_long(cap), C.byref(gs), C.byref(gb))
     if n < 0:
         raise RuntimeError(f"grid build failed: {n}")
     g = 1 << gb.value
-    return out[:n].reshape(g, g, g).copy(), gs.value, gb.value
+    return (out[:n].reshape(8, g, g, g) if directed else out[:n].reshape(g, g, g)).copy(), gs.value, gb.value

@@ -47,10 +47,11 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
         P.levels = tree.levels; P.root_shift = 2 * (tree.levels - 1);
     }
     std::vector<uint32_t> grid;
-    if (use_svo == 3) {
+    if (use_svo >= 3) {                      /* 3: closed-form walk over the undirected top grid, 4: over the directed ones */
         int gs = 0, gb = 0;
-        if (!vr_native_grid(tree.nodes.data(), tree.levels, n, grid, &gs, &gb)) return -3;
+        if (!(use_svo == 4 ? vr_native_grid_directed : vr_native_grid)(tree.nodes.data(), tree.levels, n, grid, &gs, &gb)) return -3;
         P.grid = grid.data(); P.grid_shift = gs; P.grid_bits = gb; P.grid_dim = 1 << gb;
+        P.grid_directed = use_svo == 4;
     }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = 0; y < height; y++)
@@ -60,12 +61,12 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
             bool w;
             LocalStack s;
             if (P.light_count > 1) {
-                if (use_svo == 3) w = vr_trace_svo_canon<true, true>(P, x, y, &px, &a, s);
+                if (use_svo >= 3) w = vr_trace_svo_canon<true, true>(P, x, y, &px, &a, s);
                 else if (use_svo == 2) w = vr_trace_svo<true, 1, true>(P, x, y, &px, &a, s);
                 else if (use_svo) w = vr_trace_svo<true, 0, true>(P, x, y, &px, &a, s);
                 else w = vr_trace_dense<true, true>(P, x, y, &px, &a);
             } else {
-                if (use_svo == 3) w = vr_trace_svo_canon<true, false>(P, x, y, &px, &a, s);
+                if (use_svo >= 3) w = vr_trace_svo_canon<true, false>(P, x, y, &px, &a, s);
                 else if (use_svo == 2) w = vr_trace_svo<true, 1, false>(P, x, y, &px, &a, s);
                 else if (use_svo) w = vr_trace_svo<true, 0, false>(P, x, y, &px, &a, s);
                 else w = vr_trace_dense<true, false>(P, x, y, &px, &a);
@@ -104,6 +105,32 @@ extern "C" long emu_tree_from_columns(const int32_t *lo, const int32_t *hi, int 
 extern "C" long emu_grid_from_tree(const void *nodes, int levels, int dim, uint32_t *out, long cap, int *shift, int *bits) {
     std::vector<uint32_t> g;
     if (!vr_native_grid((const vr_node *)nodes, levels, dim, g, shift, bits)) return -1;
+    if ((long)g.size() > cap) return -2;
+    memcpy(out, g.data(), g.size() * sizeof(uint32_t));
+    return (long)g.size();
+}
+
+/* vr_div_const (vr_trace.h) against the IEEE division it replaces, over the whole range of its operands: texel / 255 for
+ * texel = 0..255 and steps / 700 for steps = 0..2^24.  Returns the number of differing quotients. */
+extern "C" long emu_div_const_mismatches() {
+    long bad = 0;
+    for (int i = 0; i <= 255; i++) {
+        volatile float x = (float)i;
+        const float q = VR_DIV_255((float)i), ref = x / 255.0f;
+        bad += memcmp(&q, &ref, 4) != 0;
+    }
+    for (int i = 0; i <= (1 << 24); i++) {
+        volatile float x = (float)i;
+        const float q = VR_DIV_700((float)i), ref = x / 700.0f;
+        bad += memcmp(&q, &ref, 4) != 0;
+    }
+    return bad;
+}
+
+/* the directed top grids (vr_octree.cpp: vr_native_grid_directed): eight tables, octant 0 first */
+extern "C" long emu_grid_directed_from_tree(const void *nodes, int levels, int dim, uint32_t *out, long cap, int *shift, int *bits) {
+    std::vector<uint32_t> g;
+    if (!vr_native_grid_directed((const vr_node *)nodes, levels, dim, g, shift, bits)) return -1;
     if ((long)g.size() > cap) return -2;
     memcpy(out, g.data(), g.size() * sizeof(uint32_t));
     return (long)g.size();

@@ -1,0 +1,150 @@
+"""CPU tests of the closed-form walk (voxel-raycaster_b200/csrc/vr_canon.h, library default walk = 2) compiled for the host
+(tests/host_emu): over the undirected top grid (use_svo = 3) and over the directed ones (use_svo = 4, one table per
+direction octant of the ray: vr_octree.cpp: vr_native_grid_directed) against Oracle-B = the oracle with closed-form
+crossing times.  Same bar as the GPU suite (tests/test_gpu_canonical.py: assert_equals_oracle_b): identical on every
+pixel whose ray makes no exact multi-axis step, same first hit and RGBA8 within +-1 on the others.  Plus the invariants of
+the directed grids against the dense map."""
+import numpy as np
+import pytest
+
+import emu_lib
+from conftest import oracle_bias
+from test_gpu_canonical import assert_equals_oracle_b
+from test_gpu_parity import SMALL
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_closed_form_walk_small_scenes(pkg, oracle, name):
+    scene = pkg.scene.make_scene(name)
+    table = oracle.make_ray_table(scene.width, scene.height)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root), canonical_t=True)
+    bias = oracle_bias(oracle, scene, desc, root)
+    frames = []
+    for use_svo in (3, 4):
+        rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo)
+        assert_equals_oracle_b(ref_rgba, ref_aux, rgba, aux, f"{name} svo={use_svo}")
+        frames.append((rgba, aux))
+    # the two grids only change which empty cells a ray is handed: the frames are the same, the lookups fewer
+    assert np.array_equal(frames[0][0], frames[1][0])
+    assert frames[1][1]["lookups"].sum() <= frames[0][1]["lookups"].sum()
+
+
+def test_closed_form_walk_terrain(pkg, oracle):
+    """64^3 shell terrain with 5 % mirrors, three cameras, two lights: the directed grids hand out far larger cells (rays
+    leaving the surface towards a light), the frame must not change."""
+    S = pkg.scene
+    vol = S.terrain_map(64, "shell", reflect_fraction=0.05)
+    fewer = 0
+    for cam in (1, 3, 5):
+        pos, direction = S.make_camera(64, S.heightfield(64), cam)
+        scene = S.Scene(64, vol, 320, 180, pos, direction, S.make_lights(64, 2), max_distance=192)
+        table = oracle.make_ray_table(scene.width, scene.height)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, table, shadow_lights=2, canonical_t=True)
+        look = []
+        for use_svo in (3, 4):
+            rgba, aux = emu_lib.raycast(scene, table, use_svo=use_svo, shadow_lights=2)
+            assert_equals_oracle_b(ref_rgba, ref_aux, rgba, aux, f"terrain cam {cam} svo={use_svo}")
+            look.append(int(aux["lookups"].sum()))
+        fewer += look[1] < look[0]
+    assert fewer == 3
+
+
+def test_closed_form_walk_random_and_sparse_scenes(pkg, oracle):
+    """Differential fuzzing on the CPU: random scenes (maps 8^3..64^3, cameras inside / outside / on integer coordinates,
+    1-3 lights) and sparse 128^3 maps with cameras in collapsed empty cells (negative start bias, kernel:353)."""
+    from test_emu_parity import random_scene
+    from test_gpu_canonical import sparse_scene
+
+    rng = np.random.default_rng(21)
+    cases = [random_scene(pkg, rng) for _ in range(24)] + [sparse_scene(pkg, rng, 128) for _ in range(4)]
+    for it, (scene, nl) in enumerate(cases):
+        table = oracle.make_ray_table(scene.width, scene.height)
+        desc, root = pkg.octree_generate(scene.volume)
+        ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+        bias = oracle_bias(oracle, scene, desc, root)
+        if scene.n < 8:
+            continue                                   # no top grid below 8^3: the library falls back to walk 0
+        for use_svo in (3, 4):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_equals_oracle_b(ref_rgba, ref_aux, rgba, aux, f"scene {it} (n={scene.n}) svo={use_svo}")
+
+
+@pytest.mark.parametrize("kind", ["terrain64", "terrain256", "random32", "sparse128", "half32"])
+def test_directed_grid_invariants(pkg, kind):
+    """vr_native_grid_directed: in every octant table a block is non-empty exactly when it holds a set voxel (same node
+    entry as the undirected grid); an empty entry describes a box that starts at the block, extends along the octant's
+    direction of travel, lies inside the map and holds no set voxel; a cube entry is maximal (one more layer of blocks
+    would leave the map, hit a voxel or exceed the cap) and at least as wide as the undirected grid's centred cube."""
+    S = pkg.scene
+    rng = np.random.default_rng(8)
+    if kind.startswith("terrain"):
+        vol = S.terrain_map(int(kind[7:]), "shell")
+    elif kind == "random32":
+        vol = (rng.random((32, 32, 32)) < 0.03).astype(np.int8) * 5
+    elif kind == "sparse128":
+        vol = (rng.random((128, 128, 128)) < 0.0003).astype(np.int8) * 6
+    else:
+        vol = np.zeros((32, 32, 32), np.int8)
+        vol[:16] = 5
+    n = vol.shape[0]
+    nodes, types, levels = emu_lib.tree_from_dense(vol)
+    und, g, bits = emu_lib.grid_from_tree(nodes, levels, n)
+    grid, g2, bits2 = emu_lib.grid_from_tree(nodes, levels, n, directed=True)
+    G = 1 << bits
+    assert (g2, bits2) == (g, bits) and grid.shape == (8, G, G, G)
+    bs = 1 << g
+    cap = min(64, G)
+    solid = (vol == 5) | (vol == 6)
+    blocks = solid.reshape(G, bs, G, bs, G, bs).any(axis=(1, 3, 5))                      # [bz, by, bx]
+    occ = np.zeros((G + 1, G + 1, G + 1), np.int64)
+    empties = np.argwhere(~blocks)
+    if len(empties) > 6000:
+        empties = empties[rng.choice(len(empties), 6000, replace=False)]
+    wider = 0
+    for o in range(8):
+        t = grid[o]
+        assert np.array_equal(t[blocks], und[blocks]) and ((t & 0x80000000) != 0).sum() == blocks.sum()
+        # mirrored occupancy + summed-area table: axis a flipped when bit a of the octant is set (x = bit 0 = last axis)
+        mb = blocks
+        if o & 1: mb = mb[:, :, ::-1]
+        if o & 2: mb = mb[:, ::-1, :]
+        if o & 4: mb = mb[::-1, :, :]
+        occ[1:, 1:, 1:] = mb.astype(np.int64).cumsum(0).cumsum(1).cumsum(2)
+
+        def count(lo, hi):          # non-empty blocks in [lo, hi) per axis, mirrored block coordinates (z, y, x)
+            (z0, y0, x0), (z1, y1, x1) = lo, hi
+            return (occ[z1, y1, x1] - occ[z0, y1, x1] - occ[z1, y0, x1] - occ[z1, y1, x0]
+                    + occ[z0, y0, x1] + occ[z0, y1, x0] + occ[z1, y0, x0] - occ[z0, y0, x0])
+
+        for bz, by, bx in empties:
+            e = int(t[bz, by, bx])
+            m, ext = (1 << (e & 31)) - 1, e >> 8
+            k = (G - 1 - bz if o & 4 else bz, G - 1 - by if o & 2 else by, G - 1 - bx if o & 1 else bx)   # mirrored (z, y, x)
+            assert m >= bs - 1 and ext % bs == 0 and (ext == 0 or m == bs - 1), (kind, o, e)
+            lo = [((kk << g) & ~m) >> g for kk in k]
+            hi = [((((kk << g) | m) + ext) >> g) + 1 for kk in k]
+            assert min(lo) >= 0 and max(hi) <= G, (kind, o, bz, by, bx, e)
+            assert count(lo, hi) == 0, (kind, o, bz, by, bx, e)
+            if m == bs - 1:                                                             # a cube with the block in its rear corner
+                edge = ext // bs + 1
+                assert lo == list(k) and edge <= cap
+                if edge < cap:                                                          # maximal
+                    grown = [kk + edge + 1 for kk in k]
+                    assert max(grown) > G or count(k, grown) > 0, (kind, o, bz, by, bx, e)
+                u = int(und[bz, by, bx])
+                if (u & 31) == g:                                                       # undirected: centred cube of radius r
+                    assert edge >= min((u >> 8) // bs + 1, cap)
+                    wider += edge > (u >> 8) // bs + 1
+    if kind not in ("random32", "half32"):             # (half32: the aligned 16^3 cells reach further everywhere)
+        assert wider > 0
+
+
+def test_division_by_constants_is_the_ieee_quotient():
+    """vr_div_const (vr_trace.h): texel / 255 and steps / 700 through the reciprocal + two FMAs give the correctly rounded
+    quotient of kernel:654-656 / 565 / 716 for every operand they can see (0..255, 0..2^24): exhaustive."""
+    import ctypes as C
+
+    fn = emu_lib.lib().emu_div_const_mismatches
+    fn.restype = C.c_long
+    assert fn() == 0

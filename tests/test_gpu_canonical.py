@@ -52,9 +52,13 @@ def test_canonical_walk_small(pkg, oracle, name):
     scene = pkg.scene.make_scene(name)
     desc, root = pkg.octree_generate(scene.volume)
     ref_rgba, ref_aux, _ = oracle.raycast(scene, octree=(desc, root), canonical_t=True)
-    c = make_caster(pkg, scene, True, walk=None)        # the library default IS the closed-form walk
+    c = make_caster(pkg, scene, True, walk=None)        # the library default IS the closed-form walk over the directed grids
     assert c.compute(), c.last_error()
-    assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 {name}")
+    rgba = c.draw()
+    assert_equals_oracle_b(ref_rgba, ref_aux, rgba, c.read_aux(), f"walk 2 {name}")
+    assert c.set_option("directed_grid", 0) and c.compute(), c.last_error()            # the single undirected table
+    assert_equals_oracle_b(ref_rgba, ref_aux, c.draw(), c.read_aux(), f"walk 2 {name}, undirected grid")
+    assert np.array_equal(rgba, c.draw())
     c.close()
 
 
@@ -84,6 +88,14 @@ def test_canonical_walk_full_size_c3(pkg, oracle):
     assert c.set_option("walk", 2) and c.compute(), c.last_error()
     rgba, aux = c.draw(), c.read_aux()
     assert c.compute() and np.array_equal(c.draw(), rgba)                 # deterministic
+    # the undirected top grid hands the rays other (smaller) empty cells: not a pixel may change, only the lookup count
+    assert c.set_option("directed_grid", 0) and c.compute(), c.last_error()
+    und_aux = c.read_aux()
+    assert np.array_equal(c.draw(), rgba)
+    for f in INT_FIELDS:
+        assert np.array_equal(und_aux[f], aux[f]), f
+    print(f"c3 lookups per pixel: directed grids {aux['lookups'].mean():.2f}, undirected grid {und_aux['lookups'].mean():.2f}")
+    assert aux["lookups"].sum() < 0.7 * und_aux["lookups"].sum()
     c.close()
     k = 24
     b_rgba, b_aux, _ = oracle.raycast(scene, row_stride=k, canonical_t=True)
@@ -180,10 +192,12 @@ def test_sparse_maps_all_walks(pkg, oracle, n):
     assert biased >= 2
 
 
+@pytest.mark.parametrize("directed", [1, 0])
 @pytest.mark.parametrize("kind", ["features", "terrain64", "terrain256", "terrain512", "random32", "empty16", "sparse128"])
-def test_top_grid_device_equals_host(pkg, kind):
+def test_top_grid_device_equals_host(pkg, kind, directed):
     """The top grid of walk = 2 (vr_build.cu: vr_build_grid_device, derived from the 64-tree in HBM) equals the host
-    version (vr_octree.cpp: vr_native_grid) entry by entry, for trees built on the device."""
+    version (vr_octree.cpp: vr_native_grid_directed = the eight per-octant tables, the default; vr_native_grid = the
+    undirected table) entry by entry, for trees built on the device."""
     import emu_lib
     import torch
 
@@ -206,8 +220,9 @@ def test_top_grid_device_equals_host(pkg, kind):
     types = torch.empty(tb, dtype=torch.uint8, device="cuda:0")
     assert c.native_tree_copy(nodes.data_ptr(), types.data_ptr())
     torch.cuda.synchronize()
+    assert c.set_option("directed_grid", directed)
     grid, gs, gb = c.top_grid()
-    ref, rs, rb = emu_lib.grid_from_tree(nodes.cpu().numpy().view(np.uint32).reshape(-1, 4), levels, dim)
+    ref, rs, rb = emu_lib.grid_from_tree(nodes.cpu().numpy().view(np.uint32).reshape(-1, 4), levels, dim, directed=bool(directed))
     c.close()
     assert (gs, gb) == (rs, rb) and grid.shape == ref.shape
     assert np.array_equal(grid, ref), f"{kind}: {int((grid != ref).sum())} entries differ"

@@ -384,7 +384,8 @@ class CUDACaster:
         return bool(self._lib.vr_mgpu_shutdown(self._ctx))
 
     def top_grid(self) -> tuple[np.ndarray, int, int]:
-        """(grid entries as uint32[G, G, G] indexed [z, y, x], block shift, log2 G) of the closed-form walk's top grid."""
+        """(grid entries, block shift, log2 G) of the closed-form walk's top grid: uint32[8, G, G, G] indexed [octant, z, y, x]
+        (option directed_grid = 1, the default: one table per direction octant of a ray) or uint32[G, G, G]."""
         gs, gb = C.c_int32(0), C.c_int32(0)
         n = int(self._lib.vr_top_grid_read(self._ctx, None, 0, C.byref(gs), C.byref(gb)))
         if n == 0:
@@ -393,7 +394,7 @@ class CUDACaster:
         if int(self._lib.vr_top_grid_read(self._ctx, out.ctypes.data_as(_vp), n, C.byref(gs), C.byref(gb))) != n:
             raise RuntimeError(self.last_error())
         g = 1 << gb.value
-        return out.reshape(g, g, g), int(gs.value), int(gb.value)
+        return (out.reshape(8, g, g, g) if n == 8 * g ** 3 else out.reshape(g, g, g)), int(gs.value), int(gb.value)
 
     def native_tree_copy(self, device_nodes: int, device_types: int) -> bool:
         return bool(self._lib.vr_native_tree_copy(self._ctx, _vp(device_nodes), _vp(device_types)))

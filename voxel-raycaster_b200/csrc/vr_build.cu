@@ -354,9 +354,56 @@ __global__ void vr_grid_finish(uint32_t *grid, const uint8_t *cell, int g, unsig
     grid[i] = (((2u * d + 1u) << g) > (1u << cell[i])) ? ((uint32_t)g | ((d << g) << 8)) : (uint32_t)cell[i];
 }
 
+/* ---- directed top grids (vr_octree.cpp: vr_native_grid_directed): eight tables, one per direction octant ----------
+ * E[o][b] = edge (blocks) of the largest empty cube with block b in its rear corner that extends along octant o's
+ * direction of travel, by the 3-D maximal-square recurrence run as VR_GRID_MAX_CUBE - 1 relaxation launches: in launch r
+ * a block of edge r whose seven forward neighbours all have edge >= r gets r + 1.  In place: a neighbour raised in the
+ * same launch still passes the test, one below r never does, so the result does not depend on the order. */
+__global__ void vr_cube_init(const uint32_t *__restrict__ base, unsigned n, uint8_t *__restrict__ E) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t v = (base[i] & 0x80000000u) ? 0 : 1;
+#pragma unroll
+    for (int o = 0; o < 8; o++) E[(size_t)o * n + i] = v;
+}
+
+__global__ void vr_cube_grow(uint8_t *E, int bits, unsigned r) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = 1u << (3 * bits), G = 1u << bits;
+    if (t >= 8u * n) return;
+    if (E[t] != r) return;
+    const unsigned o = t >> (3 * bits), i = t & (n - 1u);
+    const unsigned bx = i & (G - 1u), by = (i >> bits) & (G - 1u), bz = i >> (2 * bits);
+    const int sx = (o & 1u) ? -1 : 1, sy = (o & 2u) ? -1 : 1, sz = (o & 4u) ? -1 : 1;
+    /* the forward neighbours must exist: mirrored coordinate below G - 1 on every axis */
+    if (bx == ((o & 1u) ? 0u : G - 1u) || by == ((o & 2u) ? 0u : G - 1u) || bz == ((o & 4u) ? 0u : G - 1u)) return;
+    const volatile uint8_t *Eo = E + (size_t)o * n;
+#pragma unroll
+    for (int d = 1; d < 8; d++) {
+        const unsigned j = (unsigned)((int)bx + ((d & 1) ? sx : 0)) + (((unsigned)((int)by + ((d & 2) ? sy : 0))) << bits) +
+                           (((unsigned)((int)bz + ((d & 4) ? sz : 0))) << (2 * bits));
+        if (Eo[j] < r) return;
+    }
+    E[t] = (uint8_t)(r + 1u);
+}
+
+__global__ void vr_cube_finish(const uint32_t *__restrict__ base, const uint8_t *__restrict__ cell, const uint8_t *__restrict__ E,
+                               int g, int bits, uint32_t *__restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = 1u << (3 * bits), G = 1u << bits;
+    if (t >= 8u * n) return;
+    const unsigned o = t >> (3 * bits), i = t & (n - 1u);
+    const uint32_t b = base[i];
+    if (b & 0x80000000u) { out[t] = b; return; }
+    const unsigned bx = i & (G - 1u), by = (i >> bits) & (G - 1u), bz = i >> (2 * bits);
+    const int kx = (o & 1u) ? (int)(G - 1u - bx) : (int)bx, ky = (o & 2u) ? (int)(G - 1u - by) : (int)by,
+              kz = (o & 4u) ? (int)(G - 1u - bz) : (int)bz;
+    out[t] = vr_grid_directed_entry(E[t], cell[i], g, kx, ky, kz);
+}
+
 }  // namespace
 
-cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cudaStream_t stream, uint32_t **grid_out,
+cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, bool directed, cudaStream_t stream, uint32_t **grid_out,
                                  int *grid_shift, int *grid_bits, unsigned long long *launches) {
     const int root_shift = 2 * (levels - 1);
     if (root_shift < 2 || dim < 8) return cudaErrorInvalidValue;
@@ -364,21 +411,35 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cu
     const int G = dim >> g;
     int bits = 0;
     while ((1 << bits) < G) bits++;
+    if (directed && (1 << bits) != G) return cudaErrorInvalidValue;
     const unsigned n = (unsigned)G * G * G;
-    uint32_t *grid = nullptr;
-    uint8_t *cell = nullptr;
+    uint32_t *grid = nullptr, *tables = nullptr;
+    uint8_t *cell = nullptr, *E = nullptr;
     cudaError_t e = cudaMalloc(&grid, (size_t)n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&cell, n);
-    if (e != cudaSuccess) { cudaFree(grid); cudaFree(cell); return e; }
+    if (e == cudaSuccess && directed) e = cudaMalloc(&E, (size_t)8 * n);
+    if (e == cudaSuccess && directed) e = cudaMalloc(&tables, (size_t)8 * n * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(grid); cudaFree(cell); cudaFree(E); cudaFree(tables); return e; }
     const unsigned blocks = (n + 255) / 256;
     vr_grid_classify<<<blocks, 256, 0, stream>>>(d_nodes, root_shift, g, G, dim, grid, cell);
-    const int rmax = G / 2 < 63 ? G / 2 : 63;                            /* a cube of radius r inside the grid needs G >= 2r + 1 */
-    for (int r = 1; r <= rmax; r++) vr_grid_erode<<<blocks, 256, 0, stream>>>(grid, G, (uint32_t)r);
-    vr_grid_finish<<<blocks, 256, 0, stream>>>(grid, cell, g, n);
-    if (launches) *launches += 2 + (rmax > 0 ? rmax : 0);
+    if (directed) {
+        const unsigned blocks8 = (unsigned)(((size_t)8 * n + 255) / 256);
+        const unsigned cap = (unsigned)G < VR_GRID_MAX_CUBE ? (unsigned)G : VR_GRID_MAX_CUBE;
+        vr_cube_init<<<blocks, 256, 0, stream>>>(grid, n, E);
+        for (unsigned r = 1; r < cap; r++) vr_cube_grow<<<blocks8, 256, 0, stream>>>(E, bits, r);
+        vr_cube_finish<<<blocks8, 256, 0, stream>>>(grid, cell, E, g, bits, tables);
+        if (launches) *launches += 3 + (cap > 1 ? cap - 1 : 0);
+    } else {
+        const int rmax = G / 2 < 63 ? G / 2 : 63;                        /* a cube of radius r inside the grid needs G >= 2r + 1 */
+        for (int r = 1; r <= rmax; r++) vr_grid_erode<<<blocks, 256, 0, stream>>>(grid, G, (uint32_t)r);
+        vr_grid_finish<<<blocks, 256, 0, stream>>>(grid, cell, g, n);
+        if (launches) *launches += 2 + (rmax > 0 ? rmax : 0);
+    }
     e = cudaStreamSynchronize(stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(cell);
+    cudaFree(E);
+    if (directed) { cudaFree(grid); grid = tables; }
     if (e != cudaSuccess) { cudaFree(grid); return e; }
     *grid_out = grid;
     *grid_shift = g;

@@ -29,8 +29,9 @@ cudaError_t vr_build_tree_columns_device(const int32_t *d_lo, const int32_t *d_h
                                          vr_device_tree *out, unsigned long long *launches);
 
 /* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree d_nodes: *grid_out is
- * cudaMalloc'ed (ownership passes to the caller).  cudaErrorInvalidValue when the tree is too shallow for a grid. */
-cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, cudaStream_t stream, uint32_t **grid_out,
+ * cudaMalloc'ed (ownership passes to the caller).  cudaErrorInvalidValue when the tree is too shallow for a grid.
+ * directed: the eight per-octant tables (8 << (3 * grid_bits) entries, vr_octree.cpp: vr_native_grid_directed). */
+cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, bool directed, cudaStream_t stream, uint32_t **grid_out,
                                  int *grid_shift, int *grid_bits, unsigned long long *launches);
 
 #endif

@@ -56,6 +56,11 @@
 #define VR_RARE() ((void)0)
 #endif
 
+/* analysis hook (profiles/canon_stats.py builds the host emulation with it): one call per turn of the cell loop */
+#ifndef VR_CANON_STAT
+#define VR_CANON_STAT(brick, m, ext, steps, shadow) ((void)0)
+#endif
+
 VR_HD int vr_hibit(int x) {          /* index of the highest set bit of x != 0 (31 for negative x) */
 #if defined(__CUDA_ARCH__)
     return 31 - __clz(x);
@@ -94,6 +99,7 @@ VR_HD void vr_canon_enter(const vr_frame_params &P, vr_cray<Stack> &q) {
     q.flip = (nx ? 3u : 0u) | (ny ? 0xCu : 0u) | (nz ? 0x30u : 0u);
     const uint32_t gm = (1u << P.grid_bits) - 1u;
     q.gflip = (nx ? gm : 0u) | (ny ? gm << P.grid_bits : 0u) | (nz ? gm << (2 * P.grid_bits) : 0u);
+    if (P.grid_directed) q.gflip |= ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u)) << (3 * P.grid_bits);   /* this octant's table */
     VR_PIN(q.bx); VR_PIN(q.by); VR_PIN(q.bz); VR_PIN(q.flip); VR_PIN(q.gflip);
 }
 
@@ -372,13 +378,16 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
                     int n;
                     known = vr_canon_brick(q, q.node.mask, n, T, xr, bit);
                     sum = q.px + q.py + q.pz;
+                    VR_CANON_STAT(1, 3, 0, n, r.shadow);
                     if (sum - before != n) {                               /* multi-axis steps inside the brick */
                         VR_RARE();
                         dbase -= sum - before - n;
                         tie = true;
                     }
                 } else {
+                    VR_CANON_STAT(0, c.m, c.ext, -(q.px + q.py + q.pz), r.shadow);
                     sum = vr_canon_walk(q, c, biased, T, dbase, tie, xr);
+                    VR_CANON_STAT(2, c.m, c.ext, sum, r.shadow);
                 }
                 VR_JOIN(sum);
                 r.dist = dbase + sum;

@@ -153,7 +153,7 @@ int apply_l2_window(vr_ctx *c) {
         int max_win = 0;
         cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
         const bool grid = c->l2_base && c->l2_base == (const void *)c->d_grid;
-        size_t bytes = grid ? ((size_t)4 << (3 * c->grid_bits)) : c->n_nodes * sizeof(vr_node);
+        size_t bytes = grid ? ((size_t)(c->grid_is_directed ? 32 : 4) << (3 * c->grid_bits)) : c->n_nodes * sizeof(vr_node);
         if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;      /* BFS order: top levels first */
         VR_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
         attr.accessPolicyWindow.base_ptr = grid ? (void *)c->d_grid : (void *)c->d_nodes;
@@ -187,8 +187,15 @@ int ensure_tree(vr_ctx *c) {
 int ensure_grid(vr_ctx *c) {
     if (c->d_grid || c->grid_tried) return 1;
     c->grid_tried = true;
-    const cudaError_t e = vr_build_grid_device(c->d_nodes, c->levels, c->tree_dim, c->stream, &c->d_grid, &c->grid_shift,
-                                               &c->grid_bits, &c->launches);
+    cudaError_t e = vr_build_grid_device(c->d_nodes, c->levels, c->tree_dim, c->grid_directed, c->stream, &c->d_grid, &c->grid_shift,
+                                         &c->grid_bits, &c->launches);
+    c->grid_is_directed = c->grid_directed;
+    if (e == cudaErrorMemoryAllocation && c->grid_directed) {
+        /* the eight directed tables (32 bytes per block) do not fit: the undirected table is an eighth of that */
+        cudaGetLastError();
+        e = vr_build_grid_device(c->d_nodes, c->levels, c->tree_dim, false, c->stream, &c->d_grid, &c->grid_shift, &c->grid_bits, &c->launches);
+        c->grid_is_directed = false;
+    }
     if (e != cudaSuccess && e != cudaErrorInvalidValue) return fail(c, "top grid build failed: %s", cudaGetErrorString(e));
     return 1;
 }
@@ -271,7 +278,7 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     P.levels = c->levels;
     P.root_shift = 2 * (c->levels - 1);
     P.grid = nullptr;
-    P.grid_shift = P.grid_bits = P.grid_dim = 0;
+    P.grid_shift = P.grid_bits = P.grid_dim = P.grid_directed = 0;
     if (svo && (c->tree_dim != P.dim[0] || P.dim[0] != P.dim[1] || P.dim[0] != P.dim[2]))
         return fail(c, "octree traversal needs a cubic power-of-two map");
     return 1;
@@ -295,6 +302,7 @@ int launch_frame(vr_ctx *c, uint8_t *image, bool timed) {
         P.grid_shift = c->grid_shift;
         P.grid_bits = c->grid_bits;
         P.grid_dim = 1 << c->grid_bits;
+        P.grid_directed = c->grid_is_directed ? 1 : 0;
     }
     if (c->l2_persist && use_svo) {
         /* the window covers what the selected walk reads at random: the top grid (closed-form walk) or the node array */
@@ -855,6 +863,20 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
     else if (n == "walk") c->opt.walk = (value == 1 || value == 2) ? (int)value : 0;
     else if (n == "gpu_build") c->gpu_build = value != 0;        /* 0: assign_map builds the 64-tree on the host */
+    else if (n == "directed_grid") {
+        /* top grid of the closed-form walk: 1 = one table per direction octant of the ray (default), 0 = one undirected table */
+        if (c->grid_directed != (value != 0)) {
+            c->grid_directed = value != 0;
+            if (c->d_grid) {
+                cudaSetDevice(c->device);
+                cudaStreamSynchronize(c->stream);
+                cudaFree(c->d_grid);
+                c->d_grid = nullptr;
+                if (c->l2_base && c->l2_persist) c->l2_base = nullptr;
+            }
+            c->grid_tried = false;
+        }
+    }
     else if (n == "l2_persist") {
         /* pin the 64-tree nodes in L2 (cudaAccessPolicyWindow) for every kernel launched on the context stream */
         if (!c->d_nodes) return fail(c, "set_option l2_persist: no octree yet");
@@ -915,7 +937,7 @@ uint64_t vr_top_grid_read(vr_ctx *c, uint32_t *host_out, uint64_t capacity, int3
     if (!c->tree_valid && !ensure_tree(c)) return 0;
     if (!ensure_grid(c)) return 0;
     if (!c->d_grid) { fail(c, "top_grid_read: the octree is too shallow for a top grid"); return 0; }
-    const uint64_t n = 1ull << (3 * c->grid_bits);
+    const uint64_t n = (c->grid_is_directed ? 8ull : 1ull) << (3 * c->grid_bits);     /* directed: the eight tables, octant 0 first */
     if (grid_shift) *grid_shift = c->grid_shift;
     if (grid_bits) *grid_bits = c->grid_bits;
     if (host_out && capacity >= n) {

@@ -56,6 +56,8 @@ struct vr_ctx {
     uint32_t *d_grid = nullptr;        /* top grid of the closed-form walk, built from d_nodes when first needed */
     int grid_shift = 0, grid_bits = 0;
     bool grid_tried = false;
+    bool grid_directed = true;         /* option "directed_grid": eight per-octant tables (the default) or the undirected table */
+    bool grid_is_directed = false;     /* what d_grid holds */
     bool l2_persist = false;           /* option "l2_persist": access-policy window over d_nodes, re-applied per tree */
     const void *l2_base = nullptr;
     int levels = 0, tree_dim = 0;

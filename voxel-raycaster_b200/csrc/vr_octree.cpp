@@ -418,7 +418,9 @@ int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shif
 }
 
 /* ---- top grid of the closed-form walk ------------------------------------------------------------------------- */
-bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits) {
+/* every block classified by a descent to the slot of edge 1 << g that is the block: grid = node entry (bit 31) or 0,
+ * cell = log2 edge of the aligned empty octree cell around an empty block */
+static bool grid_classify(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, std::vector<uint8_t> &cell, int *g_out, int *bits_out) {
     const int root_shift = 2 * (levels - 1);
     if (root_shift < 2 || dim < 8) return false;
     const int g = vr_grid_shift_for(root_shift, dim);
@@ -427,8 +429,7 @@ bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint3
     int bits = 0;
     while ((1 << bits) < G) bits++;
     grid.assign((size_t)G * G * G, 0u);
-    std::vector<uint8_t> cell((size_t)G * G * G, 0);      /* empty blocks: log2 edge of the aligned empty octree cell around */
-    /* (1) classify every block: descend to the slot of edge 1 << g that is the block */
+    cell.assign((size_t)G * G * G, 0);
     for (int bz = 0; bz < G; bz++)
         for (int by = 0; by < G; by++)
             for (int bx = 0; bx < G; bx++) {
@@ -450,6 +451,16 @@ bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint3
                 }
                 grid[i] = entry;
             }
+    *g_out = g;
+    *bits_out = bits;
+    return true;
+}
+
+bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits) {
+    std::vector<uint8_t> cell;
+    int g = 0, bits = 0;
+    if (!grid_classify(nodes, levels, dim, grid, cell, &g, &bits)) return false;
+    const int G = dim >> g;
     /* (2) Chebyshev distance to the nearest non-empty block or to the outside of the map, minus one, by repeated erosion
      * with the 3x3x3 cube: an empty block gets radius r when its 26 neighbours all exist and have radius >= r - 1 */
     for (uint32_t r = 1; r <= VR_GRID_MAX_RADIUS; r++) {
@@ -475,6 +486,52 @@ bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint3
         if (grid[i] & 0x80000000u) continue;
         const uint32_t d = grid[i];
         grid[i] = (((2u * d + 1u) << g) > (1u << cell[i])) ? ((uint32_t)g | ((d << g) << 8)) : (uint32_t)cell[i];
+    }
+    *grid_shift = g;
+    *grid_bits = bits;
+    return true;
+}
+
+/* ---- directed top grids: one table per direction octant ------------------------------------------------------ */
+/* A ray only ever needs the empty space AHEAD of it.  For octant o (bit a set = the ray moves towards lower coordinates
+ * on axis a) the entry of an empty block b holds the largest cube of empty blocks that has b in its rear corner and
+ * extends in the ray's direction on every axis: E(b) = 1 + min E(b + d), d in {0,1}^3 \ 0 taken along the direction of
+ * travel (the 3-D maximal-square recurrence; blocks outside the map count as 0, so a cube never leaves the map), capped
+ * at VR_GRID_MAX_CUBE.  It contains the centred cube of the undirected grid (radius r  =>  E >= r + 1) and is far wider
+ * for rays that move away from a surface.  Entry format = vr_native_grid's: m = block edge - 1, ext = (E - 1) blocks;
+ * the aligned octree cell around the block is kept where it reaches at least as far on every axis and further on one.
+ * Table o starts at entry o << (3 * grid_bits). */
+bool vr_native_grid_directed(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits) {
+    std::vector<uint32_t> base;
+    std::vector<uint8_t> cell;
+    int g = 0, bits = 0;
+    if (!grid_classify(nodes, levels, dim, base, cell, &g, &bits)) return false;
+    const int G = dim >> g;
+    if ((1 << bits) != G) return false;                                    /* the octant number is XORed into the key */
+    const size_t n3 = (size_t)G * G * G;
+    grid.assign(8 * n3, 0u);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int o = 0; o < 8; o++) {
+        std::vector<uint8_t> E(n3);
+        const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+        uint32_t *out = grid.data() + (size_t)o * n3;
+        for (int kz = G - 1; kz >= 0; kz--)
+            for (int ky = G - 1; ky >= 0; ky--)
+                for (int kx = G - 1; kx >= 0; kx--) {                      /* k = mirrored block coordinate, descending */
+                    const int bx = sx < 0 ? G - 1 - kx : kx, by = sy < 0 ? G - 1 - ky : ky, bz = sz < 0 ? G - 1 - kz : kz;
+                    const size_t i = (size_t)bx + (size_t)G * ((size_t)by + (size_t)G * bz);
+                    if (base[i] & 0x80000000u) { E[i] = 0; out[i] = base[i]; continue; }
+                    uint32_t mn = VR_GRID_MAX_CUBE;
+                    if (kx == G - 1 || ky == G - 1 || kz == G - 1) mn = 0;
+                    else
+                        for (int d = 1; d < 8; d++) {
+                            const size_t j = (size_t)(bx + ((d & 1) ? sx : 0)) + (size_t)G * ((size_t)(by + ((d & 2) ? sy : 0)) + (size_t)G * (bz + ((d & 4) ? sz : 0)));
+                            if (E[j] < mn) mn = E[j];
+                        }
+                    const uint32_t e = mn + 1 > VR_GRID_MAX_CUBE ? VR_GRID_MAX_CUBE : mn + 1;
+                    E[i] = (uint8_t)e;
+                    out[i] = vr_grid_directed_entry(e, cell[i], g, kx, ky, kz);
+                }
     }
     *grid_shift = g;
     *grid_bits = bits;

@@ -53,6 +53,8 @@ bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8
  * it on the device, vr_build.cu: vr_build_grid_device; this one serves the host emulation and checks that one).
  * Returns false when the tree is too shallow for a grid (a single level: maps up to 4^3). */
 bool vr_native_grid(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits);
+/* Directed top grids: eight tables, one per direction octant of the ray (see vr_octree.cpp); table o at o << (3 * bits). */
+bool vr_native_grid_directed(const vr_node *nodes, int levels, int dim, std::vector<uint32_t> &grid, int *grid_shift, int *grid_bits);
 #define VR_GRID_MAX_RADIUS 63
 
 /* Point query on the native tree: voxel value (5/6) or 0, and the empty-cell shift if empty. */

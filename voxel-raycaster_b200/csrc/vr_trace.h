@@ -61,6 +61,34 @@ VR_HD vf3 vr_i2f3(vi3 a) { return {(float)a.x, (float)a.y, (float)a.z}; }
 VR_HD float vr_dot(vf3 a, vf3 b) { return VR_ADD(VR_ADD(VR_MUL(a.x, b.x), VR_MUL(a.y, b.y)), VR_MUL(a.z, b.z)); }
 VR_HD float vr_length(vf3 a) { return VR_SQRT(vr_dot(a, a)); }
 VR_HD vf3 vr_normalize(vf3 a) { float l = vr_length(a); return {VR_DIV(a.x, l), VR_DIV(a.y, l), VR_DIV(a.z, l)}; }
+/* x / c for a compile-time constant c, with r = RN(1 / c): q0 = x r, q = fma(fma(-c, q0, x), r, q0).  The correctly
+ * rounded quotient -- the reference's IEEE division, bit for bit -- for the operands it is used on: texel / 255 with
+ * texel = 0..255 and steps / 700 with steps = 0..2^24 (tests/test_emu_canonical.py checks both ranges exhaustively);
+ * three FMA-pipe instructions instead of the ten of a general division.  -DVR_HIT_LITERAL restores the divisions. */
+#if defined(__CUDA_ARCH__)
+#define VR_FMA_RN(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#define VR_FMA_RN(a, b, c) fmaf((a), (b), (c))
+#endif
+VR_HD float vr_div_const(float x, float c, float r) {
+#if defined(VR_HIT_LITERAL)
+    (void)r;
+    return VR_DIV(x, c);
+#else
+    const float q0 = VR_MUL(x, r);
+    return VR_FMA_RN(VR_FMA_RN(-c, q0, x), r, q0);
+#endif
+}
+#define VR_DIV_255(x) vr_div_const((x), 255.0f, 1.0f / 255.0f)
+#define VR_DIV_700(x) vr_div_const((x), 700.0f, 1.0f / 700.0f)
+/* x / 2 and x / 4 are exact scalings */
+#if defined(VR_HIT_LITERAL)
+#define VR_HALF(x) VR_DIV((x), 2.0f)
+#define VR_QUARTER(x) VR_DIV((x), 4.0f)
+#else
+#define VR_HALF(x) VR_MUL((x), 0.5f)
+#define VR_QUARTER(x) VR_MUL((x), 0.25f)
+#endif
 VR_HD float vr_max(float x, float y) { return (x < y) ? y : x; }      /* OpenCL max(), NaN -> x */
 VR_HD float vr_min(float x, float y) { return (y < x) ? y : x; }
 VR_HD int vr_sign(float d) { return (d > 0.0f) - (d < 0.0f); }
@@ -165,7 +193,7 @@ VR_HD void vr_out_of_bounds(RayState &r) {
     r.voxel.x -= r.step.x * (r.fm & 1);
     r.voxel.y -= r.step.y * ((r.fm >> 1) & 1);
     r.voxel.z -= r.step.z * ((r.fm >> 2) & 1);
-    const float m = VR_SUB(1.0f, vr_max(VR_DIV((float)r.dist, 700.0f), 0.0f));
+    const float m = VR_SUB(1.0f, vr_max(VR_DIV_700((float)r.dist), 0.0f));
     r.color = {VR_MUL(r.voxel_color.x, m), VR_MUL(r.voxel_color.y, m), VR_MUL(r.voxel_color.z, m), VR_MUL(0.0f, m)};
     r.color.w = VR_MUL(r.color.w, 4.0f);
 }
@@ -179,20 +207,33 @@ VR_HD vf3 vr_atlas_fetch(const vr_frame_params &P, float u, float v, int tile_x,
     clamped = (cx != px) || (cy != py);
 #if defined(__CUDA_ARCH__)
     const uchar4 c = tex2D<uchar4>((cudaTextureObject_t)P.atlas_tex, (float)cx + 0.5f, (float)cy + 0.5f);
-    return {VR_DIV((float)c.x, 255.0f), VR_DIV((float)c.y, 255.0f), VR_DIV((float)c.z, 255.0f)};
+    return {VR_DIV_255((float)c.x), VR_DIV_255((float)c.y), VR_DIV_255((float)c.z)};
 #else
     const uint8_t *c = P.atlas + 4 * ((size_t)cx + (size_t)P.atlas_dim[0] * (size_t)cy);
-    return {VR_DIV((float)c[0], 255.0f), VR_DIV((float)c[1], 255.0f), VR_DIV((float)c[2], 255.0f)};
+    return {VR_DIV_255((float)c[0]), VR_DIV_255((float)c[1]), VR_DIV_255((float)c[2])};
 #endif
 }
 
-/* kernel:78-99 */
-VR_HD vf4 vr_view_light(vf3 in_color, float in_w, vf3 light, const float *rgbi, vf3 view, vi3 mask) {
+/* kernel:78-99.  `nlight_out` (optional) receives normalize(light) when it was computed (*nlight_ok): the shadow ray's
+ * direction normalize(-light) (kernel:669) is its exact negation -- a - b = -(b - a), (-x)(-x) = x x and (-x) / l = -(x / l)
+ * hold bit for bit in IEEE arithmetic -- so the caller needs no second square root and three more divisions.
+ * The face normal `mask` is a signed unit axis vector on every ray but the exact-tie ones: normalize() of it is then the
+ * vector itself (1 / sqrt(1) = 1, 0 / 1 = +0). */
+VR_HD vf4 vr_view_light(vf3 in_color, float in_w, vf3 light, const float *rgbi, vf3 view, vi3 mask, vf3 *nlight_out = nullptr,
+                        bool *nlight_ok = nullptr) {
+    if (nlight_ok) *nlight_ok = false;
     if (light.x == 0.0f && light.y == 0.0f && light.z == 0.0f) return {0.0f, 0.0f, 0.0f, 0.0f};
-    float d = VR_MUL(vr_length(light), 0.01f);
+    const float ll = vr_length(light);
+    float d = VR_MUL(ll, 0.01f);
     d = VR_MUL(d, d);
+#if defined(VR_HIT_LITERAL)
     const vf3 nmask = vr_normalize(vr_i2f3(mask));
-    const vf3 nlight = vr_normalize(light);
+#else
+    vf3 nmask = vr_i2f3(mask);
+    if (mask.x * mask.x + mask.y * mask.y + mask.z * mask.z != 1) nmask = vr_normalize(nmask);
+#endif
+    const vf3 nlight = {VR_DIV(light.x, ll), VR_DIV(light.y, ll), VR_DIV(light.z, ll)};
+    if (nlight_out) { *nlight_out = nlight; *nlight_ok = true; }
     const float diffuse = vr_max(vr_dot(nmask, nlight), 0.1f);
     float specular = 0.0f;
     if (diffuse > 0.0f) {
@@ -205,6 +246,14 @@ VR_HD vf4 vr_view_light(vf3 in_color, float in_w, vf3 light, const float *rgbi, 
     o.z = VR_ADD(in_color.z, VR_ADD(VR_MUL(diffuse, rgbi[2]), VR_DIV(VR_MUL(specular, rgbi[2]), d)));
     o.w = VR_ADD(in_w, VR_ADD(VR_MUL(diffuse, rgbi[3]), VR_DIV(VR_MUL(specular, rgbi[3]), d)));
     return o;
+}
+
+/* normalize(L - hit_pos) (kernel:669) from view_light's normalize(hit_pos - L) */
+VR_HD vf3 vr_shadow_dir(vf3 L, vf3 hit_pos, vf3 nlight, bool nlight_ok) {
+#if !defined(VR_HIT_LITERAL)
+    if (nlight_ok) return {-nlight.x, -nlight.y, -nlight.z};
+#endif
+    return vr_normalize(vr_sub3(L, hit_pos));
 }
 
 /* kernel:674-679 / 697-702: restart the DDA from hit_pos along r.ray_dir with the given step. */
@@ -237,12 +286,14 @@ VR_HD bool vr_next_light(const vr_frame_params &P, RayState &r) {
     const vf3 L = {P.light_pos[r.light][0], P.light_pos[r.light][1], P.light_pos[r.light][2]};
     const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
     r.alpha_before = r.color.w;
+    vf3 nlight = {0.0f, 0.0f, 0.0f};
+    bool nlight_ok;
     r.color = vr_view_light({r.color.x, r.color.y, r.color.z}, r.color.w, vr_sub3(r.hit_point, L), P.light_rgbi[r.light],
-                            vr_sub3(r.hit_point, cam), r.hit_normal);
+                            vr_sub3(r.hit_point, cam), r.hit_normal, &nlight, &nlight_ok);
     const int hit_steps = (int)r.fog_distance;
     r.dist = hit_steps;
     r.max_distance = (int)VR_ADD((float)hit_steps, vr_length(vr_sub3(vr_i2f3(r.hit_voxel), L)));
-    r.ray_dir = vr_normalize(vr_sub3(L, r.hit_point));
+    r.ray_dir = vr_shadow_dir(L, r.hit_point, nlight, nlight_ok);
     if (vr_any_zero(r.ray_dir)) return false;
     r.voxel = r.hit_empty;
     r.fm = 0;                                                    /* vr_restart_dda steps back by step * fm: already done */
@@ -301,9 +352,9 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
         bool clamped;
         const vf3 tex = vr_atlas_fetch(P, tu, tv, 5, 0, clamped);
         if (AUX) a->flags |= VR_FL_LIT | (clamped ? VR_FL_ATLAS_CLAMP : 0);
-        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_DIV(tex.x, 2.0f));
-        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_DIV(tex.y, 2.0f));
-        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_DIV(tex.z, 2.0f));
+        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_HALF(tex.x));
+        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_HALF(tex.y));
+        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_HALF(tex.z));
         const vf3 cam = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
         const vi3 nrm = {(r.fm & 1) * r.step.x, ((r.fm >> 1) & 1) * r.step.y, ((r.fm >> 2) & 1) * r.step.z};
         if (MULTI) {
@@ -312,10 +363,12 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
             r.hit_normal = nrm;
             r.hit_empty = {r.voxel.x - nrm.x, r.voxel.y - nrm.y, r.voxel.z - nrm.z};
         }
-        r.color = vr_view_light(r.voxel_color, 0.0f, vr_sub3(hit_pos, L), P.light_rgbi[0], vr_sub3(hit_pos, cam), nrm);
+        vf3 nlight = {0.0f, 0.0f, 0.0f};
+        bool nlight_ok;
+        r.color = vr_view_light(r.voxel_color, 0.0f, vr_sub3(hit_pos, L), P.light_rgbi[0], vr_sub3(hit_pos, cam), nrm, &nlight, &nlight_ok);
         r.fog_distance = (float)r.dist;
         r.max_distance = (int)VR_ADD((float)r.dist, vr_length(vr_sub3(vr_i2f3(r.voxel), L)));   /* kernel:667 */
-        r.ray_dir = vr_normalize(vr_sub3(L, hit_pos));
+        r.ray_dir = vr_shadow_dir(L, hit_pos, nlight, nlight_ok);
         if (vr_any_zero(r.ray_dir)) return VR_ST_SKIP_REDIRECT;          /* kernel:671 */
         vr_restart_dda(r, hit_pos, {vr_sign(r.ray_dir.x), vr_sign(r.ray_dir.y), vr_sign(r.ray_dir.z)});
         return -1;
@@ -324,9 +377,9 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
         bool clamped;
         const vf3 tex = vr_atlas_fetch(P, tu, tv, 3, 4, clamped);
         if (AUX) a->flags |= VR_FL_REFLECTED | (clamped ? VR_FL_ATLAS_CLAMP : 0);
-        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_DIV(tex.x, 4.0f));
-        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_DIV(tex.y, 4.0f));
-        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_DIV(tex.z, 4.0f));
+        r.voxel_color.x = VR_ADD(r.voxel_color.x, VR_QUARTER(tex.x));
+        r.voxel_color.y = VR_ADD(r.voxel_color.y, VR_QUARTER(tex.y));
+        r.voxel_color.z = VR_ADD(r.voxel_color.z, VR_QUARTER(tex.z));
         r.ray_dir = {VR_MUL(r.ray_dir.x, sgn.x), VR_MUL(r.ray_dir.y, sgn.y), VR_MUL(r.ray_dir.z, sgn.z)};
         if (vr_any_zero(r.ray_dir)) return VR_ST_SKIP_REDIRECT;          /* kernel:694 */
         vr_restart_dda(r, hit_pos, {1, 1, 1});                           /* kernel:698 precedence: always +1 */
@@ -340,7 +393,7 @@ VR_HD int vr_hit_block(const vr_frame_params &P, RayState &r, int voxel_data, vr
 
 /* kernel:716-721.  Packs RGBA8 little-endian (R in the low byte). */
 VR_HD uint32_t vr_epilogue(const RayState &r) {
-    const float m = VR_SUB(1.0f, vr_max(VR_DIV(r.fog_distance, 700.0f), 0.0f));
+    const float m = VR_SUB(1.0f, vr_max(VR_DIV_700(r.fog_distance), 0.0f));
     return vr_unorm8(VR_MUL(r.color.x, m)) | (vr_unorm8(VR_MUL(r.color.y, m)) << 8) |
            (vr_unorm8(VR_MUL(r.color.z, m)) << 16) | (vr_unorm8(VR_MUL(r.color.w, m)) << 24);
 }

@@ -56,6 +56,22 @@ VR_HD int vr_grid_shift_for(int root_shift, int dim) {
     return g;
 }
 
+/* Directed top grids (vr_frame_params::grid_directed): edge cap of the empty cube stored per block and direction octant,
+ * and the entry of an empty block from its cube edge e (blocks), the log2 edge `cell` of the aligned empty octree cell
+ * around it and its mirrored block coordinates k (vr_octree.cpp: vr_native_grid_directed; vr_build.cu). */
+#ifndef VR_GRID_MAX_CUBE
+#define VR_GRID_MAX_CUBE 64u
+#endif
+VR_HD uint32_t vr_grid_directed_entry(uint32_t e, int cell, int g, int kx, int ky, int kz) {
+    if (cell > g) {
+        /* the aligned cell reaches the mirrored block (k | cm) on every axis, the cube k + e - 1 */
+        const int cm = (1 << (cell - g)) - 1, c = (int)e - 1;
+        const int rx = (kx | cm) - kx, ry = (ky | cm) - ky, rz = (kz | cm) - kz;
+        if (rx >= c && ry >= c && rz >= c && rx + ry + rz > 3 * c) return (uint32_t)cell;
+    }
+    return (uint32_t)g | (((e - 1u) << g) << 8);
+}
+
 /* Per-pixel auxiliary record (32 bytes), layout-identical to the oracle's vro_aux. */
 typedef struct vr_aux {
     int32_t hit[3];
@@ -127,6 +143,8 @@ typedef struct vr_frame_params {
      * boundary, minus one) -- whichever is wider. */
     const uint32_t *grid;
     int32_t grid_shift, grid_bits, grid_dim;       /* grid_dim = G */
+    int32_t grid_directed;                         /* 1: eight tables, one per direction octant of the ray, table o at
+                                                    * o << (3 * grid_bits) (vr_octree.cpp: vr_native_grid_directed) */
 } vr_frame_params;
 
 #endif
