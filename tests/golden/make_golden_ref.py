@@ -44,3 +44,11 @@ for scene, name in scenes:
                             descriptors=ref.descriptors[used.min():])
     ref.close()
     print(name, "ok")
+
+# the ray table as written by the loop of CLCaster::create_viewport (src/CLCaster.cpp:244-275, compiled from the reference's
+# source by `make -C oracle ref`): a small even-sized and an odd-sized table in full, the 4K table as a strided sample
+if R.viewport_available():
+    t4k = R.create_viewport_table(3840, 2160)
+    np.savez_compressed(out / "viewport-tables.npz", t64x36=R.create_viewport_table(64, 36), t5x7=R.create_viewport_table(5, 7),
+                        t3840x2160_every_60th_row_40th_col=t4k[::60, ::40].copy())
+    print("viewport tables ok")

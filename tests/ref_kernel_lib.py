@@ -139,3 +139,18 @@ def normalize(v) -> np.ndarray:
     out = np.zeros(3, np.float32)
     _olib().ref_normalize(a.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+def viewport_available() -> bool:
+    return (REF_DIR / "libref_viewport.so").exists()
+
+
+def create_viewport_table(width: int, height: int) -> np.ndarray:
+    """The ray table as written by the loop of the reference's CLCaster::create_viewport (src/CLCaster.cpp:244-275, cut out
+    of the source and compiled by `make -C oracle ref`): float32[height, width, 4]."""
+    name = "libref_viewport.so"
+    if name not in _libs:
+        _libs[name] = C.CDLL(str(REF_DIR / name))
+    out = np.zeros((height, width, 4), np.float32)
+    _libs[name].ref_create_viewport_table(C.c_int(width), C.c_int(height), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out

@@ -32,6 +32,16 @@ def test_ray_table_bit_exact(pkg, oracle):
         assert c.create_viewport(w, h, 56.25, 90.0)
         assert np.array_equal(c.read_ray_table().view(np.uint32), oracle.make_ray_table(w, h).view(np.uint32))
         c.close()
+    # and the tables the loop of the reference's own create_viewport wrote (tests/golden/ref/viewport-tables.npz)
+    import pathlib
+
+    z = np.load(pathlib.Path(__file__).parent / "golden" / "ref" / "viewport-tables.npz")
+    for key, (w, h), sl in (("t64x36", (64, 36), (slice(None), slice(None))), ("t5x7", (5, 7), (slice(None), slice(None))),
+                            ("t3840x2160_every_60th_row_40th_col", (3840, 2160), (slice(None, None, 60), slice(None, None, 40)))):
+        c = pkg.CUDACaster()
+        assert c.init(0) and c.create_viewport(w, h, 56.25, 90.0)
+        assert np.array_equal(c.read_ray_table().reshape(h, w, 4)[sl].view(np.uint32), z[key].view(np.uint32)), key
+        c.close()
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -635,7 +645,7 @@ def test_cuda_equals_reference_generated_golden_vectors(pkg):
     from test_oracle import _golden_ref_scene
 
     g = pathlib.Path(__file__).parent / "golden" / "ref"
-    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
+    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz") and not f.name.startswith("viewport-"))
     assert len(frames) >= 16
     for f in frames:
         z = np.load(f)

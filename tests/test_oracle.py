@@ -197,7 +197,7 @@ def test_reference_generated_golden_vectors(pkg, oracle):
     import pathlib
 
     g = pathlib.Path(__file__).parent / "golden" / "ref"
-    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz"))
+    frames = sorted(f for f in g.glob("*.npz") if not f.name.endswith("-octree.npz") and not f.name.startswith("viewport-"))
     assert len(frames) >= 16
     for f in frames:
         z = np.load(f)
@@ -216,3 +216,16 @@ def test_reference_generated_golden_vectors(pkg, oracle):
         first = int(z["first_used"])
         assert root == int(z["root_index"]) and not buf[:first].any(), f.name
         assert np.array_equal(buf[first:], z["descriptors"]), f.name
+
+
+def test_ray_table_equals_reference_generated_viewport_tables(oracle):
+    """tests/golden/ref/viewport-tables.npz holds ray tables written by the loop of the reference's CLCaster::create_viewport
+    (src/CLCaster.cpp:244-275, compiled from the reference's source: oracle/ref_shim/ref_viewport_host.cpp, generated by
+    tests/golden/make_golden_ref.py): the oracle's table equals them bit for bit -- from git alone."""
+    import pathlib
+
+    z = np.load(pathlib.Path(__file__).parent / "golden" / "ref" / "viewport-tables.npz")
+    for key, (w, h) in (("t64x36", (64, 36)), ("t5x7", (5, 7))):
+        assert np.array_equal(oracle.make_ray_table(w, h).view(np.uint32), z[key].view(np.uint32)), key
+    t = oracle.make_ray_table(3840, 2160)[::60, ::40]
+    assert np.array_equal(t.view(np.uint32), z["t3840x2160_every_60th_row_40th_col"].view(np.uint32))

@@ -140,6 +140,20 @@ def test_ray_table_uses_reference_normalize(oracle):
             assert np.array_equal(want.view(np.uint32), np.asarray(got, np.float32).view(np.uint32)), (x, y)
 
 
+@pytest.mark.skipif(not R.viewport_available(), reason="oracle/_ref/libref_viewport.so not built")
+@pytest.mark.parametrize("size", [(64, 36), (50, 50), (1280, 720), (3840, 2160), (5, 7)])
+def test_ray_table_equals_reference_create_viewport_loop(oracle, size):
+    """The loop of CLCaster::create_viewport itself (src/CLCaster.cpp:244-275), cut out of the reference's source and compiled
+    here (oracle/ref_shim/ref_viewport_host.cpp): the oracle's table equals it bit for bit on every ray, including the
+    4K table of the headline workload.  Odd sizes: the reference's loops run over 2 * (n / 2) rows / columns, the last row
+    / column stays as `new sf::Vector4f[]` left it (zero); the oracle restates that too."""
+    w, h = size
+    want = R.create_viewport_table(w, h)
+    got = oracle.make_ray_table(w, h)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert np.isfinite(got).all() and (got[: 2 * (h // 2), : 2 * (w // 2), :3] != 0).any(axis=-1).all()
+
+
 @needs_kernel
 @needs_octree
 @pytest.mark.parametrize("name", ["head", "features", "tiny"])
