@@ -88,17 +88,27 @@ def test_canonical_walk_full_size_c3(pkg, oracle):
     assert c.set_option("walk", 2) and c.compute(), c.last_error()
     rgba, aux = c.draw(), c.read_aux()
     assert c.compute() and np.array_equal(c.draw(), rgba)                 # deterministic
-    # the undirected top grid hands the rays other (smaller) empty cells: not a pixel may change, only the lookup count
+    # the undirected top grid hands the rays other (smaller) empty cells.  Nothing may change but what an exact multi-axis
+    # (tie) step changes: such a step is counted once when it is the last step of a cell and per axis when it falls strictly
+    # inside one (module docstring), so on pixels where either run saw a tie the step count -- and through the fog RGBA8 by
+    # one -- may differ; first hits are the same everywhere
     assert c.set_option("directed_grid", 0) and c.compute(), c.last_error()
-    und_aux = c.read_aux()
-    assert np.array_equal(c.draw(), rgba)
-    for f in INT_FIELDS:
+    und_rgba, und_aux = c.draw(), c.read_aux()
+    tie = ((aux["flags"] | und_aux["flags"]) & 4) != 0
+    d = np.abs(und_rgba.astype(np.int16) - rgba.astype(np.int16)).max(axis=-1)
+    assert (d <= 1).all() and not (d[~tie] > 0).any(), f"directed vs undirected grid: {int((d[~tie] > 0).sum())} non-tie pixels differ"
+    for f in HIT_FIELDS:
         assert np.array_equal(und_aux[f], aux[f]), f
-    print(f"c3 lookups per pixel: directed grids {aux['lookups'].mean():.2f}, undirected grid {und_aux['lookups'].mean():.2f}")
+    for f in INT_FIELDS:
+        assert not (np.any(np.atleast_3d(und_aux[f] != aux[f]), axis=-1) & ~tie).any(), f
+    print(f"c3 lookups per pixel: directed grids {aux['lookups'].mean():.2f}, undirected grid {und_aux['lookups'].mean():.2f}; "
+          f"{int((d > 0).sum())} pixels differ (all on tie rays, by 1)")
     assert aux["lookups"].sum() < 0.7 * und_aux["lookups"].sum()
-    c.close()
     k = 24
-    b_rgba, b_aux, _ = oracle.raycast(scene, row_stride=k, canonical_t=True)
+    ub_rgba, ub_aux, _ = oracle.raycast(scene, row_stride=k, canonical_t=True)
+    assert_equals_oracle_b(ub_rgba[::k], ub_aux[::k], und_rgba[::k], und_aux[::k], "walk 2 c3 rows vs Oracle-B, undirected grid")
+    c.close()
+    b_rgba, b_aux = ub_rgba, ub_aux
     ties = assert_equals_oracle_b(b_rgba[::k], b_aux[::k], rgba[::k], aux[::k], "walk 2 c3 rows vs Oracle-B")
     a_rgba, a_aux, _ = oracle.raycast(scene, row_stride=k, keep_near=True)
     gt1, hit_out, hit_all, deg = north_star_statistic(a_rgba[::k], a_aux[::k], rgba[::k], aux[::k])
