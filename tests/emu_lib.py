@@ -24,6 +24,11 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_collapse(on: bool) -> None:
+    """solid-subtree collapse of every 64-tree the emulation builds (vr_native_collapse_solid): on by default, as in the library"""
+    lib().emu_set_collapse(C.c_int(1 if on else 0))
+
+
 def raycast(scene, ray_table: np.ndarray, bias=(0, 0, 0), use_svo: bool = False, max_distance: int | None = None,
             shadow_lights: int = 1):
     w, h = scene.width, scene.height

@@ -18,6 +18,10 @@ struct LocalStack {
     uint32_t get(int l) const { return v[l]; }
 };
 
+/* solid-subtree collapse (vr_octree.cpp: vr_native_collapse_solid) applied to every tree built below: 0 / 1 */
+static int g_collapse = 1;
+extern "C" void emu_set_collapse(int on) { g_collapse = on; }
+
 extern "C" int emu_raycast(int width, int height, const float *ray_table, const int8_t *map, int n,
                            const float *cam_pos, const float *cam_dir, const int32_t *bias, const float *lights,
                            const uint8_t *atlas, int atlas_w, int atlas_h, int tile_w, int tile_h, int max_distance,
@@ -43,6 +47,7 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
     P.max_bounces = 2;
     if (use_svo) {
         if (!vr_native_from_dense(map, n, tree)) return -1;
+        if (g_collapse) vr_native_collapse_solid(tree);
         P.nodes = tree.nodes.data(); P.leaf_types = tree.leaf_types.data();
         P.levels = tree.levels; P.root_shift = 2 * (tree.levels - 1);
     }
@@ -92,12 +97,14 @@ static long emu_export(const vr_native_tree &t, void *nodes, long cap_nodes, uin
 extern "C" long emu_tree_from_dense(const int8_t *map, int n, void *nodes, long cap_nodes, uint8_t *types, long cap_types, long *ntypes, int *levels) {
     vr_native_tree t;
     if (!vr_native_from_dense(map, n, t)) return -1;
+    if (g_collapse) vr_native_collapse_solid(t);
     return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
 }
 
 extern "C" long emu_tree_from_columns(const int32_t *lo, const int32_t *hi, int n, int type, void *nodes, long cap_nodes, uint8_t *types, long cap_types, long *ntypes, int *levels) {
     vr_native_tree t;
     if (!vr_native_from_columns(lo, hi, n, (uint8_t)type, t)) return -1;
+    if (g_collapse) vr_native_collapse_solid(t);
     return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
 }
 
@@ -151,5 +158,6 @@ extern "C" long emu_tree_from_ref(const uint64_t *desc, uint64_t len, uint64_t r
                                   long cap_types, long *ntypes, int *levels) {
     vr_native_tree t;
     if (!vr_native_from_ref(desc, len, root, dim, nullptr, t)) return -1;
+    if (g_collapse) vr_native_collapse_solid(t);
     return emu_export(t, nodes, cap_nodes, types, cap_types, ntypes, levels);
 }

@@ -148,3 +148,115 @@ def test_division_by_constants_is_the_ieee_quotient():
     fn = emu_lib.lib().emu_div_const_mismatches
     fn.restype = C.c_long
     assert fn() == 0
+
+
+def _solid_volumes(pkg):
+    S = pkg.scene
+    rng = np.random.default_rng(12)
+    out = {"solid64": S.terrain_map(64, "solid"), "solid128-mirrors": S.terrain_map(128, "solid", reflect_fraction=0.002)}
+    v = np.zeros((32, 32, 32), np.int8)
+    v[:17] = 5
+    v[17:21, 8:24, 8:24] = 6                       # a slab of the other type on top: solid nodes of both types
+    out["half32-two-types"] = v
+    out["full16"] = np.full((16, 16, 16), 5, np.int8)      # the root itself collapses
+    v = S.terrain_map(64, "solid").copy()
+    holes = rng.random(v.shape) < 0.01
+    v[holes & (v != 0)] = 0                        # 1 % holes: only some bricks stay solid
+    out["solid64-holes"] = v
+    return out
+
+
+@pytest.mark.parametrize("kind", ["solid64", "solid128-mirrors", "half32-two-types", "full16", "solid64-holes"])
+def test_solid_collapse_structure(pkg, kind):
+    """vr_native_collapse_solid (VR_NODE_SOLID): the collapsed tree answers every point query like the uncollapsed one,
+    is smaller, keeps BFS order (children of a node contiguous, levels in order) and holds no node below a solid node."""
+    vol = _solid_volumes(pkg)[kind]
+    n = vol.shape[0]
+    emu_lib.set_collapse(False)
+    nodes0, types0, levels0 = emu_lib.tree_from_dense(vol)
+    emu_lib.set_collapse(True)
+    nodes, types, levels = emu_lib.tree_from_dense(vol)
+    assert levels == levels0 and len(nodes) <= len(nodes0) and len(types) < len(types0)
+    SOLID = 0x80000000
+    mask = nodes[:, 0].astype(np.uint64) | (nodes[:, 1].astype(np.uint64) << np.uint64(32))
+    base = nodes[:, 2]
+    solid = (base & SOLID) != 0
+    assert solid.any() and (mask[solid] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and np.isin(base[solid] & 0xFF, (5, 6)).all()
+    # walk the levels: children of non-solid inner nodes are contiguous and consecutive across the level (BFS order)
+    lo, hi = 0, 1
+    for l in range(levels):
+        leaf = l == levels - 1
+        nxt = hi
+        for i in range(lo, hi):
+            if solid[i]:
+                continue
+            pc = bin(int(mask[i])).count("1")
+            if leaf:
+                assert int(base[i]) + pc <= len(types)
+            elif pc:
+                assert int(base[i]) == nxt
+                nxt += pc
+        lo, hi = hi, nxt
+        if lo == hi:
+            break
+    assert hi == len(nodes) or lo == hi
+
+    def query(nd, ty, x, y, z):
+        idx, s = 0, 2 * (levels - 1)
+        while True:
+            m = int(nd[idx, 0]) | (int(nd[idx, 1]) << 32)
+            b = int(nd[idx, 2])
+            if b & SOLID:
+                return b & 0xFF
+            ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4)
+            if not (m >> ci) & 1:
+                return 0
+            rank = bin(m & ((1 << ci) - 1)).count("1")
+            if s == 0:
+                return int(ty[b + rank])
+            idx, s = b + rank, s - 2
+
+    rng = np.random.default_rng(3)
+    for x, y, z in rng.integers(0, n, size=(3000, 3)):
+        want = int(vol[z, y, x])
+        x, y, z = int(x), int(y), int(z)
+        assert query(nodes, types, x, y, z) == want == query(nodes0, types0, x, y, z), (kind, x, y, z)
+
+
+@pytest.mark.parametrize("kind", ["solid64", "solid128-mirrors", "half32-two-types", "solid64-holes"])
+def test_all_walks_over_collapsed_trees(pkg, oracle, kind):
+    """Every octree walk of the device core (host build) over a tree with collapsed solid subtrees: walk 0 == the oracle's
+    dense DDA on every pixel, walk 1 except ties, the closed-form walk == Oracle-B over both kinds of top grid -- and the
+    frames equal those over the uncollapsed tree."""
+    from test_emu_parity import assert_walk_matches
+
+    S = pkg.scene
+    vol = _solid_volumes(pkg)[kind]
+    n = vol.shape[0]
+    if kind.startswith("solid"):
+        cams = [S.make_camera(n, S.heightfield(n), 3)]
+    else:
+        h = np.full((n, n), 16, np.int32)
+        h[8:24, 8:24] = 20
+        cams = [S.make_camera(n, h, 1), S.make_camera(n, h, 2)]      # one looks at the mirror slab, one at the ground
+    seen = 0.0
+    for pos, direction in cams:
+        scene = S.Scene(n, vol, 256, 144, pos, direction, S.make_lights(n, 2), max_distance=3 * n)
+        table = oracle.make_ray_table(scene.width, scene.height)
+        a_rgba, a_aux, _ = oracle.raycast(scene, table, shadow_lights=2)
+        b_rgba, b_aux, _ = oracle.raycast(scene, table, shadow_lights=2, canonical_t=True)
+        frames = {}
+        for collapse in (True, False):
+            emu_lib.set_collapse(collapse)
+            for use_svo in (1, 2, 3, 4):
+                rgba, aux = emu_lib.raycast(scene, table, use_svo=use_svo, shadow_lights=2)
+                if use_svo <= 2:
+                    assert_walk_matches(a_rgba, a_aux, rgba, aux, use_svo == 2, f"{kind} collapse={collapse} svo={use_svo}")
+                else:
+                    assert_equals_oracle_b(b_rgba, b_aux, rgba, aux, f"{kind} collapse={collapse} svo={use_svo}")
+                frames[(collapse, use_svo)] = rgba
+        emu_lib.set_collapse(True)
+        for use_svo in (1, 2, 3, 4):
+            assert np.array_equal(frames[(True, use_svo)], frames[(False, use_svo)]), use_svo
+        seen = max(seen, float(((a_aux["flags"] & 3) != 0).mean()))
+    assert seen > 0.3                                     # not mostly sky: lit or reflected hits

@@ -314,6 +314,7 @@ __global__ void vr_grid_classify(const vr_node *nodes, int root_shift, int g, in
     uint8_t cs_out = 0;
     for (int s = root_shift;; s -= 2) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nodes) + idx);
+        if (v.z & VR_NODE_SOLID) { entry = 0x80000000u | idx; break; }                   /* the block lies in a solid node */
         const unsigned long long m = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
         const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
         if (!((m >> ci) & 1ull)) {

@@ -162,6 +162,7 @@ VR_HD int vr_canon_lookup(const vr_frame_params &P, vr_cray<Stack> &q, int xr, v
     }
     const uint32_t cf = q.flip;
     for (;;) {
+        if (q.node.base & VR_NODE_SOLID) return (int)(int8_t)(q.node.base & 0xffu);      /* a collapsed solid subtree: p is a set voxel */
         const int s = q.s;
         const uint32_t ci = ((uint32_t)((q.px >> s) & 3) | ((uint32_t)((q.py >> s) & 3) << 2) | ((uint32_t)((q.pz >> s) & 3) << 4)) ^ cf;
         if (!((uint32_t)(q.node.mask >> ci) & 1u)) {
@@ -270,6 +271,7 @@ VR_HD int vr_tree_voxel(const vr_frame_params &P, int x, int y, int z) {
     uint32_t idx = 0;
     for (int s = P.root_shift;; s -= 2) {
         const vr_node_regs nd = vr_load_node(P, idx);
+        if (nd.base & VR_NODE_SOLID) return (int)(int8_t)(nd.base & 0xffu);
         const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
         if (!((nd.mask >> ci) & 1ull)) return 0;
         const uint32_t rank = (uint32_t)VR_POPC64(nd.mask & ((1ull << ci) - 1ull));

@@ -39,6 +39,7 @@ __device__ __forceinline__ void tile_xy(int tid, int &lx, int &ly) {
 
 /* local slab row -> frame row (multi-GPU row-band interleave, see vr_types.h) */
 __device__ __forceinline__ int frame_row(const vr_frame_params &P, int ly) {
+    if (P.band_stride == 1) return ly + P.band_first * P.band_rows;      /* one rank: no integer division per thread */
     const int lb = ly / P.band_rows;
     return (lb * P.band_stride + P.band_first) * P.band_rows + (ly - lb * P.band_rows);
 }

@@ -402,11 +402,84 @@ bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8
     return true;
 }
 
+size_t vr_native_collapse_solid(vr_native_tree &t) {
+    const size_t n = t.nodes.size();
+    const int L = t.levels;
+    if (L < 1 || n == 0) return 0;
+    auto mask_of = [&](size_t i) { return (uint64_t)t.nodes[i].mask_lo | ((uint64_t)t.nodes[i].mask_hi << 32); };
+    /* level l = nodes [start[l], start[l + 1]) */
+    std::vector<size_t> start((size_t)L + 1, 0);
+    start[1] = 1;
+    for (int l = 0; l + 1 < L; l++) {
+        size_t kids = 0;
+        for (size_t i = start[l]; i < start[l + 1]; i++) kids += (size_t)__builtin_popcountll(mask_of(i));
+        start[l + 2] = start[l + 1] + kids;
+    }
+    if (start[L] != n) return 0;                                  /* not a complete BFS tree (already collapsed?): leave it */
+    /* (1) bottom-up: type of the node's cube if it is solid, else -1 */
+    std::vector<int16_t> st(n, -1);
+    size_t solid = 0;
+    for (size_t i = start[L - 1]; i < start[L]; i++) {
+        if (mask_of(i) != ~0ull) continue;
+        const uint8_t *ty = t.leaf_types.data() + t.nodes[i].child_base;
+        bool same = true;
+        for (int k = 1; k < 64 && same; k++) same = ty[k] == ty[0];
+        if (same) { st[i] = ty[0]; solid++; }
+    }
+    for (int l = L - 2; l >= 0; l--)
+        for (size_t i = start[l]; i < start[l + 1]; i++) {
+            if (mask_of(i) != ~0ull) continue;
+            const size_t c = t.nodes[i].child_base;
+            bool same = st[c] >= 0;
+            for (int k = 1; k < 64 && same; k++) same = st[c + k] == st[c];
+            if (same) { st[i] = st[c]; solid++; }
+        }
+    if (!solid) return 0;
+    /* (2) top-down: a node is kept unless its parent is solid (or was dropped itself) */
+    std::vector<uint8_t> keep(n, 0);
+    keep[0] = 1;
+    for (int l = 0; l + 1 < L; l++)
+        for (size_t i = start[l]; i < start[l + 1]; i++) {
+            const int pc = __builtin_popcountll(mask_of(i));
+            const uint8_t k = keep[i] && st[i] < 0;
+            for (int j = 0; j < pc; j++) keep[t.nodes[i].child_base + (size_t)j] = k;
+        }
+    /* (3) re-pack in the same order */
+    std::vector<uint32_t> at(n, 0);
+    uint32_t cnt = 0;
+    for (size_t i = 0; i < n; i++) { at[i] = cnt; cnt += keep[i]; }
+    std::vector<vr_node> nodes;
+    std::vector<uint8_t> types;
+    nodes.reserve(cnt);
+    for (int l = 0; l < L; l++)
+        for (size_t i = start[l]; i < start[l + 1]; i++) {
+            if (!keep[i]) continue;
+            vr_node v = t.nodes[i];
+            if (st[i] >= 0) {
+                v.child_base = VR_NODE_SOLID | (uint32_t)(uint8_t)st[i];
+            } else if (l == L - 1) {
+                const int pc = __builtin_popcountll(mask_of(i));
+                const uint8_t *ty = t.leaf_types.data() + t.nodes[i].child_base;
+                v.child_base = (uint32_t)types.size();
+                types.insert(types.end(), ty, ty + pc);
+            } else if (mask_of(i)) {
+                v.child_base = at[t.nodes[i].child_base];
+            }
+            nodes.push_back(v);
+        }
+    if (types.empty()) types.push_back(0);
+    const size_t removed = n - nodes.size();
+    t.nodes.swap(nodes);
+    t.leaf_types.swap(types);
+    return removed;
+}
+
 int vr_native_query(const vr_native_tree &t, int x, int y, int z, int *cell_shift) {
     int s = 2 * (t.levels - 1);
     uint32_t idx = 0;
     for (;;) {
         const vr_node &n = t.nodes[idx];
+        if (n.child_base & VR_NODE_SOLID) { if (cell_shift) *cell_shift = 0; return (int)(int8_t)(n.child_base & 0xffu); }
         const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
         const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
         if (!((m >> ci) & 1ull)) { if (cell_shift) *cell_shift = s; return 0; }
@@ -438,6 +511,7 @@ static bool grid_classify(const vr_node *nodes, int levels, int dim, std::vector
                 uint32_t idx = 0, entry = 0;
                 for (int s = root_shift;; s -= 2) {
                     const vr_node &n = nodes[idx];
+                    if (n.child_base & VR_NODE_SOLID) { entry = 0x80000000u | idx; break; }     /* the block lies in a solid node */
                     const unsigned long long m = (unsigned long long)n.mask_lo | ((unsigned long long)n.mask_hi << 32);
                     const int ci = ((x >> s) & 3) | (((y >> s) & 3) << 2) | (((z >> s) & 3) << 4);
                     if (!((m >> ci) & 1ull)) {

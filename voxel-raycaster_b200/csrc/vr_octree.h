@@ -49,6 +49,12 @@ bool vr_native_from_ref(const uint64_t *desc, uint64_t len, uint64_t root_index,
  * value `type`.  Produces exactly the arrays vr_native_from_dense gives for the equivalent dense map. */
 bool vr_native_from_columns(const int32_t *lo, const int32_t *hi, int dim, uint8_t type, vr_native_tree &out);
 
+/* Solid-subtree collapse (vr_types.h: VR_NODE_SOLID), applied to a tree in BFS order by every producer above: bottom-up,
+ * a leaf brick of 64 set voxels of one type and an inner node whose 64 children are solid nodes of one type become solid
+ * nodes; the nodes and voxel types below a solid node are dropped and the arrays re-packed in the same BFS order.
+ * Returns the number of nodes removed.  (Device version: vr_build.cu: vr_collapse_solid_device.) */
+size_t vr_native_collapse_solid(vr_native_tree &t);
+
 /* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree: host version (the caster builds
  * it on the device, vr_build.cu: vr_build_grid_device; this one serves the host emulation and checks that one).
  * Returns false when the tree is too shallow for a grid (a single level: maps up to 4^3). */

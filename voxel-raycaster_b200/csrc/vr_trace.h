@@ -924,6 +924,10 @@ VR_HD int vr_svo_cell(const vr_frame_params &P, vr_svo_ray<Stack> &q, vr_aux *a)
         }
         q.nv = r.voxel;
         for (;;) {
+            if (q.node.base & VR_NODE_SOLID) {                           /* a collapsed solid subtree: a set voxel of its type */
+                voxel_data = (int)(int8_t)(q.node.base & 0xffu);
+                break;
+            }
             const int s = q.s;
             const int ci = ((r.voxel.x >> s) & 3) | (((r.voxel.y >> s) & 3) << 2) | (((r.voxel.z >> s) & 3) << 4);
             if (!((q.node.mask >> ci) & 1ull)) {                         /* empty slot: cache the cell */

@@ -23,7 +23,12 @@
  *           nodes[child_base + popcount(mask & ((1<<ci)-1))].
  *   s == 0: children are voxels; voxel type at leaf_types[child_base + popcount(...)].
  * Two levels of the reference's 2^3 / 8-byte child descriptors (kernel:49-54, Octree.h:89-94)
- * collapse into one node: same bytes per level, half the dependent loads. */
+ * collapse into one node: same bytes per level, half the dependent loads.
+ * SOLID nodes (the reference collapses empty subtrees only, src/map/Octree.cpp:230-233; SURVEY 8f-1 asks for both): a
+ * node whose whole cube is set voxels of ONE type is stored as a single node without children at whatever level it
+ * sits: mask = ~0, child_base = VR_NODE_SOLID | type -- no nodes below it, no leaf_types entries.  A lookup that loads
+ * such a node has found a set voxel of that type. */
+#define VR_NODE_SOLID 0x80000000u
 typedef struct vr_node {
     uint32_t mask_lo;
     uint32_t mask_hi;
