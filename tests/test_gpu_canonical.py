@@ -266,3 +266,83 @@ def test_bounce_limit_setting(pkg, oracle, limit):
             assert c.set_option("walk", 2) and c.compute()
             assert_equals_oracle_b(b_rgba, b_aux, c.draw(), c.read_aux(), f"limit {limit} walk 2")
         c.close()
+
+
+@pytest.mark.parametrize("kind", ["solid256", "solid128-mirrors", "half32-two-types"])
+def test_solid_subtree_collapse(pkg, oracle, kind, tmp_path):
+    """Solid-subtree collapse (VR_NODE_SOLID; the reference collapses empty subtrees only, src/map/Octree.cpp:230-233):
+    trees built on the device and on the host are the same arrays, far smaller than the uncollapsed tree on solid maps;
+    every walk renders through them what it renders through the uncollapsed tree and what the oracle's dense DDA does;
+    the file format carries solid nodes (version 2) and the loader validates them."""
+    from conftest import assert_same_frame
+    from test_gpu_parity import _device_tree
+
+    S = pkg.scene
+    if kind == "solid256":
+        vol = S.terrain_map(256, "solid")
+        h = S.heightfield(256)
+    elif kind == "solid128-mirrors":
+        vol = S.terrain_map(128, "solid", reflect_fraction=0.002)
+        h = S.heightfield(128)
+    else:
+        vol = np.zeros((32, 32, 32), np.int8)
+        vol[:17] = 5
+        vol[17:21, 8:24, 8:24] = 6
+        h = np.full((32, 32), 16, np.int32)
+        h[8:24, 8:24] = 20
+    n = vol.shape[0]
+    g_nodes, g_types, g_levels, g_dim, g_st = _device_tree(pkg, vol, True)
+    h_nodes, h_types, h_levels, h_dim, h_st = _device_tree(pkg, vol, False)
+    assert g_levels == h_levels and np.array_equal(g_nodes, h_nodes) and np.array_equal(g_types, h_types)
+    solid_nodes = int(((g_nodes[:, 2] & 0x80000000) != 0).sum())
+    assert solid_nodes > 0
+    pos, direction = S.make_camera(n, h, 2 if kind.startswith("half") else 3)
+    scene = S.Scene(n, vol, 480, 270, pos, direction, S.make_lights(n, 2), max_distance=3 * n)
+    a_rgba, a_aux, _ = oracle.raycast(scene, shadow_lights=2)
+    b_rgba, b_aux, _ = oracle.raycast(scene, shadow_lights=2, canonical_t=True)
+    frames = {}
+    sizes = {}
+    for collapse in (1, 0):
+        c = pkg.CUDACaster()
+        c.load_scene(scene, use_octree=True, assign_octree=False, shadow_lights=2, collapse_solid=bool(collapse))
+        assert c.enable_aux(True)
+        sizes[collapse] = c.stats().native_bytes
+        assert c.set_option("walk", 0) and c.compute(), c.last_error()
+        assert_same_frame(a_rgba, a_aux, c.draw(), c.read_aux(), f"{kind} collapse={collapse} walk 0")
+        frames[(collapse, 0)] = c.draw().copy()
+        assert c.set_option("walk", 1) and c.compute()
+        assert_equals_oracle_b(a_rgba, a_aux, c.draw(), c.read_aux(), f"{kind} collapse={collapse} walk 1")
+        frames[(collapse, 1)] = c.draw().copy()
+        for directed in (1, 0):
+            assert c.set_option("walk", 2) and c.set_option("directed_grid", directed) and c.compute()
+            assert_equals_oracle_b(b_rgba, b_aux, c.draw(), c.read_aux(), f"{kind} collapse={collapse} walk 2 directed={directed}")
+            frames[(collapse, 2 + directed)] = c.draw().copy()
+        if collapse:
+            path = tmp_path / "solid.vr64"
+            assert c.octree_save(str(path))
+            assert int.from_bytes(path.read_bytes()[4:8], "little") == 2
+            d = pkg.CUDACaster()
+            assert d.init(0)
+            assert d.add_to_settings_buffer("octree_dimensions", "OCTDIM", n) and d.add_to_settings_buffer("using_octree", "OCTENABLED", 0)
+            assert d.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance) and d.add_to_settings_buffer("light_count", "LIGHT_COUNT", 2)
+            assert d.octree_load(str(path)), d.last_error()
+            assert d.stats().native_bytes == sizes[1]
+            assert d.assign_camera(scene.cam_dir, scene.cam_pos) and d.create_viewport(scene.width, scene.height)
+            assert d.assign_lights(scene.lights) and d.create_texture_atlas(scene.atlas) and d.validate(), d.last_error()
+            assert d.set_option("walk", 0) and d.compute() and np.array_equal(d.draw(), frames[(1, 0)])
+            # a solid node whose type is not a voxel type, and one in a version-1 file, must be rejected
+            raw = bytearray(path.read_bytes())
+            first = 32 + 16 * int(np.flatnonzero((g_nodes[:, 2] & 0x80000000) != 0)[0])
+            bad = tmp_path / "bad_type.vr64"
+            raw2 = bytearray(raw); raw2[first + 8] = 9
+            bad.write_bytes(bytes(raw2))
+            assert not d.octree_load(str(bad))
+            raw3 = bytearray(raw); raw3[4] = 1
+            bad.write_bytes(bytes(raw3))
+            assert not d.octree_load(str(bad))
+            d.close()
+        c.close()
+    for w in range(4):
+        assert np.array_equal(frames[(1, w)], frames[(0, w)]), w
+    print(f"{kind}: {g_nodes.shape[0]} nodes ({solid_nodes} solid), {g_types.shape[0]} voxel types: {sizes[1]} bytes against {sizes[0]} uncollapsed")
+    assert sizes[1] < (0.5 if kind != "solid128-mirrors" else 0.9) * sizes[0]

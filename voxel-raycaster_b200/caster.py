@@ -449,7 +449,7 @@ class CUDACaster:
 
     # -- convenience: the reference's init order (ref src/Application.cpp:27-88) -----------------
     def load_scene(self, scene, use_octree: bool, assign_octree: bool = True, device: int = 0, shadow_lights: int = 1,
-                   walk: int | None = None, gpu_build: bool | None = None) -> None:
+                   walk: int | None = None, gpu_build: bool | None = None, collapse_solid: bool | None = None) -> None:
         def must(ok: bool, what: str) -> None:
             if not ok:
                 raise RuntimeError(f"{what} failed: {self.last_error()}")
@@ -457,6 +457,8 @@ class CUDACaster:
         must(self.init(device), "init")
         if gpu_build is not None:  # None = the library default (the 64-tree is built on the device)
             must(self.set_option("gpu_build", 1 if gpu_build else 0), "set_option gpu_build")
+        if collapse_solid is not None:  # None = the library default (solid subtrees of the 64-tree become single nodes)
+            must(self.set_option("collapse_solid", 1 if collapse_solid else 0), "set_option collapse_solid")
         must(self.add_to_settings_buffer("octree_dimensions", "OCTDIM", scene.n), "add OCTDIM")
         must(self.add_to_settings_buffer("using_octree", "OCTENABLED", 0 if use_octree else 1), "add OCTENABLED")
         must(self.add_to_settings_buffer("max_distance", "MAX_DISTANCE", scene.max_distance), "add MAX_DISTANCE")

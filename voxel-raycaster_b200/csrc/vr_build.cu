@@ -113,6 +113,9 @@ vr_reduce_masks(const unsigned long long *__restrict__ child, unsigned long long
 struct NonZero {
     __host__ __device__ uint32_t operator()(unsigned long long m) const { return m != 0ull ? 1u : 0u; }
 };
+struct IsSolidFlag {
+    __host__ __device__ uint32_t operator()(uint8_t v) const { return v != 0xFF ? 1u : 0u; }
+};
 struct PopCount {
     __host__ __device__ uint32_t operator()(unsigned long long m) const {
 #if defined(__CUDA_ARCH__)
@@ -445,6 +448,181 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, bo
     *grid_out = grid;
     *grid_shift = g;
     *grid_bits = bits;
+    return cudaSuccess;
+}
+
+/* ---- solid-subtree collapse on the device (vr_types.h: VR_NODE_SOLID; host version vr_octree.cpp:
+ * vr_native_collapse_solid, which this reproduces array for array) --------------------------------------------------
+ * Input: a complete tree in BFS order as the two builders emit it.  (1) bottom-up, per level: the type of a node's cube
+ * if it is solid (leaf: 64 set voxels of one type; inner: 64 solid children of one type), else 0xFF; (2) top-down: a node
+ * is kept unless its parent is solid or was dropped; (3) exclusive scans of "kept" and of the voxel types kept leaves
+ * still need; (4) re-pack in the same order. */
+namespace {
+
+__global__ void vr_solid_leaves(const vr_node *__restrict__ nodes, const uint8_t *__restrict__ types, unsigned lo, unsigned hi, uint8_t *__restrict__ st) {
+    const unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint4 v = reinterpret_cast<const uint4 *>(nodes)[i];
+    uint8_t r = 0xFF;
+    if ((v.x & v.y) == 0xFFFFFFFFu) {
+        const uint8_t *ty = types + v.z;
+        r = ty[0];
+        for (int k = 1; k < 64; k++)
+            if (ty[k] != r) { r = 0xFF; break; }
+    }
+    st[i] = r;
+}
+
+__global__ void vr_solid_inner(const vr_node *__restrict__ nodes, unsigned lo, unsigned hi, uint8_t *st) {
+    const unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint4 v = reinterpret_cast<const uint4 *>(nodes)[i];
+    uint8_t r = 0xFF;
+    if ((v.x & v.y) == 0xFFFFFFFFu) {
+        r = st[v.z];
+        for (int k = 1; k < 64 && r != 0xFF; k++)
+            if (st[v.z + k] != r) r = 0xFF;
+    }
+    st[i] = r;
+}
+
+__global__ void vr_solid_keep(const vr_node *__restrict__ nodes, const uint8_t *__restrict__ st, unsigned lo, unsigned hi, uint32_t *keep) {
+    const unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint4 v = reinterpret_cast<const uint4 *>(nodes)[i];
+    const uint32_t k = (keep[i] && st[i] == 0xFF) ? 1u : 0u;
+    const int pc = __popc(v.x) + __popc(v.y);
+    for (int j = 0; j < pc; j++) keep[v.z + j] = k;
+}
+
+/* voxel types a node still needs after the collapse: those of a kept leaf that is not solid */
+__global__ void vr_solid_type_counts(const vr_node *__restrict__ nodes, const uint8_t *__restrict__ st, const uint32_t *__restrict__ keep, unsigned leaf_lo,
+                                     unsigned n, uint32_t *__restrict__ cnt) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = 0;
+    if (i >= leaf_lo && keep[i] && st[i] == 0xFF) {
+        const uint4 v = reinterpret_cast<const uint4 *>(nodes)[i];
+        c = (uint32_t)(__popc(v.x) + __popc(v.y));
+    }
+    cnt[i] = c;
+}
+
+__global__ void vr_solid_emit(const vr_node *__restrict__ nodes, const uint8_t *__restrict__ types, const uint8_t *__restrict__ st,
+                              const uint32_t *__restrict__ keep, const uint32_t *__restrict__ at, const uint32_t *__restrict__ tat, unsigned leaf_lo,
+                              unsigned n, vr_node *__restrict__ out_nodes, uint8_t *__restrict__ out_types) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    uint4 v = reinterpret_cast<const uint4 *>(nodes)[i];
+    if (st[i] != 0xFF) {
+        v.z = VR_NODE_SOLID | (uint32_t)st[i];
+    } else if (i >= leaf_lo) {
+        const int pc = __popc(v.x) + __popc(v.y);
+        const uint8_t *src = types + v.z;
+        uint8_t *dst = out_types + tat[i];
+        for (int j = 0; j < pc; j++) dst[j] = src[j];
+        v.z = tat[i];
+    } else if (v.x | v.y) {
+        v.z = at[v.z];
+    }
+    reinterpret_cast<uint4 *>(out_nodes)[at[i]] = v;
+}
+
+}  // namespace
+
+cudaError_t vr_collapse_solid_device(vr_device_tree *t, cudaStream_t stream, unsigned long long *launches) {
+    if (!t || !t->nodes || t->levels < 1 || t->n_nodes < 1 || t->n_nodes >= (1ull << 31)) return cudaErrorInvalidValue;
+    const int L = t->levels;
+    const unsigned n = (unsigned)t->n_nodes;
+    /* level l = nodes [start[l], start[l + 1]): the children of the first node of an inner level open the next one */
+    unsigned start[VR_MAX_LEVELS + 1] = {0};
+    start[1] = 1;
+    for (int l = 1; l < L; l++) {
+        if (l == L - 1) { start[l + 1] = n; break; }
+        if (start[l] >= n) { start[l + 1] = n; continue; }
+        vr_node first;
+        cudaError_t e = cudaMemcpyAsync(&first, t->nodes + start[l], sizeof(vr_node), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        start[l + 1] = first.child_base;
+        if (start[l + 1] < start[l] || start[l + 1] > n) return cudaErrorInvalidValue;
+    }
+    if (L == 1) start[1] = n;
+    if (start[L] != n) return cudaErrorInvalidValue;
+    const unsigned leaf_lo = start[L - 1];
+
+    uint8_t *st = nullptr, *types = nullptr;
+    uint32_t *keep = nullptr, *at = nullptr, *cnt = nullptr, *tat = nullptr, *d_solid = nullptr;
+    vr_node *nodes = nullptr;
+    void *tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(st); cudaFree(keep); cudaFree(at); cudaFree(cnt); cudaFree(tat); cudaFree(d_solid); cudaFree(tmp); };
+    auto fail_out = [&]() { cudaFree(nodes); cudaFree(types); };
+    VRB(cudaMalloc(&st, n));
+    VRB(cudaMalloc(&keep, (size_t)(n + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&at, (size_t)(n + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&cnt, (size_t)(n + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&tat, (size_t)(n + 1) * sizeof(uint32_t)));
+    VRB(cudaMalloc(&d_solid, sizeof(uint32_t)));
+    size_t tmp_bytes = 0, b = 0;
+    VRB(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep, at, (int)(n + 1), stream));
+    {
+        auto it = thrust::make_transform_iterator((const uint8_t *)st, IsSolidFlag());
+        VRB(cub::DeviceReduce::Sum(nullptr, b, it, d_solid, (int)n, stream));
+        if (b > tmp_bytes) tmp_bytes = b;
+    }
+    VRB(cudaMalloc(&tmp, tmp_bytes));
+    /* (1) */
+    vr_solid_leaves<<<(n - leaf_lo + 255) / 256, 256, 0, stream>>>(t->nodes, t->types, leaf_lo, n, st);
+    for (int l = L - 2; l >= 0; l--)
+        if (start[l + 1] > start[l]) vr_solid_inner<<<(start[l + 1] - start[l] + 255) / 256, 256, 0, stream>>>(t->nodes, start[l], start[l + 1], st);
+    uint32_t solid = 0;
+    {
+        auto it = thrust::make_transform_iterator((const uint8_t *)st, IsSolidFlag());
+        b = tmp_bytes;
+        VRB(cub::DeviceReduce::Sum(tmp, b, it, d_solid, (int)n, stream));
+        VRB(cudaMemcpyAsync(&solid, d_solid, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        VRB(cudaStreamSynchronize(stream));
+    }
+    if (launches) *launches += (unsigned long long)L;
+    if (!solid) { cleanup(); return cudaSuccess; }                       /* nothing to collapse: the tree stays as it is */
+    /* (2) */
+    VRB(cudaMemsetAsync(keep, 0, (size_t)(n + 1) * sizeof(uint32_t), stream));
+    {
+        const uint32_t one = 1;
+        VRB(cudaMemcpyAsync(keep, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
+    for (int l = 0; l + 1 < L; l++)
+        if (start[l + 1] > start[l]) vr_solid_keep<<<(start[l + 1] - start[l] + 255) / 256, 256, 0, stream>>>(t->nodes, st, start[l], start[l + 1], keep);
+    /* (3) */
+    b = tmp_bytes;
+    VRB(cub::DeviceScan::ExclusiveSum(tmp, b, keep, at, (int)(n + 1), stream));
+    VRB(cudaMemsetAsync(cnt + n, 0, sizeof(uint32_t), stream));
+    vr_solid_type_counts<<<(n + 255) / 256, 256, 0, stream>>>(t->nodes, st, keep, leaf_lo, n, cnt);
+    b = tmp_bytes;
+    VRB(cub::DeviceScan::ExclusiveSum(tmp, b, cnt, tat, (int)(n + 1), stream));
+    uint32_t kept = 0, ntypes = 0;
+    VRB(cudaMemcpyAsync(&kept, at + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VRB(cudaMemcpyAsync(&ntypes, tat + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    VRB(cudaStreamSynchronize(stream));
+    /* (4) */
+    {
+        cudaError_t e = cudaMalloc(&nodes, (size_t)kept * sizeof(vr_node));
+        if (e == cudaSuccess) e = cudaMalloc(&types, ntypes ? ntypes : 1);
+        if (e == cudaSuccess && !ntypes) e = cudaMemsetAsync(types, 0, 1, stream);
+        if (e != cudaSuccess) { fail_out(); cleanup(); return e; }
+    }
+    vr_solid_emit<<<(n + 255) / 256, 256, 0, stream>>>(t->nodes, t->types, st, keep, at, tat, leaf_lo, n, nodes, types);
+    if (launches) *launches += (unsigned long long)L + 2;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { fail_out(); cleanup(); return e; }
+    cudaFree(t->nodes);
+    cudaFree(t->types);
+    t->nodes = nodes;
+    t->types = types;
+    t->n_nodes = kept;
+    t->n_types = ntypes ? ntypes : 1;
+    cleanup();
     return cudaSuccess;
 }
 

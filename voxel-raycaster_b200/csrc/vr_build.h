@@ -28,6 +28,11 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
 cudaError_t vr_build_tree_columns_device(const int32_t *d_lo, const int32_t *d_hi, int dim, uint8_t type, cudaStream_t stream,
                                          vr_device_tree *out, unsigned long long *launches);
 
+/* Solid-subtree collapse of a tree just built by one of the two builders above (vr_types.h: VR_NODE_SOLID): the arrays
+ * are replaced by the re-packed ones (same BFS order); a tree without a solid cube is left untouched.  Equals the host
+ * version (vr_octree.cpp: vr_native_collapse_solid) array for array. */
+cudaError_t vr_collapse_solid_device(vr_device_tree *t, cudaStream_t stream, unsigned long long *launches);
+
 /* Top grid of the closed-form walk (vr_types.h: vr_frame_params::grid) from the 64-tree d_nodes: *grid_out is
  * cudaMalloc'ed (ownership passes to the caller).  cudaErrorInvalidValue when the tree is too shallow for a grid.
  * directed: the eight per-octant tables (8 << (3 * grid_bits) entries, vr_octree.cpp: vr_native_grid_directed). */

@@ -118,7 +118,8 @@ void free_tree(vr_ctx *c) {
     c->n_nodes = c->n_leaf_types = c->solid_voxels = 0;
 }
 
-int upload_tree(vr_ctx *c, const vr_native_tree &t, bool from_map) {
+int upload_tree(vr_ctx *c, vr_native_tree &t, bool from_map) {
+    if (c->collapse_solid) vr_native_collapse_solid(t);      /* (a no-op for a tree that holds solid nodes already) */
     free_tree(c);
     VR_CUDA(c, cudaMalloc(&c->d_nodes, t.nodes.size() * sizeof(vr_node)));
     VR_CUDA(c, cudaMalloc(&c->d_leaf_types, t.leaf_types.size()));
@@ -524,7 +525,11 @@ int vr_assign_map(vr_ctx *c, const int8_t *voxels, int nx, int ny, int nz) {
         /* on the device, from the copy just uploaded (vr_build.cu) */
         vr_device_tree dt;
         memset(&dt, 0, sizeof(dt));
-        const cudaError_t be = vr_build_tree_device(c->d_map, nx, c->stream, &dt, &c->launches);
+        cudaError_t be = vr_build_tree_device(c->d_map, nx, c->stream, &dt, &c->launches);
+        if (be == cudaSuccess && c->collapse_solid) {
+            be = vr_collapse_solid_device(&dt, c->stream, &c->launches);
+            if (be != cudaSuccess) { cudaFree(dt.nodes); cudaFree(dt.types); }
+        }
         if (be != cudaSuccess) {
             /* e.g. out of memory for the builder's workspace: the host builder produces the same arrays */
             cudaGetLastError();
@@ -581,6 +586,10 @@ int vr_assign_columns(vr_ctx *c, const int32_t *lo, const int32_t *hi, int dim, 
         vr_device_tree dt;
         memset(&dt, 0, sizeof(dt));
         if (e == cudaSuccess) e = vr_build_tree_columns_device(d_lo, d_hi, dim, (uint8_t)type, c->stream, &dt, &c->launches);
+        if (e == cudaSuccess && c->collapse_solid) {
+            e = vr_collapse_solid_device(&dt, c->stream, &c->launches);
+            if (e != cudaSuccess) { cudaFree(dt.nodes); cudaFree(dt.types); }
+        }
         cudaFree(d_lo);
         cudaFree(d_hi);
         if (e == cudaSuccess) {
@@ -863,6 +872,7 @@ int vr_set_option(vr_ctx *c, const char *name, int64_t value) {
     else if (n == "ctas_per_sm") c->opt.ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
     else if (n == "walk") c->opt.walk = (value == 1 || value == 2) ? (int)value : 0;
     else if (n == "gpu_build") c->gpu_build = value != 0;        /* 0: assign_map builds the 64-tree on the host */
+    else if (n == "collapse_solid") c->collapse_solid = value != 0;   /* applies to the trees built from now on */
     else if (n == "directed_grid") {
         /* top grid of the closed-form walk: 1 = one table per direction octant of the ray (default), 0 = one undirected table */
         if (c->grid_directed != (value != 0)) {
@@ -1057,7 +1067,9 @@ int vr_octree_save(vr_ctx *c, const char *path) {
     VR_CUDA(c, cudaMemcpy(types.data(), c->d_leaf_types, types.size(), cudaMemcpyDeviceToHost));
     FILE *f = fopen(path, "wb");
     if (!f) return fail(c, "octree_save: cannot open %s", path);
-    const uint32_t version = 1;
+    uint32_t version = 1;                                    /* 2: the tree holds solid nodes (VR_NODE_SOLID) */
+    for (const vr_node &n : nodes)
+        if (n.child_base & VR_NODE_SOLID) { version = 2; break; }
     const int32_t dim = c->tree_dim, levels = c->levels;
     const uint64_t nn = nodes.size(), nt = types.size();
     bool ok = fwrite("VR64", 1, 4, f) == 4 && fwrite(&version, 4, 1, f) == 1 && fwrite(&dim, 4, 1, f) == 1 &&
@@ -1075,7 +1087,7 @@ int vr_octree_load(vr_ctx *c, const char *path) {
     uint32_t version = 0;
     int32_t dim = 0, levels = 0;
     uint64_t nn = 0, nt = 0;
-    bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "VR64", 4) == 0 && fread(&version, 4, 1, f) == 1 && version == 1 &&
+    bool ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "VR64", 4) == 0 && fread(&version, 4, 1, f) == 1 && (version == 1 || version == 2) &&
               fread(&dim, 4, 1, f) == 1 && fread(&levels, 4, 1, f) == 1 && fread(&nn, 8, 1, f) == 1 && fread(&nt, 8, 1, f) == 1 &&
               nn >= 1 && nn < (1ull << 32) && nt >= 1 && nt < (1ull << 32) && levels >= 1 && levels <= VR_MAX_LEVELS && dim >= 1 &&
               !(dim & (dim - 1)) && (1ll << (2 * levels)) >= dim;
@@ -1112,6 +1124,11 @@ int vr_octree_load(vr_ctx *c, const char *path) {
                 const uint64_t m = (uint64_t)n.mask_lo | ((uint64_t)n.mask_hi << 32);
                 const uint64_t pc = (uint64_t)__builtin_popcountll(m);
                 n.aux = vr_node_planes(m);                      /* derived from the mask: never trusted from the file */
+                if (n.child_base & VR_NODE_SOLID) {             /* a collapsed solid cube: full mask, a voxel type, no children */
+                    const uint32_t ty = n.child_base & ~VR_NODE_SOLID;
+                    ok = version == 2 && m == ~0ull && (ty == 5 || ty == 6);
+                    continue;
+                }
                 if (!pc) { ok = nn == 1; continue; }            /* only the root of an all-empty map has no children */
                 const uint64_t b = n.child_base;
                 if (leaf) { ok = b + pc <= nt; continue; }

@@ -63,6 +63,7 @@ struct vr_ctx {
     int levels = 0, tree_dim = 0;
     uint64_t n_nodes = 0, n_leaf_types = 0, solid_voxels = 0;
     bool tree_valid = false, tree_from_map = false;
+    bool collapse_solid = true;        /* option "collapse_solid": solid subtrees of the 64-tree become single nodes (VR_NODE_SOLID) */
     bool gpu_build = true;             /* assign_map builds the 64-tree with vr_build.cu (option "gpu_build") */
     float build_ms = 0.f, build_masks_ms = 0.f;
 

@@ -410,12 +410,14 @@ size_t vr_native_collapse_solid(vr_native_tree &t) {
     /* level l = nodes [start[l], start[l + 1]) */
     std::vector<size_t> start((size_t)L + 1, 0);
     start[1] = 1;
+    for (size_t i = 0; i < n; i++)
+        if (t.nodes[i].child_base & VR_NODE_SOLID) return 0;      /* collapsed already (a loaded file, a received tree) */
     for (int l = 0; l + 1 < L; l++) {
         size_t kids = 0;
-        for (size_t i = start[l]; i < start[l + 1]; i++) kids += (size_t)__builtin_popcountll(mask_of(i));
+        for (size_t i = start[l]; i < start[l + 1] && i < n; i++) kids += (size_t)__builtin_popcountll(mask_of(i));
         start[l + 2] = start[l + 1] + kids;
     }
-    if (start[L] != n) return 0;                                  /* not a complete BFS tree (already collapsed?): leave it */
+    if (start[L] != n) return 0;                                  /* not a complete BFS tree: leave it */
     /* (1) bottom-up: type of the node's cube if it is solid, else -1 */
     std::vector<int16_t> st(n, -1);
     size_t solid = 0;
