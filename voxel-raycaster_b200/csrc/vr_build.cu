@@ -550,6 +550,7 @@ cudaError_t vr_collapse_solid_device(vr_device_tree *t, cudaStream_t stream, uns
     if (L == 1) start[1] = n;
     if (start[L] != n) return cudaErrorInvalidValue;
     const unsigned leaf_lo = start[L - 1];
+    if (leaf_lo >= n) return cudaSuccess;                               /* no leaf level: an empty map (a root without children) */
 
     uint8_t *st = nullptr, *types = nullptr;
     uint32_t *keep = nullptr, *at = nullptr, *cnt = nullptr, *tat = nullptr, *d_solid = nullptr;
