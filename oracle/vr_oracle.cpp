@@ -164,12 +164,33 @@ inline void svo_lookup(const vro_scene *s, i3 v, CellTrack &c, vro_counters &k) 
         return;                                                           /* same cell: no fetch */
     }
     /* full descent to find the new cell */
-    const uint64_t *buf = s->oct_desc;
-    uint64_t idx = (uint64_t)s->oct_root_index;
-    uint64_t cd = buf[idx];
     int dimension = (int)s->octdim;
     i3 o = {0, 0, 0};
     int len = 1;
+    if (!s->oct_desc) {
+        /* the same path read off a 4^3-per-node occupancy tree (vro_scene::tree64): every node is two 2^3 levels */
+        const uint32_t *t = s->tree64;
+        uint32_t idx = 0;
+        for (int sh = 2 * (s->tree64_levels - 1);; sh -= 2) {
+            const uint64_t m = (uint64_t)t[4 * idx] | ((uint64_t)t[4 * idx + 1] << 32);
+            const int cx = (v.x >> sh) & 3, cy = (v.y >> sh) & 3, cz = (v.z >> sh) & 3;
+            const int ci = cx | (cy << 2) | (cz << 4);
+            /* upper 2^3 level: the octant of 2x2x2 slots around the slot, edge 2 << sh */
+            dimension = 2 << sh;
+            o = {(v.x >> (sh + 1)) << (sh + 1), (v.y >> (sh + 1)) << (sh + 1), (v.z >> (sh + 1)) << (sh + 1)};
+            if (((m >> (ci & 0x2A)) & 0x00330033ull) == 0ull) break;      /* !valid: an empty child */
+            len++;                                                        /* the octant's descriptor */
+            /* lower 2^3 level: the slot, edge 1 << sh */
+            dimension = 1 << sh;
+            o = {(v.x >> sh) << sh, (v.y >> sh) << sh, (v.z >> sh) << sh};
+            if (!((m >> ci) & 1ull) || sh == 0) break;                    /* !valid, or half == 1 */
+            len++;
+            idx = t[4 * idx + 2] + (uint32_t)__builtin_popcountll(m & ((1ull << ci) - 1ull));
+        }
+    } else {
+    const uint64_t *buf = s->oct_desc;
+    uint64_t idx = (uint64_t)s->oct_root_index;
+    uint64_t cd = buf[idx];
     for (;;) {
         int half = dimension / 2;
         bool gx = v.x >= half + o.x, gy = v.y >= half + o.y, gz = v.z >= half + o.z;
@@ -184,6 +205,7 @@ inline void svo_lookup(const vro_scene *s, i3 v, CellTrack &c, vro_counters &k) 
         cd = buf[idx];
         dimension = half;
         len++;
+    }
     }
     int shared = 0;   /* path nodes (depth 0..shared-1) that contain both the old and new voxel */
     if (c.size) {
@@ -581,7 +603,7 @@ void vro_get_oct_vox(const uint64_t *desc, int64_t root_index, int64_t octdim, c
 int vro_raycast(const vro_scene *s, int y0, int y1, int row_stride, uint8_t *rgba, vro_aux *aux,
                 vro_counters *counters, int count_svo, int num_threads) {
     if (!s || !s->ray_table || (!s->map && !(s->col_lo && s->col_hi)) || !s->lights || !s->atlas || !rgba) return -1;
-    if (count_svo && !s->oct_desc) return -2;
+    if (count_svo && !s->oct_desc && !(s->tree64 && s->tree64_levels >= 1 && (1ll << (2 * s->tree64_levels)) == s->octdim)) return -2;
     y0 = std::max(y0, 0);
     y1 = std::min(y1, (int)s->height);
     if (row_stride < 1) row_stride = 1;

@@ -82,6 +82,14 @@ typedef struct vro_scene {
     /* kernel:357 `bounce_count < 2`: lifted into a parameter like max_distance (0 = the reference's 2).  The reflection
      * limit as a setting is on the reference's own TODO list (src/main.cpp:31-33). */
     int32_t max_bounces;
+    /* Counters only (the D_svo byte model of maps too large for a reference-format buffer: 4096^3 has no dense map to run
+     * Octree::Generate on).  An occupancy tree with 4x4x4 children per node = two levels of the reference's 2^3 octree
+     * per node: tree64[4 * i + 0..1] = 64-bit child mask (bit cx | cy << 2 | cz << 4), tree64[4 * i + 2] = index of the
+     * first child node (children contiguous, ascending set-bit order), root at 0, `tree64_levels` levels, dimension
+     * covered 4^levels == octdim.  When oct_desc is NULL and this is given, svo_lookup derives the path of 2^3 descriptors
+     * from it (an octant of 2x2x2 slots that is empty = an empty child one level up).  Ignored by the ray cast itself. */
+    const uint32_t *tree64;
+    int32_t tree64_levels;
 } vro_scene;
 
 /* Per-pixel auxiliary record, 32 bytes.  The reference kernel only writes RGBA8; these expose

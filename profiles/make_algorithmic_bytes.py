@@ -63,11 +63,24 @@ if args.config == "c5":
 
 scene = bench.bench_scene(args.config, lights=args.lights)
 t0 = time.time()
-desc, root = pkg.octree_generate(scene.volume)
-print(f"reference-format octree: {desc.size} descriptors ({desc.nbytes / 1e6:.1f} MB) in {time.time() - t0:.1f} s")
-t0 = time.time()
-_, aux, cnt = O.raycast(scene, octree=(desc, root), want_counters=True, count_svo=True, row_stride=args.row_stride,
-                        shadow_lights=args.lights)
+if scene.volume is None:
+    # c4 (4096^3): no dense map, hence no reference-format buffer; the path of 2^3 descriptors is read off an occupancy tree
+    # with 4^3 children per node built from the column tables (vro_scene::tree64; tests/test_oracle.py holds the two
+    # counters equal on maps that have both)
+    import emu_lib  # noqa: E402
+
+    emu_lib.set_collapse(False)
+    nodes, _, levels = emu_lib.tree_from_columns(scene.columns[0], scene.columns[1])
+    print(f"occupancy tree from the column tables: {nodes.shape[0]} nodes, {levels} levels in {time.time() - t0:.1f} s")
+    t0 = time.time()
+    _, aux, cnt = O.raycast(scene, want_counters=True, count_svo=True, row_stride=args.row_stride, shadow_lights=args.lights,
+                            tree64=(nodes, levels))
+else:
+    desc, root = pkg.octree_generate(scene.volume)
+    print(f"reference-format octree: {desc.size} descriptors ({desc.nbytes / 1e6:.1f} MB) in {time.time() - t0:.1f} s")
+    t0 = time.time()
+    _, aux, cnt = O.raycast(scene, octree=(desc, root), want_counters=True, count_svo=True, row_stride=args.row_stride,
+                            shadow_lights=args.lights)
 print(f"oracle counters over 1/{args.row_stride} of the rows in {time.time() - t0:.1f} s: {cnt}")
 k = scene.height * scene.width / cnt["pixels"]
 P = scene.width * scene.height
@@ -80,7 +93,8 @@ out = {
     "dda_steps": cnt["dda_steps"] * k, "texel_fetches": cnt["texel_fetches"] * k,
     "svo_desc_fetches": cnt["svo_desc_fetches"] * k, "svo_cell_changes": cnt["svo_cell_changes"] * k,
     "tie_pixels": cnt["tie_pixels"] * k,
-    "ref_octree_descriptors": int(desc.size),
+    "ref_octree_descriptors": int(desc.size) if scene.volume is not None else None,
+    "descriptor_path_source": "reference-format octree" if scene.volume is not None else "4^3 occupancy tree built from the column tables (two 2^3 levels per node)",
 }
 out["bytes_svo"] = P * 20 + 8 * out["svo_desc_fetches"] + 4 * out["texel_fetches"]
 out["bytes_dense"] = P * 20 + 1 * out["dda_steps"] + 4 * out["texel_fetches"]

@@ -37,6 +37,7 @@ class VroScene(C.Structure):
         ("max_distance", C.c_int32), ("shadow_lights", C.c_int32),
         ("col_lo", C.POINTER(C.c_int32)), ("col_hi", C.POINTER(C.c_int32)),
         ("canonical_t", C.c_int32), ("max_bounces", C.c_int32),
+        ("tree64", C.POINTER(C.c_uint32)), ("tree64_levels", C.c_int32),
     ]
 
 
@@ -112,7 +113,7 @@ def trig_of(cam_dir) -> np.ndarray:
 def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray, int] | None = None,
             rows: tuple[int, int] | None = None, want_aux: bool = True, want_counters: bool = False,
             count_svo: bool = False, threads: int = 0, max_distance: int | None = None, row_stride: int = 1,
-            shadow_lights: int = 1, canonical_t: bool = False, keep_near: bool = False, max_bounces: int = 0):
+            shadow_lights: int = 1, canonical_t: bool = False, keep_near: bool = False, max_bounces: int = 0, tree64=None):
     """Runs the restated reference kernel (dense branch) on a scene.Scene.
     Returns (rgba [H,W,4] prefilled with (255,255,255,100), aux or None, counters dict or None)."""
     w, h = scene.width, scene.height
@@ -147,6 +148,10 @@ def raycast(scene, ray_table: np.ndarray | None = None, octree: tuple[np.ndarray
         s.oct_desc = desc.ctypes.data_as(C.POINTER(C.c_uint64))
         s.oct_desc_len = desc.size
         s.oct_root_index = root
+    if tree64 is not None:                   # (nodes uint32[n, 4], levels): descriptor-fetch counters without a reference-format buffer
+        t64 = np.ascontiguousarray(tree64[0], dtype=np.uint32)
+        s.tree64 = t64.ctypes.data_as(C.POINTER(C.c_uint32))
+        s.tree64_levels = int(tree64[1])
     s.octdim = scene.n
     s.max_distance = scene.max_distance if max_distance is None else max_distance
     s.shadow_lights = shadow_lights          # 1 = the reference (light 0 only); > 1 = the multi-light extension

@@ -229,3 +229,25 @@ def test_ray_table_equals_reference_generated_viewport_tables(oracle):
         assert np.array_equal(oracle.make_ray_table(w, h).view(np.uint32), z[key].view(np.uint32)), key
     t = oracle.make_ray_table(3840, 2160)[::60, ::40]
     assert np.array_equal(t.view(np.uint32), z["t3840x2160_every_60th_row_40th_col"].view(np.uint32))
+
+
+def test_descriptor_counters_from_a_4x4x4_occupancy_tree(pkg, oracle):
+    """The D_svo byte model of 4096^3 (no dense map, hence no reference-format buffer) reads the path of 2^3 descriptors
+    off an occupancy tree with 4^3 children per node (vro_scene::tree64): on maps that have both, the counters are the
+    same as from the reference-format octree."""
+    import emu_lib
+
+    S = pkg.scene
+    n = 64
+    vol = S.terrain_map(n, "shell")
+    pos, d = S.make_camera(n, S.heightfield(n), 3)
+    scene = S.Scene(n, vol, 320, 180, pos, d, S.make_lights(n), max_distance=3 * n)
+    desc, root = pkg.octree_generate(vol)
+    _, _, a = oracle.raycast(scene, octree=(desc, root), want_aux=False, want_counters=True, count_svo=True)
+    emu_lib.set_collapse(False)
+    try:
+        nodes, _, levels = emu_lib.tree_from_dense(vol)
+    finally:
+        emu_lib.set_collapse(True)
+    _, _, b = oracle.raycast(scene, want_aux=False, want_counters=True, count_svo=True, tree64=(nodes, levels))
+    assert a["svo_desc_fetches"] == b["svo_desc_fetches"] > 0 and a["svo_cell_changes"] == b["svo_cell_changes"]
