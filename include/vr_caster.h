@@ -132,6 +132,18 @@ int vr_read_framebuffer(vr_ctx *ctx, uint8_t *rgba_out, size_t bytes);
 int vr_frame_begin(vr_ctx *ctx);
 int vr_frame_end(vr_ctx *ctx, const uint8_t **rgba);
 
+/* CLCaster::draw(sf::RenderWindow*) with CL/GL sharing (ref src/CLCaster.cpp:330-332; the viewport texture is shared with
+ * OpenCL by clCreateFromGLTexture, :840-842, and acquired / released around the kernel, :952, :978): the CUDA-GL interop
+ * equivalent.  vr_gl_register_texture registers an RGBA8 OpenGL texture of the viewport's size (the sprite's texture:
+ * sf::Texture::getNativeHandle(); target GL_TEXTURE_2D = 0x0DE1) with the context -- it must be called on the thread whose
+ * OpenGL context owns the texture; vr_gl_draw maps it, copies the last frame into it device-to-device on the context
+ * stream and unmaps it (no host round trip), after which the caller draws its sprite.  Both fail with a message when
+ * there is no current OpenGL context.  NOT exercised on a GL machine: this image has no GL / EGL; the
+ * GPU suite only checks the failure path. */
+int vr_gl_register_texture(vr_ctx *ctx, uint32_t gl_texture, uint32_t gl_target);
+int vr_gl_draw(vr_ctx *ctx);
+int vr_gl_unregister(vr_ctx *ctx);
+
 /* ---- extensions beyond the reference API ------------------------------------------------------- */
 
 /* Multi-GPU screen-tile split: this context renders only the row bands b with b % stride == first

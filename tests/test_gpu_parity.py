@@ -791,3 +791,19 @@ def test_gpu_column_builder_equals_host_builder(pkg, kind):
     assert np.array_equal(d_nodes, h_nodes), f"{kind}: {int((d_nodes != h_nodes).any(axis=1).sum())} nodes differ"
     assert np.array_equal(d_types, h_types)
     print(f"{kind}: {d_nodes.shape[0]} nodes, {d_types.shape[0]} voxel types, device build {ms:.2f} ms")
+
+
+@pytest.mark.gpu
+def test_gl_interop_entry_points_fail_loudly_without_a_gl_context(pkg):
+    """draw() with CL/GL sharing (ref src/CLCaster.cpp:330-332, :840-842) -> CUDA-GL interop (vr_gl_register_texture /
+    vr_gl_draw).  This image has no OpenGL, so only the failure path can run: registering a texture without a current GL
+    context is refused with a message, drawing without a registered texture too, and the context keeps working."""
+    scene = pkg.scene.make_scene("head")
+    c = make_caster(pkg, scene, False, aux=False)
+    assert c.compute()
+    before = c.draw().copy()
+    assert not c.gl_draw() and "no texture registered" in c.last_error()
+    assert not c.gl_register_texture(1) and "gl_register_texture" in c.last_error()
+    assert c.gl_unregister()
+    assert c.compute() and np.array_equal(c.draw(), before)
+    c.close()

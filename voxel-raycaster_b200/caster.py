@@ -85,6 +85,9 @@ SYMBOLS = {
     "vr_read_ray_table": (_i, [_vp, _f32p, C.c_size_t]),
     "vr_native_tree_info": (_i, [_vp, _u64p, _u64p, _i32p, _i32p]),
     "vr_native_tree_copy": (_i, [_vp, _vp, _vp]),
+    "vr_gl_register_texture": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
+    "vr_gl_draw": (C.c_int, [_vp]),
+    "vr_gl_unregister": (C.c_int, [_vp]),
     "vr_top_grid_read": (C.c_uint64, [_vp, _vp, C.c_uint64, _i32p, _i32p]),
     "vr_mgpu_init": (_i, [_vp, C.c_char_p, _i, _i, C.c_uint]),
     "vr_mgpu_broadcast_octree": (_i, [_vp]),
@@ -382,6 +385,17 @@ class CUDACaster:
 
     def mgpu_shutdown(self) -> bool:
         return bool(self._lib.vr_mgpu_shutdown(self._ctx))
+
+    def gl_register_texture(self, gl_texture: int, gl_target: int = 0x0DE1) -> bool:
+        """CUDA-GL interop of the viewer path (CLCaster::draw with CL/GL sharing): registers an RGBA8 GL texture (default
+        target GL_TEXTURE_2D); needs a current OpenGL context."""
+        return bool(self._lib.vr_gl_register_texture(self._ctx, int(gl_texture), int(gl_target)))
+
+    def gl_draw(self) -> bool:
+        return bool(self._lib.vr_gl_draw(self._ctx))
+
+    def gl_unregister(self) -> bool:
+        return bool(self._lib.vr_gl_unregister(self._ctx))
 
     def top_grid(self) -> tuple[np.ndarray, int, int]:
         """(grid entries, block shift, log2 G) of the closed-form walk's top grid: uint32[8, G, G, G] indexed [octant, z, y, x]

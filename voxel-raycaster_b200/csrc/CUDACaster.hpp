@@ -69,6 +69,11 @@ public:
         return vr_read_framebuffer(ctx_, frame.data(), frame.size()) != 0;
     }
 
+    /* draw(sf::RenderWindow*) with CL/GL sharing (src/CLCaster.cpp:330-332, :840-842): register the sprite's texture once
+     * (sf::Texture::getNativeHandle()), then draw_gl() after every compute() copies the frame into it on the device */
+    bool register_gl_texture(unsigned texture, unsigned target = 0x0DE1 /* GL_TEXTURE_2D */) { return vr_gl_register_texture(ctx_, texture, target) != 0; }
+    bool draw_gl() { return vr_gl_draw(ctx_) != 0; }
+
     /* ref :148-151 */
     bool load_config() { return vr_load_config(ctx_, nullptr) != 0; }
     void save_config() { vr_save_config(ctx_, nullptr); }

@@ -394,6 +394,7 @@ void vr_destroy(vr_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     vr_i_mgpu_destroy(c);
+    if (c->gl_resource) { cudaGraphicsUnregisterResource(c->gl_resource); c->gl_resource = nullptr; }
     vr_release_viewport(c);
     vr_release_map(c);
     vr_release_octree(c);
@@ -816,6 +817,52 @@ int vr_read_framebuffer(vr_ctx *c, uint8_t *rgba_out, size_t bytes) {
     if (n > full) n = full;
     VR_CUDA(c, cudaMemcpyAsync(rgba_out, c->d_image[c->cur_image], n, cudaMemcpyDeviceToHost, c->stream));
     return vr_sync(c);
+}
+
+/* ---- CUDA-GL interop for the viewer (cuda_gl_interop.h needs <GL/gl.h>, which this image lacks: the one entry point
+ * used is declared here with GLuint / GLenum spelled out) */
+extern "C" cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource **resource, unsigned int image, unsigned int target,
+                                                   unsigned int flags);
+
+int vr_gl_unregister(vr_ctx *c) {
+    if (!c) return 0;
+    if (c->gl_resource) {
+        cudaSetDevice(c->device);
+        cudaGraphicsUnregisterResource(c->gl_resource);
+        c->gl_resource = nullptr;
+    }
+    return 1;
+}
+
+int vr_gl_register_texture(vr_ctx *c, uint32_t gl_texture, uint32_t gl_target) {
+    if (!c) return 0;
+    if (!c->d_image[0]) return fail(c, "gl_register_texture: viewport not created");
+    cudaSetDevice(c->device);
+    vr_gl_unregister(c);
+    const cudaError_t e = cudaGraphicsGLRegisterImage(&c->gl_resource, gl_texture, gl_target, cudaGraphicsRegisterFlagsWriteDiscard);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c->gl_resource = nullptr;
+        return fail(c, "gl_register_texture: %s (is an OpenGL context current on this thread, and is texture %u an RGBA8 texture of it?)",
+                    cudaGetErrorString(e), gl_texture);
+    }
+    return 1;
+}
+
+int vr_gl_draw(vr_ctx *c) {
+    if (!c) return 0;
+    if (!c->gl_resource) return fail(c, "gl_draw: no texture registered (vr_gl_register_texture)");
+    if (c->band_stride > 1 || c->tile_world > 1) return fail(c, "gl_draw: the context renders a part of the frame only");
+    cudaSetDevice(c->device);
+    VR_CUDA(c, cudaGraphicsMapResources(1, &c->gl_resource, c->stream));
+    cudaArray_t arr = nullptr;
+    cudaError_t e = cudaGraphicsSubResourceGetMappedArray(&arr, c->gl_resource, 0, 0);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DToArrayAsync(arr, 0, 0, c->d_image[c->cur_image], (size_t)c->width * 4, (size_t)c->width * 4, (size_t)c->height,
+                                     cudaMemcpyDeviceToDevice, c->stream);
+    const cudaError_t u = cudaGraphicsUnmapResources(1, &c->gl_resource, c->stream);      /* orders GL after the copy */
+    if (e != cudaSuccess || u != cudaSuccess) return fail(c, "gl_draw: %s", cudaGetErrorString(e != cudaSuccess ? e : u));
+    return 1;
 }
 
 int vr_frame_begin(vr_ctx *c) {

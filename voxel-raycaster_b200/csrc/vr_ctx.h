@@ -88,6 +88,7 @@ struct vr_ctx {
     int used_svo = 0;
     int bias[3] = {0, 0, 0};
     vr_launch_options opt = {0, 8, 3, 148, nullptr, 2};      /* walk 2 = the closed-form walk is the default */
+    struct cudaGraphicsResource *gl_resource = nullptr;   /* the viewer's texture (vr_gl_register_texture) */
     vr_mgpu *mgpu = nullptr;           /* multi-GPU frame scheduler state (vr_mgpu_init) */
 };
 
