@@ -45,10 +45,17 @@ __device__ __forceinline__ uint32_t solid4(uint32_t w) {
     return ((v * 0x00204081u) >> 21) & 15u;                        /* gathered into one nibble (no colliding partial products) */
 }
 
-__device__ __forceinline__ uint32_t brick_key(uint32_t bx, uint32_t by, uint32_t bz, int digits) {
+/* Hierarchical key of a leaf brick: one 6-bit child slot per level below the root, the root's slot on top.  `half`: the map
+ * edge is 2 * 4^(levels-1), not 4^levels, so only the 2x2x2 root slots {0,1}^3 lie inside the map: that top digit is
+ * stored as 3 bits (cx | cy << 1 | cz << 2 -- the same order as the slot numbers 0,1,4,5,16,17,20,21), which makes the key
+ * space of every level exactly the cells of the map at that level instead of eight times as many. */
+__device__ __forceinline__ uint32_t brick_key(uint32_t bx, uint32_t by, uint32_t bz, int digits, int half) {
     uint32_t key = 0;
-    for (int j = 0; j < digits; j++)
+    const int full = half ? digits - 1 : digits;
+    for (int j = 0; j < full; j++)
         key |= (((bx >> (2 * j)) & 3u) | (((by >> (2 * j)) & 3u) << 2) | (((bz >> (2 * j)) & 3u) << 4)) << (6 * j);
+    if (half && digits > 0)
+        key |= (((bx >> (2 * full)) & 1u) | (((by >> (2 * full)) & 1u) << 1) | (((bz >> (2 * full)) & 1u) << 2)) << (6 * full);
     return key;
 }
 
@@ -57,7 +64,7 @@ __device__ __forceinline__ uint32_t brick_key(uint32_t bx, uint32_t by, uint32_t
  * the 4 masks of a lane are 32 contiguous bytes of the key-ordered output (4 consecutive x slots of one node).
  * Requires dim >= 16; smaller maps take vr_brick_masks_small. */
 __global__ void __launch_bounds__(128)
-vr_brick_masks(const int8_t *__restrict__ map, int dim, int nb, int nquad, int digits, unsigned long long *__restrict__ leaf) {
+vr_brick_masks(const int8_t *__restrict__ map, int dim, int nb, int nquad, int digits, int half, unsigned long long *__restrict__ leaf) {
     const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long total = (unsigned long long)nb * nb * nquad;
     if (gid >= total) return;
@@ -80,13 +87,13 @@ vr_brick_masks(const int8_t *__restrict__ map, int dim, int nb, int nquad, int d
             }
         }
     /* bricks 4*qx .. 4*qx+3 differ in the lowest key digit only: keys k, k+1, k+2, k+3 */
-    uint4 *dst = reinterpret_cast<uint4 *>(leaf + brick_key(4 * qx, by, bz, digits));
+    uint4 *dst = reinterpret_cast<uint4 *>(leaf + brick_key(4 * qx, by, bz, digits, half));
     dst[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
     dst[1] = make_uint4(lo[2], hi[2], lo[3], hi[3]);
 }
 
 /* maps narrower than 16 voxels: one thread per brick */
-__global__ void vr_brick_masks_small(const int8_t *__restrict__ map, int dim, int nb, int digits, unsigned long long *__restrict__ leaf) {
+__global__ void vr_brick_masks_small(const int8_t *__restrict__ map, int dim, int nb, int digits, int half, unsigned long long *__restrict__ leaf) {
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (unsigned)(nb * nb * nb)) return;
     const unsigned bx = gid % (unsigned)nb, by = (gid / (unsigned)nb) % (unsigned)nb, bz = gid / (unsigned)(nb * nb);
@@ -96,7 +103,7 @@ __global__ void vr_brick_masks_small(const int8_t *__restrict__ map, int dim, in
     for (int z = 0; z < 4; z++)
         for (int y = 0; y < 4; y++)
             m |= (unsigned long long)solid4(words[bx + wdim * ((size_t)(4 * by + y) + (size_t)dim * (size_t)(4 * bz + z))]) << (4 * y + 16 * z);
-    leaf[brick_key(bx, by, bz, digits)] = m;
+    leaf[brick_key(bx, by, bz, digits, half)] = m;
 }
 
 /* 2. one warp per parent: bit ci = child ci has any voxel */
@@ -125,6 +132,13 @@ struct PopCount {
 #endif
     }
 };
+/* the root of a map of edge 2 * 4^(levels-1): its 8 children are the level-1 keys 0..7 (brick_key), slot cx | cy<<2 | cz<<4 */
+__global__ void vr_reduce_root_half(const unsigned long long *__restrict__ child, unsigned long long *__restrict__ root) {
+    unsigned long long m = 0ull;
+    for (int c = 0; c < 8; c++)
+        if (child[c] != 0ull) m |= 1ull << ((c & 1) | (((c >> 1) & 1) << 2) | (((c >> 2) & 1) << 4));
+    root[0] = m;
+}
 
 /* totals[l] = non-empty masks of level l (l >= 1), totals[levels] = solid voxels */
 __global__ void vr_level_totals(const unsigned long long *masks, const uint32_t *prefix, const uint32_t *vox_prefix,
@@ -132,11 +146,12 @@ __global__ void vr_level_totals(const unsigned long long *masks, const uint32_t 
     const int l = threadIdx.x;
     if (l > levels) return;
     if (l == 0) { totals[0] = 1u; return; }
+    const unsigned long long *level_keys = level_off + (VR_MAX_LEVELS + 1);          /* keys per level */
     if (l < levels) {
-        const unsigned long long last = level_off[l] + (1ull << (6 * l)) - 1;
+        const unsigned long long last = level_off[l] + level_keys[l] - 1;
         totals[l] = prefix[last] + (masks[last] != 0ull ? 1u : 0u);
     } else {
-        const unsigned long long first = level_off[levels - 1], last = first + (1ull << (6 * (levels - 1))) - 1;
+        const unsigned long long first = level_off[levels - 1], last = first + level_keys[levels - 1] - 1;
         totals[levels] = vox_prefix[last - first] + (uint32_t)__popcll(masks[last]);
     }
 }
@@ -160,18 +175,25 @@ __global__ void vr_emit_nodes(const unsigned long long *__restrict__ masks, cons
 }
 
 /* 5. voxel values of the set bits of every leaf brick, in ascending bit order */
-__global__ void vr_emit_types(const int8_t *__restrict__ map, int dim, int digits, const unsigned long long *__restrict__ leaf,
+__global__ void vr_emit_types(const int8_t *__restrict__ map, int dim, int digits, int half, const unsigned long long *__restrict__ leaf,
                               const uint32_t *__restrict__ vox_prefix, unsigned nkeys, uint8_t *__restrict__ types) {
     const unsigned key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= nkeys) return;
     unsigned long long m = leaf[key];
     if (m == 0ull) return;
     unsigned bx = 0, by = 0, bz = 0;
-    for (int j = 0; j < digits; j++) {
+    const int full = half ? digits - 1 : digits;
+    for (int j = 0; j < full; j++) {
         const unsigned d = (key >> (6 * j)) & 63u;
         bx |= (d & 3u) << (2 * j);
         by |= ((d >> 2) & 3u) << (2 * j);
         bz |= (d >> 4) << (2 * j);
+    }
+    if (half && digits > 0) {
+        const unsigned d = (key >> (6 * full)) & 7u;
+        bx |= (d & 1u) << (2 * full);
+        by |= ((d >> 1) & 1u) << (2 * full);
+        bz |= (d >> 2) << (2 * full);
     }
     uint32_t at = vox_prefix[key];
     while (m) {
@@ -197,10 +219,16 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
     while ((1 << (2 * L)) < dim) L++;
     if (L > VR_MAX_LEVELS) return cudaErrorInvalidValue;
     const int nb = dim / 4, nquad = nb / 4, digits = L - 1;
-    unsigned long long off[VR_MAX_LEVELS + 1];
+    /* keys per level = cells of the map at that level: 64^l, or 8 * 64^(l-1) when the map edge is 2 * 4^(L-1) (only the
+     * 2x2x2 root slots inside the map exist: brick_key) -- no workspace for the part of a wider root outside the map */
+    const int half = (L > 1 && (1 << (2 * L)) != dim) ? 1 : 0;
+    unsigned long long off[2 * (VR_MAX_LEVELS + 1)], *nk = off + (VR_MAX_LEVELS + 1);
     off[0] = 0;
-    for (int l = 0; l < L; l++) off[l + 1] = (off[l] + (1ull << (6 * l)) + 3ull) & ~3ull;   /* level l has 64^l keys; 32-byte aligned */
-    const unsigned long long nkeys_all = off[L], nleaf = 1ull << (6 * (L - 1));
+    for (int l = 0; l < L; l++) {
+        nk[l] = l == 0 ? 1ull : (half ? 8ull << (6 * (l - 1)) : 1ull << (6 * l));
+        off[l + 1] = (off[l] + nk[l] + 3ull) & ~3ull;                                       /* 32-byte aligned */
+    }
+    const unsigned long long nkeys_all = off[L], nleaf = nk[L - 1];
     if (nleaf > (1ull << 31)) return cudaErrorInvalidValue;
 
     unsigned long long *masks = nullptr, *d_off = nullptr;
@@ -221,8 +249,8 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
     VRB(cudaMalloc(&prefix, nkeys_all * sizeof(uint32_t)));
     VRB(cudaMalloc(&vox_prefix, nleaf * sizeof(uint32_t)));
     VRB(cudaMalloc(&d_totals, (VR_MAX_LEVELS + 1) * sizeof(uint32_t)));
-    VRB(cudaMalloc(&d_off, (VR_MAX_LEVELS + 1) * sizeof(unsigned long long)));
-    VRB(cudaMemcpyAsync(d_off, off, (L + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    VRB(cudaMalloc(&d_off, 2 * (VR_MAX_LEVELS + 1) * sizeof(unsigned long long)));
+    VRB(cudaMemcpyAsync(d_off, off, 2 * (VR_MAX_LEVELS + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     size_t tmp_bytes = 0;
     {
         auto it = thrust::make_transform_iterator((const unsigned long long *)masks, PopCount());
@@ -234,25 +262,24 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
     VRB(cudaEventCreate(&e2));
 
     VRB(cudaEventRecord(e0, stream));
-    if ((1 << (2 * L)) != dim)           /* root wider than the map: the keys outside the map are never written */
-        VRB(cudaMemsetAsync(masks + off[L - 1], 0, nleaf * sizeof(unsigned long long), stream));
     if (dim >= 16) {
         const unsigned long long lanes = (unsigned long long)nb * nb * nquad;
-        vr_brick_masks<<<(unsigned)((lanes + 127) / 128), 128, 0, stream>>>(d_map, dim, nb, nquad, digits, masks + off[L - 1]);
+        vr_brick_masks<<<(unsigned)((lanes + 127) / 128), 128, 0, stream>>>(d_map, dim, nb, nquad, digits, half, masks + off[L - 1]);
     } else {
-        vr_brick_masks_small<<<(nb * nb * nb + 63) / 64, 64, 0, stream>>>(d_map, dim, nb, digits, masks + off[L - 1]);
+        vr_brick_masks_small<<<(nb * nb * nb + 63) / 64, 64, 0, stream>>>(d_map, dim, nb, digits, half, masks + off[L - 1]);
     }
     if (launches) ++*launches;
     VRB(cudaEventRecord(e1, stream));
     for (int l = L - 2; l >= 0; l--) {
-        const unsigned nparent = 1u << (6 * l);
-        vr_reduce_masks<<<(nparent * 32 + 127) / 128, 128, 0, stream>>>(masks + off[l + 1], masks + off[l], nparent);
+        const unsigned nparent = (unsigned)nk[l];
+        if (l == 0 && half) vr_reduce_root_half<<<1, 1, 0, stream>>>(masks + off[1], masks + off[0]);
+        else vr_reduce_masks<<<(nparent * 32 + 127) / 128, 128, 0, stream>>>(masks + off[l + 1], masks + off[l], nparent);
         if (launches) ++*launches;
     }
     for (int l = 1; l < L; l++) {
         auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[l]), NonZero());
         size_t need = tmp_bytes;
-        VRB(cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, prefix + off[l], (int)(1ull << (6 * l)), stream));
+        VRB(cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, prefix + off[l], (int)nk[l], stream));
     }
     {
         auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[L - 1]), PopCount());
@@ -276,14 +303,14 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
         if (e != cudaSuccess) { fail_out(); cleanup(); return e; }
     }
     for (int l = 0; l < L; l++) {
-        const unsigned nk = 1u << (6 * l);
+        const unsigned nkl = (unsigned)nk[l];
         const bool leaf = l == L - 1;
-        vr_emit_nodes<<<(nk + 255) / 256, 256, 0, stream>>>(masks + off[l], prefix + off[l], leaf ? vox_prefix : prefix + off[l + 1], nk,
-                                                            start[l], leaf ? 0u : start[l + 1], leaf ? 1 : 0, nodes);
+        vr_emit_nodes<<<(nkl + 255) / 256, 256, 0, stream>>>(masks + off[l], prefix + off[l], leaf ? vox_prefix : prefix + off[l + 1], nkl,
+                                                             start[l], leaf ? 0u : start[l + 1], leaf ? 1 : 0, nodes);
         if (launches) ++*launches;
     }
     if (solid) {
-        vr_emit_types<<<(unsigned)((nleaf + 255) / 256), 256, 0, stream>>>(d_map, dim, digits, masks + off[L - 1], vox_prefix,
+        vr_emit_types<<<(unsigned)((nleaf + 255) / 256), 256, 0, stream>>>(d_map, dim, digits, half, masks + off[L - 1], vox_prefix,
                                                                            (unsigned)nleaf, types);
         if (launches) ++*launches;
     }
@@ -371,11 +398,8 @@ __global__ void vr_cube_init(const uint32_t *__restrict__ base, unsigned n, uint
     for (int o = 0; o < 8; o++) E[(size_t)o * n + i] = v;
 }
 
-__global__ void vr_cube_grow(uint8_t *E, int bits, unsigned r) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void cube_grow_one(uint8_t *E, int bits, unsigned r, unsigned t) {
     const unsigned n = 1u << (3 * bits), G = 1u << bits;
-    if (t >= 8u * n) return;
-    if (E[t] != r) return;
     const unsigned o = t >> (3 * bits), i = t & (n - 1u);
     const unsigned bx = i & (G - 1u), by = (i >> bits) & (G - 1u), bz = i >> (2 * bits);
     const int sx = (o & 1u) ? -1 : 1, sy = (o & 2u) ? -1 : 1, sz = (o & 4u) ? -1 : 1;
@@ -389,6 +413,29 @@ __global__ void vr_cube_grow(uint8_t *E, int bits, unsigned r) {
         if (Eo[j] < r) return;
     }
     E[t] = (uint8_t)(r + 1u);
+}
+
+/* one thread per 16 consecutive entries (one 128-bit load): almost all of them are final already (edge != r) */
+__global__ void vr_cube_grow(uint8_t *E, int bits, unsigned r) {
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = 8u << (3 * bits);
+    const unsigned t0 = q * 16u;
+    if (t0 >= total) return;
+    if (total < 16u) {                                           /* (grids of 1^3: nothing can grow) */
+        for (unsigned t = 0; t < total; t++)
+            if (E[t] == r) cube_grow_one(E, bits, r, t);
+        return;
+    }
+    const uint4 v = *reinterpret_cast<const uint4 *>(E + t0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t rr = r * 0x01010101u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = w[k] ^ rr;                            /* a zero byte = an entry with edge r */
+        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0u) continue;
+        for (int b = 0; b < 4; b++)
+            if (((w[k] >> (8 * b)) & 0xffu) == r) cube_grow_one(E, bits, r, t0 + 4u * k + b);
+    }
 }
 
 __global__ void vr_cube_finish(const uint32_t *__restrict__ base, const uint8_t *__restrict__ cell, const uint8_t *__restrict__ E,
@@ -430,7 +477,8 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, bo
         const unsigned blocks8 = (unsigned)(((size_t)8 * n + 255) / 256);
         const unsigned cap = (unsigned)G < VR_GRID_MAX_CUBE ? (unsigned)G : VR_GRID_MAX_CUBE;
         vr_cube_init<<<blocks, 256, 0, stream>>>(grid, n, E);
-        for (unsigned r = 1; r < cap; r++) vr_cube_grow<<<blocks8, 256, 0, stream>>>(E, bits, r);
+        const unsigned blocks16 = (unsigned)(((size_t)8 * n / 16 + 255) / 256) + 1u;
+        for (unsigned r = 1; r < cap; r++) vr_cube_grow<<<blocks16, 256, 0, stream>>>(E, bits, r);
         vr_cube_finish<<<blocks8, 256, 0, stream>>>(grid, cell, E, g, bits, tables);
         if (launches) *launches += 3 + (cap > 1 ? cap - 1 : 0);
     } else {
@@ -697,7 +745,7 @@ __global__ void vr_col_bricks(const int32_t *__restrict__ lo, const int32_t *__r
             const int z0 = a[c] > 4 * bz ? a[c] : 4 * bz, z1 = b[c] < 4 * bz + 3 ? b[c] : 4 * bz + 3;
             for (int z = z0; z <= z1; z++) m |= 1ull << (c + 16 * (z - 4 * bz));
         }
-        keys[at] = m ? brick_key(bx, by, (unsigned)bz, digits) : 0xffffffffu;
+        keys[at] = m ? brick_key(bx, by, (unsigned)bz, digits, 0) : 0xffffffffu;
         masks[at] = m;
     }
 }
