@@ -77,29 +77,42 @@ class ClockSampler:
     def __init__(self, index: int) -> None:
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
-    def _run_nvml(self) -> bool:
-        """fast path: NVML in-process (sub-millisecond per sample), same counters as the nvidia-smi recipe"""
+    def _open_nvml(self) -> bool:
+        """NVML in-process (sub-millisecond per sample), same counters as the nvidia-smi recipe; opened BEFORE the timed region
+        starts (nvmlInit takes longer than a short timed region), so that the first sample falls inside it"""
         try:
             import pynvml as N
 
             N.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            h = N.nvmlDeviceGetHandleByIndex(phys)
-            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            self._nvml, self._h = N, N.nvmlDeviceGetHandleByIndex(phys)
+            self._mx = N.nvmlDeviceGetMaxClockInfo(self._h, N.NVML_CLOCK_SM)
+            return True
+        except Exception:
+            self._nvml = None
+            return False
+
+    def _run_nvml(self) -> bool:
+        N = getattr(self, "_nvml", None)
+        if N is None:
+            return False
+        try:
+            h, mx = self._h, self._mx
             bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
             order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            while not self._stop.is_set():
+            while True:
                 sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
                 try:
                     reasons = N.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append([str(sm), str(mx)] + ["Active" if reasons & bits[k] else "Not Active" for k in order])
-                self._stop.wait(0.005)
+                if self._stop.wait(0.001):
+                    break
             return True
         except Exception:
-            return False
+            return bool(self.samples)
 
     def _run(self) -> None:
         if self._run_nvml():
@@ -115,6 +128,7 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def __enter__(self):
+        self._open_nvml()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self

@@ -386,10 +386,12 @@ __global__ void vr_grid_finish(uint32_t *grid, const uint8_t *cell, int g, unsig
 }
 
 /* ---- directed top grids (vr_octree.cpp: vr_native_grid_directed): eight tables, one per direction octant ----------
- * E[o][b] = edge (blocks) of the largest empty cube with block b in its rear corner that extends along octant o's
- * direction of travel, by the 3-D maximal-square recurrence run as VR_GRID_MAX_CUBE - 1 relaxation launches: in launch r
- * a block of edge r whose seven forward neighbours all have edge >= r gets r + 1.  In place: a neighbour raised in the
- * same launch still passes the test, one below r never does, so the result does not depend on the order. */
+ * E[o][b] = edge (blocks, capped) of the largest empty cube with block b in its rear corner that extends along octant o's
+ * direction of travel: the 3-D maximal-square recurrence E(b) = min(cap, 1 + min E(b + d)), d in {0,1}^3 \ 0 forward.
+ * Every forward neighbour has a larger coordinate sum, so the recurrence is evaluated in ONE pass over the anti-diagonal
+ * planes kx + ky + kz = 3(G-1) .. 0 of the mirrored coordinates, one launch per plane for all eight octants (766 small
+ * launches at G = 256: ~4 ms; a relaxation "raise every block whose neighbours allow it, 63 times" read the neighbours of
+ * every open-sky block in every launch and took 46 ms). */
 __global__ void vr_cube_init(const uint32_t *__restrict__ base, unsigned n, uint8_t *__restrict__ E) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -398,44 +400,31 @@ __global__ void vr_cube_init(const uint32_t *__restrict__ base, unsigned n, uint
     for (int o = 0; o < 8; o++) E[(size_t)o * n + i] = v;
 }
 
-__device__ __forceinline__ void cube_grow_one(uint8_t *E, int bits, unsigned r, unsigned t) {
-    const unsigned n = 1u << (3 * bits), G = 1u << bits;
-    const unsigned o = t >> (3 * bits), i = t & (n - 1u);
-    const unsigned bx = i & (G - 1u), by = (i >> bits) & (G - 1u), bz = i >> (2 * bits);
-    const int sx = (o & 1u) ? -1 : 1, sy = (o & 2u) ? -1 : 1, sz = (o & 4u) ? -1 : 1;
-    /* the forward neighbours must exist: mirrored coordinate below G - 1 on every axis */
-    if (bx == ((o & 1u) ? 0u : G - 1u) || by == ((o & 2u) ? 0u : G - 1u) || bz == ((o & 4u) ? 0u : G - 1u)) return;
-    const volatile uint8_t *Eo = E + (size_t)o * n;
+/* one anti-diagonal plane kx + ky + kz = sum of the mirrored block coordinates, all eight octants: every forward
+ * neighbour of a block on it lies on one of the three planes behind (sum + 1 .. sum + 3), which are final */
+__global__ void vr_cube_plane(uint8_t *E, int bits, int sum, unsigned cap) {
+    const unsigned G = 1u << bits, n = 1u << (3 * bits);
+    const unsigned kx = blockIdx.x * blockDim.x + threadIdx.x, ky = blockIdx.y, o = blockIdx.z;
+    const int kzs = sum - (int)kx - (int)ky;
+    if (kx >= G || kzs < 0 || kzs >= (int)G) return;
+    const unsigned kz = (unsigned)kzs;
+    const unsigned bx = (o & 1u) ? G - 1u - kx : kx, by = (o & 2u) ? G - 1u - ky : ky, bz = (o & 4u) ? G - 1u - kz : kz;
+    uint8_t *Eo = E + (size_t)o * n;
+    const unsigned i = bx + (by << bits) + (bz << (2 * bits));
+    if (Eo[i] == 0) return;                                              /* a block that holds voxels */
+    unsigned mn = cap;
+    if (kx == G - 1u || ky == G - 1u || kz == G - 1u) mn = 0;            /* a forward neighbour outside the map */
+    else {
+        const int sx = (o & 1u) ? -1 : 1, sy = (o & 2u) ? -1 : 1, sz = (o & 4u) ? -1 : 1;
 #pragma unroll
-    for (int d = 1; d < 8; d++) {
-        const unsigned j = (unsigned)((int)bx + ((d & 1) ? sx : 0)) + (((unsigned)((int)by + ((d & 2) ? sy : 0))) << bits) +
-                           (((unsigned)((int)bz + ((d & 4) ? sz : 0))) << (2 * bits));
-        if (Eo[j] < r) return;
+        for (int d = 1; d < 8; d++) {
+            const unsigned j = (unsigned)((int)bx + ((d & 1) ? sx : 0)) + (((unsigned)((int)by + ((d & 2) ? sy : 0))) << bits) +
+                               (((unsigned)((int)bz + ((d & 4) ? sz : 0))) << (2 * bits));
+            const unsigned e = Eo[j];
+            mn = e < mn ? e : mn;
+        }
     }
-    E[t] = (uint8_t)(r + 1u);
-}
-
-/* one thread per 16 consecutive entries (one 128-bit load): almost all of them are final already (edge != r) */
-__global__ void vr_cube_grow(uint8_t *E, int bits, unsigned r) {
-    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned total = 8u << (3 * bits);
-    const unsigned t0 = q * 16u;
-    if (t0 >= total) return;
-    if (total < 16u) {                                           /* (grids of 1^3: nothing can grow) */
-        for (unsigned t = 0; t < total; t++)
-            if (E[t] == r) cube_grow_one(E, bits, r, t);
-        return;
-    }
-    const uint4 v = *reinterpret_cast<const uint4 *>(E + t0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    const uint32_t rr = r * 0x01010101u;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t x = w[k] ^ rr;                            /* a zero byte = an entry with edge r */
-        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0u) continue;
-        for (int b = 0; b < 4; b++)
-            if (((w[k] >> (8 * b)) & 0xffu) == r) cube_grow_one(E, bits, r, t0 + 4u * k + b);
-    }
+    Eo[i] = (uint8_t)(mn + 1u > cap ? cap : mn + 1u);
 }
 
 __global__ void vr_cube_finish(const uint32_t *__restrict__ base, const uint8_t *__restrict__ cell, const uint8_t *__restrict__ E,
@@ -477,10 +466,11 @@ cudaError_t vr_build_grid_device(const vr_node *d_nodes, int levels, int dim, bo
         const unsigned blocks8 = (unsigned)(((size_t)8 * n + 255) / 256);
         const unsigned cap = (unsigned)G < VR_GRID_MAX_CUBE ? (unsigned)G : VR_GRID_MAX_CUBE;
         vr_cube_init<<<blocks, 256, 0, stream>>>(grid, n, E);
-        const unsigned blocks16 = (unsigned)(((size_t)8 * n / 16 + 255) / 256) + 1u;
-        for (unsigned r = 1; r < cap; r++) vr_cube_grow<<<blocks16, 256, 0, stream>>>(E, bits, r);
+        /* E(b) = min(cap, 1 + min over the 7 forward neighbours): one pass, plane by plane from the far corner */
+        const dim3 pgrid(((unsigned)G + 63u) / 64u, (unsigned)G, 8u);
+        for (int sum = 3 * (G - 1); sum >= 0; sum--) vr_cube_plane<<<pgrid, 64, 0, stream>>>(E, bits, sum, cap);
         vr_cube_finish<<<blocks8, 256, 0, stream>>>(grid, cell, E, g, bits, tables);
-        if (launches) *launches += 3 + (cap > 1 ? cap - 1 : 0);
+        if (launches) *launches += 3 + (unsigned long long)(3 * (G - 1) + 1);
     } else {
         const int rmax = G / 2 < 63 ? G / 2 : 63;                        /* a cube of radius r inside the grid needs G >= 2r + 1 */
         for (int r = 1; r <= rmax; r++) vr_grid_erode<<<blocks, 256, 0, stream>>>(grid, G, (uint32_t)r);
