@@ -68,55 +68,50 @@ def bench_scene(config: str = "c3", with_volume: bool = True, lights: int = 1):
     return S.make_scene(config, camera_index=BENCH_CAMERA, lights=lights)
 
 
+_SAMPLER_CHILD = r"""
+import sys, time
+idx = int(sys.argv[1])
+try:
+    import os
+    import pynvml as N
+    N.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(vis.split(",")[idx]) if vis and vis.split(",")[idx].isdigit() else idx
+    h = N.nvmlDeviceGetHandleByIndex(phys)
+    mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+except Exception as e:
+    print("nvml-failed", e, flush=True)
+    sys.exit(0)
+print("ready", flush=True)
+import select
+bits = [0x8, 0x40, 0x20, 0x4]     # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+out = []
+while True:
+    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    try:
+        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    out.append("%d,%d,%s" % (sm, mx, ",".join("Active" if r & b else "Not Active" for b in bits)))
+    if select.select([sys.stdin], [], [], 0.001)[0]:
+        break
+print("\n".join(out), flush=True)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the nvidia-smi counters, read
+    through NVML every millisecond).  The sampler is a CHILD PROCESS started -- and NVML opened -- before the timed region: a
+    thread of this process would have to fight the launch loop for the interpreter lock (one sample in an 18 ms region),
+    and nvmlInit alone takes longer than a short timed region.  Falls back to polling nvidia-smi from a thread."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int) -> None:
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
-
-    def _open_nvml(self) -> bool:
-        """NVML in-process (sub-millisecond per sample), same counters as the nvidia-smi recipe; opened BEFORE the timed region
-        starts (nvmlInit takes longer than a short timed region), so that the first sample falls inside it"""
-        try:
-            import pynvml as N
-
-            N.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            self._nvml, self._h = N, N.nvmlDeviceGetHandleByIndex(phys)
-            self._mx = N.nvmlDeviceGetMaxClockInfo(self._h, N.NVML_CLOCK_SM)
-            return True
-        except Exception:
-            self._nvml = None
-            return False
-
-    def _run_nvml(self) -> bool:
-        N = getattr(self, "_nvml", None)
-        if N is None:
-            return False
-        try:
-            h, mx = self._h, self._mx
-            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
-            order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            while True:
-                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-                try:
-                    reasons = N.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append([str(sm), str(mx)] + ["Active" if reasons & bits[k] else "Not Active" for k in order])
-                if self._stop.wait(0.001):
-                    break
-            return True
-        except Exception:
-            return bool(self.samples)
+        self.index, self.samples, self._stop, self._t, self._child = index, [], threading.Event(), None, None
 
     def _run(self) -> None:
-        if self._run_nvml():
-            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
@@ -128,12 +123,27 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def __enter__(self):
-        self._open_nvml()
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._child = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(self.index)], stdin=subprocess.PIPE,
+                                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self._child.stdout.readline().strip() != "ready":          # blocks until NVML is open in the child
+                self._child.kill()
+                self._child = None
+        except Exception:
+            self._child = None
+        if self._child is None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *exc) -> None:
+        if self._child is not None:
+            try:
+                out, _ = self._child.communicate("stop\n", timeout=10)
+                self.samples = [line.split(",") for line in out.splitlines() if line.count(",") >= 5]
+            except Exception:
+                self._child.kill()
+            return
         self._stop.set()
         self._t.join(timeout=10)
 
