@@ -123,6 +123,15 @@ struct NonZero {
 struct IsSolidFlag {
     __host__ __device__ uint32_t operator()(uint8_t v) const { return v != 0xFF ? 1u : 0u; }
 };
+struct PopCount64 {
+    __host__ __device__ unsigned long long operator()(unsigned long long m) const {
+#if defined(__CUDA_ARCH__)
+        return (unsigned long long)__popcll(m);
+#else
+        return (unsigned long long)__builtin_popcountll(m);
+#endif
+    }
+};
 struct PopCount {
     __host__ __device__ uint32_t operator()(unsigned long long m) const {
 #if defined(__CUDA_ARCH__)
@@ -249,7 +258,7 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
     VRB(cudaMalloc(&prefix, nkeys_all * sizeof(uint32_t)));
     VRB(cudaMalloc(&vox_prefix, nleaf * sizeof(uint32_t)));
     VRB(cudaMalloc(&d_totals, (VR_MAX_LEVELS + 1) * sizeof(uint32_t)));
-    VRB(cudaMalloc(&d_off, 2 * (VR_MAX_LEVELS + 1) * sizeof(unsigned long long)));
+    VRB(cudaMalloc(&d_off, (2 * (VR_MAX_LEVELS + 1) + 1) * sizeof(unsigned long long)));     /* offsets, key counts, one sum */
     VRB(cudaMemcpyAsync(d_off, off, 2 * (VR_MAX_LEVELS + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     size_t tmp_bytes = 0;
     {
@@ -285,6 +294,20 @@ cudaError_t vr_build_tree_device(const int8_t *d_map, int dim, cudaStream_t stre
         auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[L - 1]), PopCount());
         size_t need = tmp_bytes;
         VRB(cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, vox_prefix, (int)nleaf, stream));
+    }
+    {
+        /* child_base / leaf_types positions are 32-bit: a map with 2^32 or more solid voxels cannot be represented */
+        auto it = thrust::make_transform_iterator((const unsigned long long *)(masks + off[L - 1]), PopCount64());
+        size_t need = 0;
+        unsigned long long *d_sum = d_off + 2 * (VR_MAX_LEVELS + 1);
+        VRB(cub::DeviceReduce::Sum(nullptr, need, it, d_sum, (int)nleaf, stream));
+        if (need > tmp_bytes) { cudaFree(scan_tmp); scan_tmp = nullptr; tmp_bytes = need; VRB(cudaMalloc(&scan_tmp, tmp_bytes)); }
+        need = tmp_bytes;
+        VRB(cub::DeviceReduce::Sum(scan_tmp, need, it, d_sum, (int)nleaf, stream));
+        unsigned long long total = 0;
+        VRB(cudaMemcpyAsync(&total, d_sum, sizeof(total), cudaMemcpyDeviceToHost, stream));
+        VRB(cudaStreamSynchronize(stream));
+        if (total > 0xFFFFFFFFull) { cleanup(); return cudaErrorInvalidValue; }
     }
     vr_level_totals<<<1, 32, 0, stream>>>(masks, prefix, vox_prefix, d_off, L, d_totals);
     if (launches) ++*launches;

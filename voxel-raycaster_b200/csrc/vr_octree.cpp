@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <stdexcept>
 
 namespace {
 
@@ -173,6 +174,8 @@ void pyramid_emit(Pyramid &p, int dim, const std::function<uint8_t(int, int, int
         cur.swap(next);
     }
     if (out.leaf_types.empty()) out.leaf_types.push_back(0);   /* keep the device buffer non-empty */
+    if (out.leaf_types.size() > 0xFFFFFFFFull || out.nodes.size() > 0x7FFFFFFFull)
+        throw std::length_error("64-tree: more solid voxels or nodes than its 32-bit child pointers can address");
 }
 
 }  // namespace
