@@ -68,50 +68,65 @@ def bench_scene(config: str = "c3", with_volume: bool = True, lights: int = 1):
     return S.make_scene(config, camera_index=BENCH_CAMERA, lights=lights)
 
 
-_SAMPLER_CHILD = r"""
-import sys, time
-idx = int(sys.argv[1])
-try:
-    import os
-    import pynvml as N
-    N.nvmlInit()
-    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-    phys = int(vis.split(",")[idx]) if vis and vis.split(",")[idx].isdigit() else idx
-    h = N.nvmlDeviceGetHandleByIndex(phys)
-    mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
-except Exception as e:
-    print("nvml-failed", e, flush=True)
-    sys.exit(0)
-print("ready", flush=True)
-import select
-bits = [0x8, 0x40, 0x20, 0x4]     # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
-out = []
-while True:
-    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-    try:
-        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
-    except Exception:
-        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-    out.append("%d,%d,%s" % (sm, mx, ",".join("Active" if r & b else "Not Active" for b in bits)))
-    if select.select([sys.stdin], [], [], 0.001)[0]:
-        break
-print("\n".join(out), flush=True)
-"""
-
-
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the nvidia-smi counters, read
-    through NVML every millisecond).  The sampler is a CHILD PROCESS started -- and NVML opened -- before the timed region: a
-    thread of this process would have to fight the launch loop for the interpreter lock (one sample in an 18 ms region),
-    and nvmlInit alone takes longer than a short timed region.  Falls back to polling nvidia-smi from a thread."""
+    through NVML in-process, sub-millisecond per sample).  NVML is opened BEFORE the timed region starts (nvmlInit takes
+    longer than a short timed region).  Clock queries are not free: polling every millisecond from one process per rank slowed
+    the kernels of an 8-GPU run down by an order of magnitude (profiles/r2c_scale8_*: per-rank frame times 0.09 .. 2.6 ms
+    instead of 0.09; with 4 ranks 10 %; one process and one GPU: no effect).  Hence: 5 ms interval; at N > 1 only rank 0
+    samples, its first query one interval after the start, and the clocks under load are (also) sampled over an UNTIMED
+    continuation of the same frames right after the timed region (run_mgpu)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    INTERVAL_S = 0.005
 
-    def __init__(self, index: int) -> None:
-        self.index, self.samples, self._stop, self._t, self._child = index, [], threading.Event(), None, None
+    def __init__(self, index: int, enabled: bool = True, delay_first: bool = False) -> None:
+        """enabled = False: a no-op (N > 1: only rank 0 samples).  delay_first: the first sample is taken one interval after
+        the start instead of at once (N > 1: a region shorter than the interval then sees no query at all)."""
+        self.index, self.samples, self._stop, self._t, self._nvml = index, [], threading.Event(), None, None
+        self.enabled, self.delay_first = enabled, delay_first
+
+    def _open_nvml(self) -> bool:
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self._h = N.nvmlDeviceGetHandleByIndex(phys)
+            self._mx = N.nvmlDeviceGetMaxClockInfo(self._h, N.NVML_CLOCK_SM)
+            self._nvml = N
+            return True
+        except Exception:
+            self._nvml = None
+            return False
+
+    def _run_nvml(self) -> bool:
+        N = self._nvml
+        if N is None:
+            return False
+        try:
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            if self.delay_first and self._stop.wait(self.INTERVAL_S):
+                return True
+            while True:
+                sm = N.nvmlDeviceGetClockInfo(self._h, N.NVML_CLOCK_SM)
+                try:
+                    reasons = N.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    reasons = N.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append([str(sm), str(self._mx)] + ["Active" if reasons & bits[k] else "Not Active" for k in order])
+                if self._stop.wait(self.INTERVAL_S):
+                    break
+            return True
+        except Exception:
+            return bool(self.samples)
 
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
@@ -123,29 +138,16 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def __enter__(self):
-        try:
-            self._child = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(self.index)], stdin=subprocess.PIPE,
-                                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            if self._child.stdout.readline().strip() != "ready":          # blocks until NVML is open in the child
-                self._child.kill()
-                self._child = None
-        except Exception:
-            self._child = None
-        if self._child is None:
+        if self.enabled:
+            self._open_nvml()
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
 
     def __exit__(self, *exc) -> None:
-        if self._child is not None:
-            try:
-                out, _ = self._child.communicate("stop\n", timeout=10)
-                self.samples = [line.split(",") for line in out.splitlines() if line.count(",") >= 5]
-            except Exception:
-                self._child.kill()
-            return
         self._stop.set()
-        self._t.join(timeout=10)
+        if self._t is not None:
+            self._t.join(timeout=10)
 
     def summary(self) -> dict:
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
@@ -353,7 +355,7 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     barrier()
     l0 = c.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             must(c.compute_views(mine, frames.data_ptr()), "compute_views")
@@ -490,7 +492,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     barrier()
     launches0 = c.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=True) as clocks:
         ev0.record(stream)
         last, ptr = frames(args.steps)
         ev1.record(stream)
@@ -507,6 +509,14 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     per_rank_ms = [round(float(t.item()) / args.steps, 4) for t in per_rank]
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
+    # clocks under load: the timed region is a few milliseconds and NVML queries during it perturb the ranks (ClockSampler),
+    # so rank 0 samples over an untimed continuation of the same frames (>= 60 ms of them)
+    load_frames = max(args.steps, int(60.0 / max(ms_per_step, 1e-3)))
+    with ClockSampler(local_rank, enabled=(rank == 0)) as load_clocks:
+        last, ptr = frames(load_frames)
+        barrier()
+    c.mgpu_frame_release(last)
+    clocks.samples += load_clocks.samples
     must(c.mgpu_shutdown(), "mgpu_shutdown")
 
     # ---- end to end with the result in HOST memory: every rank copies its bands into a shared pinned host frame
@@ -554,6 +564,8 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                                       "1 launch per frame and rank (the completion counter is a stream memory operation, cuStreamWriteValue64)",
                        "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
                        "per_rank_ms_per_frame": per_rank_ms,
+                       "clock_sampling": f"rank 0 only, 5 ms interval, first query 5 ms into the timed region; plus an untimed continuation of {load_frames} "
+                                         "frames right after it (NVML queries from every rank during a timed region of a few ms slow the kernels down: ClockSampler)",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
@@ -738,7 +750,7 @@ def main() -> None:
     launches0 = c.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)) as clocks:
         ev0.record(stream)
         for i in range(args.steps):
             if pipe:
@@ -785,7 +797,7 @@ def main() -> None:
     if world == 1:
         n_sus = max(args.steps, int(0.6e3 / max(ms_per_step, 1e-3)))
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as sus_clocks:
+        with ClockSampler(local_rank, enabled=(rank == 0)) as sus_clocks:
             s0.record(stream)
             for _ in range(n_sus):
                 must(c.compute_into(slab.data_ptr()), "compute_into")
