@@ -70,12 +70,14 @@ def bench_scene(config: str = "c3", with_volume: bool = True, lights: int = 1):
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the nvidia-smi counters, read
-    through NVML in-process, sub-millisecond per sample).  NVML is opened BEFORE the timed region starts (nvmlInit takes
-    longer than a short timed region).  Clock queries are not free: polling every millisecond from one process per rank slowed
-    the kernels of an 8-GPU run down by an order of magnitude (profiles/r2c_scale8_*: per-rank frame times 0.09 .. 2.6 ms
-    instead of 0.09; with 4 ranks 10 %; one process and one GPU: no effect).  Hence: 5 ms interval; at N > 1 only rank 0
-    samples, its first query one interval after the start, and the clocks under load are (also) sampled over an UNTIMED
-    continuation of the same frames right after the timed region (run_mgpu)."""
+    through NVML in-process, sub-millisecond per sample, every 5 ms).
+    `prepare()` opens NVML and MUST be called before the barrier that precedes the timed region: nvmlInit takes 10+ ms, and
+    anything a rank does between that barrier and its first launch skews the ranks against each other -- the other ranks run
+    into the scheduler's frame ring and wait, inside their timed regions (measured: with the set-up after the barrier, and
+    one sampler process per rank, an 8-GPU run showed per-rank frame times of 0.09 .. 2.6 ms instead of 0.09,
+    profiles/r2c_scale8_*; with NVML opened by rank 0 only, rank 1 of 2 lost 11 ms, profiles/r2c_check_c3_n2.json).
+    Entering the context only starts the sampling thread.  At N > 1 only rank 0 samples, and the clocks under load are also
+    sampled over an untimed continuation of the same frames (run_mgpu), because the timed region is a few milliseconds."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -100,6 +102,7 @@ class ClockSampler:
             return True
         except Exception:
             self._nvml = None
+            self._tried = True
             return False
 
     def _run_nvml(self) -> bool:
@@ -137,9 +140,16 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
+    def prepare(self):
+        """opens NVML (slow): call BEFORE the barrier in front of the timed region"""
+        if self.enabled and self._nvml is None:
+            self._open_nvml()
+        return self
+
     def __enter__(self):
         if self.enabled:
-            self._open_nvml()
+            if self._nvml is None and not getattr(self, "_tried", False):
+                self._open_nvml()                     # (not prepared: still works, but skews this rank's start)
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
@@ -352,10 +362,11 @@ def run_views(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
 
     for _ in range(args.warmup):
         must(c.compute_views(mine, frames.data_ptr()), "compute_views")
+    sampler = ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)).prepare()      # NVML opened before the barrier
     barrier()
     l0 = c.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)) as clocks:
+    with sampler as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             must(c.compute_views(mine, frames.data_ptr()), "compute_views")
@@ -489,10 +500,13 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
 
     last, ptr = frames(args.warmup)
     c.mgpu_frame_release(last)
-    barrier()
-    launches0 = c.stats().kernel_launches
+    # everything slow happens BEFORE the barrier: what a rank does between the barrier and its first launch makes the other
+    # ranks wait for it at the scheduler's frame ring, inside their timed regions (ClockSampler)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0), delay_first=True).prepare()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=True) as clocks:
+    launches0 = c.stats().kernel_launches
+    barrier()
+    with sampler as clocks:
         ev0.record(stream)
         last, ptr = frames(args.steps)
         ev1.record(stream)
@@ -509,10 +523,10 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     per_rank_ms = [round(float(t.item()) / args.steps, 4) for t in per_rank]
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
-    # clocks under load: the timed region is a few milliseconds and NVML queries during it perturb the ranks (ClockSampler),
-    # so rank 0 samples over an untimed continuation of the same frames (>= 60 ms of them)
+    # clocks under load: the timed region is a few milliseconds (one or two 5 ms samples at best), so rank 0 also samples
+    # over an untimed continuation of the same frames (>= 60 ms of them)
     load_frames = max(args.steps, int(60.0 / max(ms_per_step, 1e-3)))
-    with ClockSampler(local_rank, enabled=(rank == 0)) as load_clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)).prepare() as load_clocks:
         last, ptr = frames(load_frames)
         barrier()
     c.mgpu_frame_release(last)
@@ -565,7 +579,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                        "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
                        "per_rank_ms_per_frame": per_rank_ms,
                        "clock_sampling": f"rank 0 only, 5 ms interval, first query 5 ms into the timed region; plus an untimed continuation of {load_frames} "
-                                         "frames right after it (NVML queries from every rank during a timed region of a few ms slow the kernels down: ClockSampler)",
+                                         "frames right after it (the timed region of a multi-GPU run is a few milliseconds)",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
@@ -746,11 +760,12 @@ def main() -> None:
         pipe.step() if pipe else render_step()
     if pipe:
         pipe.drain()
-    barrier()
-    launches0 = c.stats().kernel_launches
+    sampler = ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)).prepare()      # NVML opened before the barrier
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank, enabled=(rank == 0), delay_first=(world > 1)) as clocks:
+    barrier()
+    launches0 = c.stats().kernel_launches
+    with sampler as clocks:
         ev0.record(stream)
         for i in range(args.steps):
             if pipe:
@@ -797,7 +812,7 @@ def main() -> None:
     if world == 1:
         n_sus = max(args.steps, int(0.6e3 / max(ms_per_step, 1e-3)))
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank, enabled=(rank == 0)) as sus_clocks:
+        with ClockSampler(local_rank, enabled=(rank == 0)).prepare() as sus_clocks:
             s0.record(stream)
             for _ in range(n_sus):
                 must(c.compute_into(slab.data_ptr()), "compute_into")
