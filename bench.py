@@ -71,12 +71,13 @@ def bench_scene(config: str = "c3", with_volume: bool = True, lights: int = 1):
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe: the nvidia-smi counters, read
     through NVML in-process, sub-millisecond per sample, every 5 ms).
-    `prepare()` opens NVML and MUST be called before the barrier that precedes the timed region: nvmlInit takes 10+ ms, and
+    `prepare()` opens NVML, starts the (parked) sampling thread and MUST be called before the barrier that precedes the
+    timed region: nvmlInit takes 10+ ms, a Python thread 0.1 ms to start, and
     anything a rank does between that barrier and its first launch skews the ranks against each other -- the other ranks run
     into the scheduler's frame ring and wait, inside their timed regions (measured: with the set-up after the barrier, and
     one sampler process per rank, an 8-GPU run showed per-rank frame times of 0.09 .. 2.6 ms instead of 0.09,
     profiles/r2c_scale8_*; with NVML opened by rank 0 only, rank 1 of 2 lost 11 ms, profiles/r2c_check_c3_n2.json).
-    Entering the context only starts the sampling thread.  At N > 1 only rank 0 samples, and the clocks under load are also
+    Entering the context only sets the event the thread waits for.  At N > 1 only rank 0 samples, and the clocks under load are also
     sampled over an untimed continuation of the same frames (run_mgpu), because the timed region is a few milliseconds."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -87,6 +88,7 @@ class ClockSampler:
         """enabled = False: a no-op (N > 1: only rank 0 samples).  delay_first: the first sample is taken one interval after
         the start instead of at once (N > 1: a region shorter than the interval then sees no query at all)."""
         self.index, self.samples, self._stop, self._t, self._nvml = index, [], threading.Event(), None, None
+        self._go = threading.Event()              # set on entering the context: the thread exists (parked) before that
         self.enabled, self.delay_first = enabled, delay_first
 
     def _open_nvml(self) -> bool:
@@ -128,6 +130,9 @@ class ClockSampler:
             return bool(self.samples)
 
     def _run(self) -> None:
+        self._go.wait()
+        if self._stop.is_set():
+            return
         if self._run_nvml():
             return
         while not self._stop.is_set():
@@ -141,21 +146,23 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def prepare(self):
-        """opens NVML (slow): call BEFORE the barrier in front of the timed region"""
-        if self.enabled and self._nvml is None:
-            self._open_nvml()
-        return self
-
-    def __enter__(self):
-        if self.enabled:
+        """opens NVML (10+ ms) and starts the sampling thread, parked (thread start-up: 0.1 ms): call BEFORE the barrier in
+        front of the timed region.  Entering the context then only sets an event."""
+        if self.enabled and self._t is None:
             if self._nvml is None and not getattr(self, "_tried", False):
-                self._open_nvml()                     # (not prepared: still works, but skews this rank's start)
+                self._open_nvml()
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
 
+    def __enter__(self):
+        self.prepare()                                # (not prepared: still works, but skews this rank's start)
+        self._go.set()
+        return self
+
     def __exit__(self, *exc) -> None:
         self._stop.set()
+        self._go.set()
         if self._t is not None:
             self._t.join(timeout=10)
 
@@ -506,6 +513,10 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = c.stats().kernel_launches
     barrier()
+    # the ranks leave the NCCL barrier + device synchronize some tens of microseconds apart; the scheduler's own CPU
+    # rendezvous on the shared segment aligns them to about a microsecond (best effort: its result is not checked --
+    # a timed region of 20 frames at 8 GPUs is under 2 ms, and a rank that starts late costs the others that time)
+    c.mgpu_barrier()
     with sampler as clocks:
         ev0.record(stream)
         last, ptr = frames(args.steps)
@@ -538,11 +549,13 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     last, ptr = frames(args.warmup)
     c.mgpu_frame_release(last)
     barrier()
+    c.mgpu_barrier()
     t0 = time.perf_counter()
-    last, ptr = frames(args.steps)
+    last, ptr = frames(args.steps)                      # returns on the root when every rank's bands of the last frame are in host memory
     torch.cuda.synchronize()
+    t1 = time.perf_counter()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)      # per rank: aligned start -> its frames done; MAX = the root's
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
     checksum = 0

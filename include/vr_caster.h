@@ -226,6 +226,11 @@ int vr_push_bands(vr_ctx *ctx, const void *slab, void *frame, void *cuda_stream)
  *   vr_mgpu_flush           makes the context's stream (vr_set_stream) wait for the frames enqueued so far: consecutive frames
  *                           run on two alternating streams of the scheduler (the next frame's first CTAs fill the tail
  *                           of the current one), host-frame copies on a third.
+ *   vr_mgpu_barrier         collective, CPU only: returns when every rank has called it (a spin on the shared segment; the
+ *                           ranks leave it within a microsecond of each other).  Enqueues nothing and waits for no
+ *                           stream.  For a frame loop that must start on all GPUs at the same instant (a benchmark's
+ *                           timed region, a scene change): a rank that starts late makes the others wait at the frame
+ *                           ring.
  *   vr_mgpu_shutdown        collective.
  * Completion is signalled through per-rank counters in the shared segment, stored by the device after the rank's kernel
  * and polled by the CPU with time-outs: no per-frame collective.  All calls return 1 on success, 0 + last error. */
@@ -236,6 +241,7 @@ int vr_mgpu_frame(vr_ctx *ctx, uint64_t *frame_no);
 int vr_mgpu_frame_wait(vr_ctx *ctx, uint64_t frame_no, const uint8_t **rgba);
 int vr_mgpu_frame_release(vr_ctx *ctx, uint64_t frame_no);
 int vr_mgpu_flush(vr_ctx *ctx);        /* the context's stream waits for every frame enqueued so far (they run on the scheduler's own streams) */
+int vr_mgpu_barrier(vr_ctx *ctx);
 int vr_mgpu_shutdown(vr_ctx *ctx);
 
 /* Page-locks host memory the caller owns (e.g. a frame in a POSIX shared-memory segment mapped by every rank) so

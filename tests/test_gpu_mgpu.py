@@ -40,6 +40,7 @@ def test_scheduler_world_1(pkg, host_frame):
     flags = c.MGPU_HOST_FRAME if host_frame else 0
     assert c.mgpu_init(f"t1_{os.getpid()}_{int(host_frame)}", 1, 0, flags), c.last_error()
     assert c.mgpu_broadcast_octree(), c.last_error()
+    assert c.mgpu_barrier(), c.last_error()              # CPU rendezvous of the ranks (a world of one: returns at once)
     h, w = scene.height, scene.width
     for i in range(7):                                   # more frames than the ring holds
         k = c.mgpu_frame()
@@ -76,6 +77,7 @@ WORKER = textwrap.dedent("""
     assert c.mgpu_init(session, world, rank, host), c.last_error()
     assert c.mgpu_broadcast_octree(), c.last_error()
     assert c.validate(), c.last_error()
+    assert c.mgpu_barrier(), c.last_error()
     frames = []
     for i in range(5):
         k = c.mgpu_frame(); assert k == i, c.last_error()

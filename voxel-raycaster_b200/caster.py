@@ -95,6 +95,7 @@ SYMBOLS = {
     "vr_mgpu_frame_wait": (_i, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "vr_mgpu_frame_release": (_i, [_vp, C.c_uint64]),
     "vr_mgpu_flush": (_i, [_vp]),
+    "vr_mgpu_barrier": (_i, [_vp]),
     "vr_mgpu_shutdown": (_i, [_vp]),
     "vr_assign_native_tree": (_i, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int32, C.c_int32]),
     "vr_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -382,6 +383,10 @@ class CUDACaster:
 
     def mgpu_flush(self) -> bool:
         return bool(self._lib.vr_mgpu_flush(self._ctx))
+
+    def mgpu_barrier(self) -> bool:
+        """collective, CPU only: every rank leaves within a microsecond of the others (spin on the shared segment)"""
+        return bool(self._lib.vr_mgpu_barrier(self._ctx))
 
     def mgpu_shutdown(self) -> bool:
         return bool(self._lib.vr_mgpu_shutdown(self._ctx))

@@ -107,6 +107,7 @@ public:
     bool mgpu_frame(uint64_t *frame_no) { return vr_mgpu_frame(ctx_, frame_no) != 0; }
     bool mgpu_frame_wait(uint64_t frame_no, const uint8_t **rgba) { return vr_mgpu_frame_wait(ctx_, frame_no, rgba) != 0; }
     bool mgpu_frame_release(uint64_t frame_no) { return vr_mgpu_frame_release(ctx_, frame_no) != 0; }
+    bool mgpu_barrier() { return vr_mgpu_barrier(ctx_) != 0; }
     bool mgpu_shutdown() { return vr_mgpu_shutdown(ctx_) != 0; }
 
     const char *last_error() const { return vr_last_error(ctx_); }

@@ -469,6 +469,14 @@ int vr_mgpu_frame_release(vr_ctx *c, uint64_t frame_no) {
     return 1;
 }
 
+int vr_mgpu_barrier(vr_ctx *c) {
+    if (!c || !c->mgpu) return c ? vr_i_fail(c, "mgpu_barrier: call mgpu_init first") : 0;
+    /* the bootstrap barrier of the shared segment (one generation counter per rank, spun on by the CPU): the ranks leave
+     * it within a cache-line transfer of each other.  Nothing is enqueued and no stream is waited for. */
+    if (!barrier(c->mgpu, 30.0)) return vr_i_fail(c, "mgpu_barrier: a rank did not arrive within 30 s");
+    return 1;
+}
+
 int vr_mgpu_shutdown(vr_ctx *c) {
     if (!c || !c->mgpu) return 0;
     vr_mgpu *m = c->mgpu;
