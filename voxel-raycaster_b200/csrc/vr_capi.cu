@@ -455,7 +455,12 @@ int vr_create_viewport(vr_ctx *c, int width, int height, float v_fov, float h_fo
     c->width = width;
     c->height = height;
     std::vector<float> table;
-    make_ray_table(width, height, table);
+    try {                                                   /* (no exception may cross the C ABI) */
+        make_ray_table(width, height, table);
+    } catch (const std::exception &e) {
+        c->width = c->height = 0;
+        return fail(c, "create_viewport: %dx%d ray table: %s", width, height, e.what());
+    }
     const size_t tbytes = table.size() * sizeof(float), ibytes = (size_t)width * height * 4;
     VR_CUDA(c, cudaMalloc(&c->d_ray_table, tbytes));
     VR_CUDA(c, upload(c, c->d_ray_table, table.data(), tbytes));
@@ -635,7 +640,13 @@ int vr_assign_octree(vr_ctx *c, const uint64_t *descriptors, const uint32_t *att
     (void)attach_lookup; (void)attach;                     /* all zero in the reference (Octree.cpp:8-9) */
     if (!c) return 0;
     if (!descriptors || !entries || root_index >= entries) return fail(c, "assign_octree: bad arguments");
-    c->oct_desc.assign(descriptors, descriptors + entries);
+    try {                                                   /* (no exception may cross the C ABI) */
+        c->oct_desc.assign(descriptors, descriptors + entries);
+    } catch (const std::exception &e) {
+        c->oct_desc.clear();
+        c->has_octree = false;
+        return fail(c, "assign_octree: %llu entries: %s", (unsigned long long)entries, e.what());
+    }
     c->oct_root = root_index;
     c->has_octree = true;
     if (!c->tree_from_map) free_tree(c);                   /* re-import lazily at validate/compute */
@@ -1108,8 +1119,15 @@ int vr_octree_save(vr_ctx *c, const char *path) {
     if (!c || !path) return 0;
     if (!c->tree_valid && !ensure_tree(c)) return 0;
     cudaSetDevice(c->device);
-    std::vector<vr_node> nodes(c->n_nodes);
-    std::vector<uint8_t> types(c->n_leaf_types);
+    std::vector<vr_node> nodes;
+    std::vector<uint8_t> types;
+    try {                                                   /* (no exception may cross the C ABI) */
+        nodes.resize(c->n_nodes);
+        types.resize(c->n_leaf_types);
+    } catch (const std::exception &e) {
+        return fail(c, "octree_save: host copy of the tree: %s", e.what());
+    }
+    VR_CUDA(c, cudaStreamSynchronize(c->stream));           /* the tree may have just been built on the context's stream */
     VR_CUDA(c, cudaMemcpy(nodes.data(), c->d_nodes, nodes.size() * sizeof(vr_node), cudaMemcpyDeviceToHost));
     VR_CUDA(c, cudaMemcpy(types.data(), c->d_leaf_types, types.size(), cudaMemcpyDeviceToHost));
     FILE *f = fopen(path, "wb");
