@@ -517,6 +517,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     # rendezvous on the shared segment aligns them to about a microsecond (best effort: its result is not checked --
     # a timed region of 20 frames at 8 GPUs is under 2 ms, and a rank that starts late costs the others that time)
     c.mgpu_barrier()
+    t_start_ns = time.clock_gettime_ns(time.CLOCK_MONOTONIC)      # (system-wide clock: comparable between the ranks of a node)
     with sampler as clocks:
         ev0.record(stream)
         last, ptr = frames(args.steps)
@@ -536,12 +537,30 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
     ms_per_step = float(t_ms.item()) / args.steps
     # clocks under load: the timed region is a few milliseconds (one or two 5 ms samples at best), so rank 0 also samples
     # over an untimed continuation of the same frames (>= 60 ms of them)
+    # That continuation is timed as well (config.sustained: the same frames back to back, hundreds instead of K, so that the
+    # fill and drain of the frame pipeline and the start skew of the ranks do not weigh; rank 0 polls NVML during it).
     load_frames = max(args.steps, int(60.0 / max(ms_per_step, 1e-3)))
-    with ClockSampler(local_rank, enabled=(rank == 0)).prepare() as load_clocks:
+    load_sampler = ClockSampler(local_rank, enabled=(rank == 0)).prepare()
+    sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    c.mgpu_barrier()
+    with load_sampler as load_clocks:
+        sv0.record(stream)
         last, ptr = frames(load_frames)
+        sv1.record(stream)
         barrier()
     c.mgpu_frame_release(last)
     clocks.samples += load_clocks.samples
+    sus_ms = torch.tensor([sv0.elapsed_time(sv1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+    sustained = {"frames": load_frames, "ms_per_frame": float(sus_ms.item()) / load_frames,
+                 "how": "untimed continuation of the timed frames, CUDA events, MAX over ranks; rank 0 samples its clocks every 5 ms during it",
+                 "clocks": load_clocks.summary()}
+    # how far apart the ranks entered the timed region (CLOCK_MONOTONIC right after the alignment)
+    starts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(starts, torch.tensor([t_start_ns], dtype=torch.int64, device=dev))
+    starts = [int(t.item()) for t in starts]
+    start_skew_us = (max(starts) - min(starts)) / 1e3
     must(c.mgpu_shutdown(), "mgpu_shutdown")
 
     # ---- end to end with the result in HOST memory: every rank copies its bands into a shared pinned host frame
@@ -590,9 +609,9 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                                       "into the root GPU's frame over NVLink (CUDA IPC), device-stored completion counters polled by the root's CPU, 4 frame buffers; "
                                       "1 launch per frame and rank (the completion counter is a stream memory operation, cuStreamWriteValue64)",
                        "l2": "per-frame streams (ray table + image) exceed the 126 MB L2 at N = 1; the octree stays L2-resident by design",
-                       "per_rank_ms_per_frame": per_rank_ms,
-                       "clock_sampling": f"rank 0 only, 5 ms interval, first query 5 ms into the timed region; plus an untimed continuation of {load_frames} "
-                                         "frames right after it (the timed region of a multi-GPU run is a few milliseconds)",
+                       "per_rank_ms_per_frame": per_rank_ms, "start_skew_us": round(start_skew_us, 1), "sustained": sustained,
+                       "clock_sampling": f"rank 0 only, 5 ms interval, first query 5 ms into the timed region; plus a continuation of {load_frames} "
+                                         "frames right after it (config.sustained; the timed region of a multi-GPU run is a few milliseconds)",
                        "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
@@ -911,6 +930,24 @@ def main() -> None:
     e2e_ms = 1e3 * float(e2e_s.item()) / args.steps
     e2e_value = rays / (e2e_ms / 1e3) / 1e6
 
+    # what the end-to-end leg is bound by at N = 1: the same 4-byte-per-pixel frame copied device -> pinned host memory with
+    # nothing else running (a diagnostic next to e2e, outside every timed region; failure only drops the field)
+    d2h_alone = None
+    if world == 1 and host_frame is not None:
+        try:
+            src = slab[:H]
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(3 + 10):
+                if i == 3:
+                    d0.record(stream)
+                host_frame.copy_(src, non_blocking=True)
+            d1.record(stream)
+            torch.cuda.synchronize()
+            d2h_ms = d0.elapsed_time(d1) / 10
+            d2h_alone = {"ms_per_frame": d2h_ms, "gbs": W * H * 4 / (d2h_ms / 1e3) / 1e9}
+        except Exception as e:                       # noqa: BLE001
+            d2h_alone = {"error": str(e)[:200]}
+
     if rank == 0:
         peak, peak_how = measured_peak_gbs()
         ab = load_algorithmic_bytes(args.config, args.lights)
@@ -962,7 +999,7 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 5 * 4 + 10 * 4 + 64 * 8,
-                    "d2h_bytes_per_step": W * H * 4, "how": e2e_how},
+                    "d2h_bytes_per_step": W * H * 4, "how": e2e_how, "d2h_copy_alone": d2h_alone},
             "clocks": clocks.summary(),
         }
         print(json.dumps(out))
