@@ -75,3 +75,42 @@ def test_bench_defaults_are_the_contract():
     assert 'add_argument("--gpus", type=int, default=1)' in src
     assert "args.warmup = max(args.warmup, 3)" in src
     assert bench.METRIC.startswith("Mrays/s")
+
+
+REQUIRED_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                 "data", "gpu_launches", "config", "roofline", "cpu_baseline", "e2e", "clocks"}
+
+
+def _mock_bench(cmd_prefix, *flags, timeout=600):
+    r = subprocess.run([*cmd_prefix, str(ROOT / "tests" / "bench_mock_device.py"), "--config", "c1", "--steps", "6", "--warmup", "3", *flags],
+                       capture_output=True, text=True, timeout=timeout, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, f"exactly one JSON line on stdout, got {len(lines)}"
+    return json.loads(lines[0])
+
+
+def test_bench_control_flow_one_gpu_on_a_fake_device():
+    """bench.py's N = 1 path, start to JSON line, against tests/bench_mock_device.py (no rendering, virtual event clock): every
+    key of the contract is there, the step count is the launch count, the roofline and e2e objects are well-formed."""
+    j = _mock_bench([sys.executable])
+    assert REQUIRED_KEYS <= set(j), REQUIRED_KEYS - set(j)
+    assert j["n_gpus"] == 1 and j["steps"] == 6 and j["gpu_launches"] == 6 and j["ms_per_step"] == 0.5
+    assert j["config"]["workload"].startswith("c1:") and j["config"]["sustained"]["frames"] >= 6
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(j["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "d2h_copy_alone"} <= set(j["e2e"])
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+
+
+def test_bench_control_flow_two_ranks_on_a_fake_device():
+    """the N > 1 path (run_mgpu) under torch.distributed.run with two gloo ranks: the collectives match on both ranks, rank 0
+    alone prints the line, and it carries the per-rank times, the start skew after the alignment and the sustained leg."""
+    port = 29000 + os.getpid() % 2000
+    j = _mock_bench([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                     "--master-port", str(port)], "--gpus", "2")
+    assert REQUIRED_KEYS <= set(j), REQUIRED_KEYS - set(j)
+    assert j["n_gpus"] == 2 and j["steps"] == 6 and j["gpu_launches"] == 6
+    cfg = j["config"]
+    assert len(cfg["per_rank_ms_per_frame"]) == 2 and cfg["start_skew_us"] >= 0.0
+    assert cfg["sustained"]["frames"] >= 6 and cfg["sustained"]["ms_per_frame"] > 0
+    assert j["e2e"]["value"] > 0 and j["cpu_baseline"] is None
