@@ -612,7 +612,7 @@ def run_mgpu(args, pkg, torch, dist, rank, world, local_rank, dev) -> None:
                        "per_rank_ms_per_frame": per_rank_ms, "start_skew_us": round(start_skew_us, 1), "sustained": sustained,
                        "clock_sampling": f"rank 0 only, 5 ms interval, first query 5 ms into the timed region; plus a continuation of {load_frames} "
                                          "frames right after it (config.sustained; the timed region of a multi-GPU run is a few milliseconds)",
-                       "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
+                       "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow, "primary_mpix_per_s": primary / (ms_per_step / 1e3) / 1e6,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "octree_broadcast": "ncclBroadcast from rank 0 (vr_mgpu_broadcast_octree)", "scene_build_s": round(t_build, 2),
                        "dda_steps_per_frame": steps_total, "octree_lookups_per_frame": lookups, "frame_checksum": checksum, "device_frame_checksum": device_checksum},
@@ -986,7 +986,7 @@ def main() -> None:
                        "other_walk_ms_per_frame": other_walk_ms, "sustained": sustained,
                        "kernel_variant": (f"persistent warps, refill_min {args.refill_min}, {args.ctas_per_sm} CTAs/SM" if args.persistent else "static 32x4 tiles, 128-thread CTAs, 8 CTAs/SM"), "parallelism": (f"tiles{world}: 2-D interleave of 32x4-pixel tiles ((tx + ty) % {world}), every rank's kernel stores its pixels in place into the root's frame over NVLink (CUDA IPC mapping), 1-element NCCL all_reduce as frame-complete signal, 3 frame buffers" if args.gather == "direct" else f"tiles{world}: interleaved {BAND_ROWS}-row bands, {'copy-engine push over NVLink (CUDA IPC) + 1-element NCCL all_reduce' if args.gather == 'p2p' else 'NCCL all_gather'} of frame k overlapped with rendering of frame k+1") if world > 1 else "1 GPU",
                        "l2": "per-frame streams (ray table 133 MB + image 33 MB) exceed the 126 MB L2; the octree stays L2-resident by design",
-                       "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow,
+                       "rays_per_frame": rays, "primary_rays": primary, "shadow_rays": shadow, "primary_mpix_per_s": primary / (ms_per_step / 1e3) / 1e6,
                        "tree_nodes": int(st.native_nodes), "tree_bytes": int(st.native_bytes), "levels": int(st.levels),
                        "octree_broadcast_bytes": bcast_bytes, "scene_build_s": round(t_build, 2),
                        "octree_build": ({"where": "device (vr_build.cu) from the uploaded dense map", "ms": round(float(st.build_ms), 3),

@@ -31,7 +31,7 @@ int main() {
     // the multi-GPU frame loop of the library with a world of one: same frame, in shared host memory
     char session[64];
     std::snprintf(session, sizeof(session), "facade_%d", (int)getpid());
-    ok = c.mgpu_init(session, 1, 0, true) && c.mgpu_broadcast_octree();
+    ok = c.mgpu_init(session, 1, 0, true) && c.mgpu_broadcast_octree() && c.mgpu_barrier();
     for (int i = 0; ok && i < 6; i++) {
         uint64_t k = 0;
         const uint8_t *rgba = nullptr;
