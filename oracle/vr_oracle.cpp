@@ -335,10 +335,11 @@ void cast_pixel(const vro_scene *s, int px, int py, i3 bias, uint8_t *rgba, vro_
         Lc = {lp[0], lp[1], lp[2], lp[3]};
         alpha_before = color.w;
         color = view_light(color, hit_point - L, Lc, hit_point - cam, hit_normal);
-        distance_traveled = hit_steps + 1;                                /* as after the first redirect (kernel:714) */
+        distance_traveled = hit_steps;                                    /* a skipped pixel reports the counter of the hit's iteration, as at the first light (kernel:671) */
         max_distance = (int)((float)hit_steps + cl_length(to_f3(hit_voxel) - L));
         ray_dir = cl_normalize(L - hit_point);
         if (ray_dir.x == 0.0f || ray_dir.y == 0.0f || ray_dir.z == 0.0f) return false;
+        distance_traveled = hit_steps + 1;                                /* as after the first redirect (kernel:714) */
         if (COUNT) k.shadow_rays++;
         voxel = hit_empty;
         voxel_step = {cl_sign_step(ray_dir.x), cl_sign_step(ray_dir.y), cl_sign_step(ray_dir.z)};

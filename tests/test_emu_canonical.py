@@ -260,3 +260,84 @@ def test_all_walks_over_collapsed_trees(pkg, oracle, kind):
             assert np.array_equal(frames[(True, use_svo)], frames[(False, use_svo)]), use_svo
         seen = max(seen, float(((a_aux["flags"] & 3) != 0).mean()))
     assert seen > 0.3                                     # not mostly sky: lit or reflected hits
+
+
+def _fuzz_case(pkg, seed, it, kind):
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "fuzz"))
+    import fuzz_closed_form as F
+
+    F.KINDS = [kind]
+    return F, F.make_case(seed, it)
+
+
+def test_fuzz_finding_skipped_next_light_reports_the_hit_iteration(pkg, oracle):
+    """tests/fuzz/fuzz_closed_form.py, scene (202, 902): a pixel whose SECOND light lies exactly in a coordinate plane of the
+    hit point is skipped (kernel:671 applied to the multi-light extension).  The device core reports the step counter of the
+    hit's iteration for it, as both do for a first light; the oracle used to report one more.  All walks == oracle on every
+    pixel, including that counter."""
+    from test_emu_parity import assert_walk_matches
+
+    F, (kind, scene, nl, collapse) = _fuzz_case(pkg, 202, 902, "tunnel")
+    assert nl == 2
+    table = oracle.make_ray_table(scene.width, scene.height)
+    desc, root = pkg.octree_generate(scene.volume)
+    ref_rgba, ref_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl)
+    b_rgba, b_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+    skipped = (ref_aux["status"] == oracle.ST_SKIP_REDIRECT) & ((ref_aux["flags"] & oracle.FL_LIT) != 0)
+    assert skipped.any(), "the scene holds a pixel skipped at a light"
+    bias = oracle_bias(oracle, scene, desc, root)
+    emu_lib.set_collapse(collapse)
+    try:
+        for use_svo in (0, 1, 2):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_walk_matches(ref_rgba, ref_aux, rgba, aux, use_svo == 2, f"svo={use_svo}")
+            assert np.array_equal(aux["steps_total"][skipped], ref_aux["steps_total"][skipped])
+        for use_svo in (3, 4):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_equals_oracle_b(b_rgba, b_aux, rgba, aux, f"svo={use_svo}")
+    finally:
+        emu_lib.set_collapse(True)
+
+
+def test_fuzz_finding_unobserved_ties_inside_a_cell(pkg, oracle):
+    """The closed-form walk sees a multi-axis step only where it looks: at the step that leaves an empty cell and inside
+    bricks.  An exact tie strictly inside a cell is walked as two steps, so distance_traveled is one higher than Oracle-B's
+    (which steps voxel by voxel).  Visible on tie pixels only: fog (RGBA +-1), and -- scene (302, 250) -- a shadow ray that ends
+    by max_distance (kernel:357) one step short of the voxel Oracle-B's still reaches (alpha of a shadowed vs a lit pixel);
+    scene (301, 103): the two kinds of top grid hand out different cells, so their frames differ by 1 on such a pixel.
+    First hit and face are the same in all of them; on that pixel of (302, 250) the walk agrees with the REFERENCE walk (oracle A)."""
+    F, (kind, scene, nl, collapse) = _fuzz_case(pkg, 302, 250, "sparse")
+    table = oracle.make_ray_table(scene.width, scene.height)
+    desc, root = pkg.octree_generate(scene.volume)
+    a_rgba, a_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl)
+    b_rgba, b_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+    bias = oracle_bias(oracle, scene, desc, root)
+    emu_lib.set_collapse(collapse)
+    try:
+        for use_svo in (3, 4):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            problems, ties, far = F.classify(b_rgba, b_aux, rgba, aux)
+            assert not problems, problems
+            assert far == 1
+            y, x = np.argwhere(np.abs(rgba.astype(int) - b_rgba.astype(int)).max(-1) > 1)[0]
+            assert (b_aux["flags"][y, x] & 4) and aux["steps_total"][y, x] == b_aux["steps_total"][y, x] + 1
+            assert np.array_equal(rgba[y, x], a_rgba[y, x]) and aux["steps_total"][y, x] == a_aux["steps_total"][y, x]
+        F2, (kind, scene, nl, collapse) = _fuzz_case(pkg, 301, 103, "sparse")
+        table = oracle.make_ray_table(scene.width, scene.height)
+        desc, root = pkg.octree_generate(scene.volume)
+        b_rgba, b_aux, _ = oracle.raycast(scene, table, octree=(desc, root), shadow_lights=nl, canonical_t=True)
+        bias = oracle_bias(oracle, scene, desc, root)
+        emu_lib.set_collapse(collapse)
+        frames = []
+        for use_svo in (3, 4):
+            rgba, aux = emu_lib.raycast(scene, table, bias=bias, use_svo=use_svo, shadow_lights=nl)
+            assert_equals_oracle_b(b_rgba, b_aux, rgba, aux, f"svo={use_svo}")
+            frames.append(rgba)
+        d = np.abs(frames[0].astype(int) - frames[1].astype(int)).max(-1)
+        tie = (b_aux["flags"] & 4) != 0
+        assert (d > 0).sum() == 1 and d.max() == 1 and not (d[~tie] > 0).any()
+    finally:
+        emu_lib.set_collapse(True)
