@@ -11,7 +11,7 @@
  *
  * PARITY PINNED AGAINST THE REFERENCE'S OWN CODE, EXECUTED.  The reference ships no tests, golden images or
  * known-answer vectors for this path and no OpenCL runtime, SFML or GL exists in the image,
- * but its sources can be compiled for the CPU from where they lie (`make -C oracle ref` -> oracle/_ref/*.so):
+ * but its sources can be compiled for the CPU from where they lie (`make -C oracle ref` -> oracle/_ref/ (the .so files)):
  *   - kernels/ray_caster_kernel.cl by g++ through ref_shim/cl_shim.h (OpenCL C vector types, operators and built-ins
  *     in C++; the only edit, by sed on the fly, is the vector-literal syntax `(typeN)(` -> `typeN(`), verbatim, with
  *     kernel:326's max_distance read from a variable, and with the three 8-entry private stacks widened to 32;

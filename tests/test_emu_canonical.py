@@ -269,7 +269,7 @@ def _fuzz_case(pkg, seed, it, kind):
     sys.path.insert(0, str(Path(__file__).resolve().parent / "fuzz"))
     import fuzz_closed_form as F
 
-    F.KINDS = [kind]
+    F.KINDS = [kind] if kind else "random,random,sparse,terrain,tunnel".split(",")      # (the campaign's default mix)
     return F, F.make_case(seed, it)
 
 
@@ -339,5 +339,36 @@ def test_fuzz_finding_unobserved_ties_inside_a_cell(pkg, oracle):
         d = np.abs(frames[0].astype(int) - frames[1].astype(int)).max(-1)
         tie = (b_aux["flags"] & 4) != 0
         assert (d > 0).sum() == 1 and d.max() == 1 and not (d[~tie] > 0).any()
+    finally:
+        emu_lib.set_collapse(True)
+
+
+def test_fuzz_finding_camera_on_a_voxel_corner(pkg, oracle):
+    """tests/fuzz/fuzz_closed_form.py, scene (1002, 4830): camera at integer coordinates, max_distance 5.  intersection_t
+    starts at 0 on all three axes, so the first step of every primary ray moves along all of them at once and counts ONCE
+    (kernel:558, 714).  Inside the camera's empty cell the closed-form walk would not see that tie, count three steps and
+    end every ray (max_distance, kernel:357) before the voxel the reference still reaches: the first cell of a primary ray
+    is therefore the start voxel alone when the camera sits on a voxel edge (vr_canon.h: on_edge).  Every pixel and every
+    counter equals Oracle-B's -- and the same for a camera on an edge (two integer coordinates) of a terrain map."""
+    F, (kind, scene, nl, collapse) = _fuzz_case(pkg, 1002, 4830, None)
+    assert np.array_equal(scene.cam_pos, np.floor(scene.cam_pos)) and scene.max_distance == 5
+    S = pkg.scene
+    n = 64
+    pos, direction = S.make_camera(n, S.heightfield(n), 2)
+    pos = np.array([np.floor(pos[0]), np.floor(pos[1]), pos[2]], np.float32)
+    edge = S.Scene(n, S.terrain_map(n, "shell"), 160, 96, pos, direction, S.make_lights(n, 1), max_distance=20)
+    emu_lib.set_collapse(collapse)
+    try:
+        for sc, lights in ((scene, nl), (edge, 1)):
+            table = oracle.make_ray_table(sc.width, sc.height)
+            desc, root = pkg.octree_generate(sc.volume)
+            b_rgba, b_aux, _ = oracle.raycast(sc, table, octree=(desc, root), shadow_lights=lights, canonical_t=True)
+            assert ((b_aux["flags"] & 4) != 0).mean() > 0.9, "(nearly) every ray starts with a multi-axis step"
+            bias = oracle_bias(oracle, sc, desc, root)
+            for use_svo in (3, 4):
+                rgba, aux = emu_lib.raycast(sc, table, bias=bias, use_svo=use_svo, shadow_lights=lights)
+                assert np.array_equal(rgba, b_rgba), f"svo={use_svo}"
+                for f in ("hit", "face", "status", "hit_type", "steps_first", "steps_total"):
+                    assert np.array_equal(aux[f], b_aux[f]), (use_svo, f)
     finally:
         emu_lib.set_collapse(True)

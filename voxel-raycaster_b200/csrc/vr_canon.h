@@ -227,6 +227,32 @@ VR_HD int vr_canon_walk(vr_cray<Stack> &q, const vr_ccell &c, bool biased, float
     return nx + ny + nz;
 }
 
+/* The first step of a ray is made at m0 = min(t0) by every axis whose t0 equals it: c0 axes, ONE step (kernel:558, 714).
+ * vr_canon_walk counts steps per axis and sees a multi-axis step only where it looks -- at the step that leaves the cell,
+ * and there only the axes that leave it.  For generic rays a tie at the very first step is as rare as any other; with the
+ * camera on a voxel edge EVERY primary ray starts with one, and counting it per axis would end rays up to two steps early
+ * (kernel:357, 667).  Returns what has to be taken off dbase for the first walk of the segment over cell `c`: the c0 - 1
+ * surplus steps, less what the walk will take off itself when the first step is the step that leaves the cell (m0 == T) and
+ * `together` >= 2 of the axes leave with it.  A brick walk observes every step: nothing to correct. */
+template <class Stack>
+VR_HD int vr_canon_first_step_tie(const vr_cray<Stack> &q, vr_ccell c, bool bricks_walked) {
+    const RayState &r = q.r;
+    const float m0 = vr_min3(q.t0x, q.t0y, q.t0z);
+    const int c0 = (q.t0x == m0 ? 1 : 0) + (q.t0y == m0 ? 1 : 0) + (q.t0z == m0 ? 1 : 0);
+    if (c0 < 2) return 0;
+    if (c.brick) {
+        if (bricks_walked) return 0;
+        c = {0, 0, false};                     /* as in the cell loop: a brick is walked voxel by voxel when the ray is about to end */
+    }
+    const int ox = (q.px | c.m) + c.ext, oy = (q.py | c.m) + c.ext, oz = (q.pz | c.m) + c.ext;
+    const float Tx = VR_FMA(VR_SUB(vr_bits2f(ox - q.bx), VR_MAGIC_F), r.delta.x, q.t0x);
+    const float Ty = VR_FMA(VR_SUB(vr_bits2f(oy - q.by), VR_MAGIC_F), r.delta.y, q.t0y);
+    const float Tz = VR_FMA(VR_SUB(vr_bits2f(oz - q.bz), VR_MAGIC_F), r.delta.z, q.t0z);
+    const float T = vr_min3(Tx, Ty, Tz);
+    const int together = (Tx == T ? 1 : 0) + (Ty == T ? 1 : 0) + (Tz == T ? 1 : 0);
+    return c0 - ((m0 < T || together < 2) ? 1 : together);
+}
+
 /* Leaf brick (4^3 voxels, occupancy = mask): the step of kernel:558-560 with closed-form times, followed by a bit test
  * of the voxel entered.  Stops when a step leaves the brick (returns false) or lands on a set voxel (returns true,
  * `bit` = its slot).  The caller guarantees that max_distance cannot be reached inside (a brick holds <= 10 steps).
@@ -345,6 +371,9 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
     }
     const int N = P.dim[0];
     const bool biased = P.bias[0] != 0.0f || P.bias[1] != 0.0f || P.bias[2] != 0.0f;      /* frame-uniform */
+    /* frame-uniform too: a camera on a voxel edge or corner (two or three integer coordinates).  intersection_t then starts
+     * at the same value on those axes, and the first step of EVERY primary ray moves along them at once (kernel:558) */
+    const bool on_edge = P.cam_on_edge != 0;
     q.first_hit_done = false;
     q.s = 0;
     int status = VR_ST_MAXDIST;
@@ -365,6 +394,10 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
         if (!(r.bounce < P.max_bounces)) { status = VR_ST_BOUNCES; break; }            /* kernel:357; bounce_count only changes at a hit */
         if (r.dist < r.max_distance) {                                     /* kernel:357 */
             int dbase = r.dist - (q.px + q.py + q.pz);                     /* distance_traveled = dbase + px + py + pz */
+            if (on_edge) {
+                VR_RARE();
+                if (!r.shadow && r.bounce == 0) dbase -= vr_canon_first_step_tie(q, c, r.max_distance - r.dist > 12);
+            }
             for (;;) {                     /* one turn per empty cell */
                 int sum, bit = 0;
                 bool known = false;        /* the brick walk already knows that the voxel entered is set */

@@ -8,6 +8,7 @@
 #ifndef VR_TYPES_H
 #define VR_TYPES_H
 
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -150,6 +151,16 @@ typedef struct vr_frame_params {
     int32_t grid_shift, grid_bits, grid_dim;       /* grid_dim = G */
     int32_t grid_directed;                         /* 1: eight tables, one per direction octant of the ray, table o at
                                                     * o << (3 * grid_bits) (vr_octree.cpp: vr_native_grid_directed) */
+    int32_t cam_on_edge;                           /* host evaluated (vr_cam_on_edge): the camera sits on a voxel edge or corner */
 } vr_frame_params;
+
+/* A camera with two or three integer coordinates: intersection_t starts at the same value on those axes (kernel:317-323
+ * with a zero fraction), so the first step of every primary ray moves along them at once (kernel:558).  vr_canon.h counts
+ * that step once (vr_canon_first_step_tie). */
+static inline int32_t vr_cam_on_edge(const float *cam_pos) {
+    int n = 0;
+    for (int i = 0; i < 3; i++) n += cam_pos[i] == floorf(cam_pos[i]) ? 1 : 0;
+    return n >= 2 ? 1 : 0;
+}
 
 #endif
