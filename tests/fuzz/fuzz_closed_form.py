@@ -133,7 +133,7 @@ def classify(ref_rgba, ref_aux, rgba, aux, lights=1):
 
 
 def main():
-    bad = known = ties = far = pixels = grids = scenes = 0
+    bad = edge_frames = voxelwise_frames = ties = far = pixels = grids = scenes = 0
     for it in range(first, first + count):
         case = make_case(seed, it)
         if case is None:
@@ -145,7 +145,8 @@ def main():
         ref_rgba, ref_aux, _ = O.raycast(scene, table, octree=(desc, root), shadow_lights=nl, canonical_t=True)
         bias = oracle_bias(O, scene, desc, root)
         on_edge = int((scene.cam_pos == np.floor(scene.cam_pos)).sum()) >= 2
-        edge_in_collapsed_cell = on_edge and any(int(b) != 0 for b in bias)
+        edge_frames += on_edge                # camera on a voxel edge / corner: vr_cam_on_edge (csrc/vr_types.h)
+        voxelwise_frames += on_edge and any(int(b) != 0 for b in bias)
         emu_lib.set_collapse(collapse)
         frames = []
         for use_svo in (3, 4):
@@ -157,13 +158,7 @@ def main():
             pixels += rgba.shape[0] * rgba.shape[1]
             if f:
                 print("tie pixel(s) beyond +-1, explained by the step count:", seed, it, kind, scene.n, use_svo, f, flush=True)
-            if problems and edge_in_collapsed_cell:
-                # known limitation, reported apart: a camera on a voxel edge INSIDE a collapsed empty octree cell.  The start
-                # bias (kernel:353) shifts the axes apart, so the tie of the integer axes is not the ray's first step and
-                # stays a tie strictly inside a cell (vr_canon_first_step_tie handles the first step only)
-                known += 1
-                print("known (camera on an edge of a collapsed empty cell):", seed, it, kind, scene.n, use_svo, "; ".join(problems)[:160], flush=True)
-            elif problems:
+            if problems:
                 bad += 1
                 print("MISMATCH", seed, it, kind, scene.n, use_svo, collapse, nl, scene.max_distance, "; ".join(problems)[:300], flush=True)
         if LITERAL:
@@ -187,7 +182,7 @@ def main():
         if it % 100 == 0:
             print(seed, it, kind, scene.n, "max steps", int(ref_aux["steps_total"].max()), "tie pixels so far", ties, "of", pixels, flush=True)
     emu_lib.set_collapse(True)
-    print(f"done seed {seed} scenes {scenes} (x 2 grids) unexplained {bad} known-limitation frames {known} pixels {pixels} tie pixels {ties} "
+    print(f"done seed {seed} scenes {scenes} (x 2 grids) unexplained {bad} edge-camera scenes {edge_frames} (voxelwise {voxelwise_frames}) pixels {pixels} tie pixels {ties} "
           f"tie pixels beyond +-1 (step count) {far} pixels on which the two grids differ (tie pixels) {grids}")
     return bad
 

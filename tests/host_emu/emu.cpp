@@ -35,7 +35,7 @@ extern "C" int emu_raycast(int width, int height, const float *ray_table, const 
     P.map = map;
     P.dim[0] = P.dim[1] = P.dim[2] = n;
     for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = (float)bias[i]; }
-    P.cam_on_edge = vr_cam_on_edge(P.cam_pos);
+    P.cam_on_edge = vr_cam_on_edge(P.cam_pos, P.bias);
     P.light_count = shadow_lights < 1 ? 1 : (shadow_lights > VR_MAX_LIGHTS ? VR_MAX_LIGHTS : shadow_lights);
     for (int l = 0; l < P.light_count; l++) {
         for (int i = 0; i < 4; i++) P.light_rgbi[l][i] = lights[10 * l + i];

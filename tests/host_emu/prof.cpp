@@ -62,7 +62,7 @@ extern "C" int emu_profile(int width, int height, const float *ray_table, const 
     P.ray_table = ray_table;
     P.dim[0] = P.dim[1] = P.dim[2] = n;
     for (int i = 0; i < 3; i++) { P.cam_pos[i] = cam_pos[i]; P.bias[i] = 0.0f; P.light_pos[0][i] = lights[4 + i]; }
-    P.cam_on_edge = vr_cam_on_edge(P.cam_pos);
+    P.cam_on_edge = vr_cam_on_edge(P.cam_pos, P.bias);
     for (int i = 0; i < 4; i++) P.light_rgbi[0][i] = lights[i];
     P.light_count = 1;
     P.trig[0] = sinf(cam_dir[0]); P.trig[1] = cosf(cam_dir[0]); P.trig[2] = sinf(cam_dir[1]); P.trig[3] = cosf(cam_dir[1]);

@@ -357,14 +357,19 @@ def test_fuzz_finding_camera_on_a_voxel_corner(pkg, oracle):
     pos, direction = S.make_camera(n, S.heightfield(n), 2)
     pos = np.array([np.floor(pos[0]), np.floor(pos[1]), pos[2]], np.float32)
     edge = S.Scene(n, S.terrain_map(n, "shell"), 160, 96, pos, direction, S.make_lights(n, 1), max_distance=20)
+    # (5002, 2093): a corner camera inside a collapsed empty octree cell.  The start bias (kernel:353) differs between the
+    # axes, so the tie of the integer axes is not the first step: such frames are traced voxel by voxel (vr_cam_on_edge = 2)
+    _, (_, biased, nl_b, _) = _fuzz_case(pkg, 5002, 2093, None)
+    assert np.array_equal(biased.cam_pos, np.floor(biased.cam_pos))
     emu_lib.set_collapse(collapse)
     try:
-        for sc, lights in ((scene, nl), (edge, 1)):
+        for sc, lights in ((scene, nl), (edge, 1), (biased, nl_b)):
             table = oracle.make_ray_table(sc.width, sc.height)
             desc, root = pkg.octree_generate(sc.volume)
             b_rgba, b_aux, _ = oracle.raycast(sc, table, octree=(desc, root), shadow_lights=lights, canonical_t=True)
             assert ((b_aux["flags"] & 4) != 0).mean() > 0.9, "(nearly) every ray starts with a multi-axis step"
             bias = oracle_bias(oracle, sc, desc, root)
+            assert (sc is biased) == any(b != 0 for b in bias)
             for use_svo in (3, 4):
                 rgba, aux = emu_lib.raycast(sc, table, bias=bias, use_svo=use_svo, shadow_lights=lights)
                 assert np.array_equal(rgba, b_rgba), f"svo={use_svo}"

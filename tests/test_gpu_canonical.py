@@ -369,7 +369,10 @@ def test_camera_on_a_voxel_corner_or_edge(pkg, oracle):
     pos, direction = S.make_camera(n, S.heightfield(n), 2)
     pos = np.array([np.floor(pos[0]), np.floor(pos[1]), pos[2]], np.float32)
     edge = S.Scene(n, S.terrain_map(n, "shell"), 160, 96, pos, direction, S.make_lights(n, 1), max_distance=20)
-    for scene, lights in ((corner, nl), (edge, 1)):
+    # (5002, 2093): a corner camera inside a collapsed empty octree cell (start bias, kernel:353): traced voxel by voxel
+    _, biased, nl_b, _ = F.make_case(5002, 2093)
+    assert np.array_equal(biased.cam_pos, np.floor(biased.cam_pos))
+    for scene, lights in ((corner, nl), (edge, 1), (biased, nl_b)):
         desc, root = pkg.octree_generate(scene.volume)
         b_rgba, b_aux, _ = oracle.raycast(scene, octree=(desc, root), shadow_lights=lights, canonical_t=True)
         c = pkg.CUDACaster()

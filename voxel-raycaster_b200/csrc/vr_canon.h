@@ -374,13 +374,14 @@ VR_HD bool vr_trace_svo_canon(const vr_frame_params &P, int x, int y, uint32_t *
     /* frame-uniform too: a camera on a voxel edge or corner (two or three integer coordinates).  intersection_t then starts
      * at the same value on those axes, and the first step of EVERY primary ray moves along them at once (kernel:558) */
     const bool on_edge = P.cam_on_edge != 0;
+    const bool voxelwise = P.cam_on_edge == 2;      /* ... inside a collapsed empty octree cell: see vr_cam_on_edge (vr_types.h) */
     q.first_hit_done = false;
     q.s = 0;
     int status = VR_ST_MAXDIST;
     bool slow = false;
     int xr = -1;                           /* changed voxel bits since the last lookup; -1 = everything */
     for (;;) {                             /* one turn per ray segment: primary ray, shadow ray(s), reflections */
-        if (!vr_ray_finite(r)) { slow = true; break; }
+        if (!vr_ray_finite(r) || voxelwise) { slow = true; break; }
         vr_canon_enter(P, q);
         /* the cell around the voxel the segment starts in; that voxel itself is never tested (the reference steps before
          * it loads, kernel:555-570) and may even lie outside the map */

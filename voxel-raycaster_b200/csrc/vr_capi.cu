@@ -238,7 +238,6 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
     if (c->d_map) { P.dim[0] = c->dim[0]; P.dim[1] = c->dim[1]; P.dim[2] = c->dim[2]; }
     else P.dim[0] = P.dim[1] = P.dim[2] = c->tree_dim;
     for (int i = 0; i < 3; i++) P.cam_pos[i] = c->cam_pos[i];
-    P.cam_on_edge = vr_cam_on_edge(P.cam_pos);
     P.trig[0] = sinf(c->cam_dir[0]);
     P.trig[1] = cosf(c->cam_dir[0]);
     P.trig[2] = sinf(c->cam_dir[1]);
@@ -256,6 +255,7 @@ int build_params(vr_ctx *c, vr_frame_params &P, uint8_t *image, int *use_svo) {
         for (int i = 0; i < 3; i++) c->bias[i] = ((sub[i] - pos[i]) * res) / 2;
     }
     for (int i = 0; i < 3; i++) P.bias[i] = (float)c->bias[i];
+    P.cam_on_edge = vr_cam_on_edge(P.cam_pos, P.bias);
 
     /* the reference binds light_count but reads slot 0 only (host:193, kernel:660-670): LIGHT_COUNT defaults to 1 */
     P.light_count = 1;

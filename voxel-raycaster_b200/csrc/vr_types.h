@@ -155,12 +155,16 @@ typedef struct vr_frame_params {
 } vr_frame_params;
 
 /* A camera with two or three integer coordinates: intersection_t starts at the same value on those axes (kernel:317-323
- * with a zero fraction), so the first step of every primary ray moves along them at once (kernel:558).  vr_canon.h counts
- * that step once (vr_canon_first_step_tie). */
-static inline int32_t vr_cam_on_edge(const float *cam_pos) {
+ * with a zero fraction), so every primary ray makes a step along them at once (kernel:558), which counts once (kernel:714).
+ * Returns 0: no such camera; 1: without a start bias -- the tie is the ray's first step, vr_canon.h corrects the step
+ * count for it (vr_canon_first_step_tie); 2: with a get_oct_vox start bias (kernel:353) -- the bias shifts the axes apart,
+ * the tie falls anywhere along the ray, and the closed-form walk hands such frames to its voxel-by-voxel form
+ * (vr_canon_slow: every step observed). */
+static inline int32_t vr_cam_on_edge(const float *cam_pos, const float *bias) {
     int n = 0;
     for (int i = 0; i < 3; i++) n += cam_pos[i] == floorf(cam_pos[i]) ? 1 : 0;
-    return n >= 2 ? 1 : 0;
+    if (n < 2) return 0;
+    return (bias[0] != 0.0f || bias[1] != 0.0f || bias[2] != 0.0f) ? 2 : 1;
 }
 
 #endif
