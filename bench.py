@@ -3,9 +3,12 @@
 
 Metric (BASELINE.json): Mrays/s and ms/frame, 1024^3 SVO @ 3840x2160 + shadows, at 1/2/4/8 B200.
 A "step" is one frame: every pixel casts its primary ray and, on a hit, the shadow ray towards light 0,
-through the 64-tree kernel.  With N > 1 (torchrun, one rank per GPU, NCCL) the frame is split into
-interleaved 8-row bands ("screen-tile split"), the octree is broadcast once from rank 0, and the band
-slabs are gathered to rank 0 every frame.
+through the 64-tree kernel.  With N > 1 (torchrun, one rank per GPU) the frame loop is the C library's
+multi-GPU scheduler (vr_mgpu_*, run_mgpu below): the octree is broadcast once from rank 0 with NCCL, the
+frame is split into the kernel's 32x4-pixel tiles, tile (tx, ty) on rank (tx + ty) mod N, and every rank's
+kernel stores its pixels in place into the frame on the root GPU over NVLink; torch.distributed supplies
+the barrier around the timed region and the MAX over ranks.  (--gather direct|p2p|nccl: the round-1 Python
+pipelines, kept for comparison.)
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
